@@ -1,0 +1,148 @@
+/* include/secphase_b200.h -- C ABI of libsecphase_b200.so
+ *
+ * B200 (sm_100a) implementation of Secphase's marker-mode scoring of read groups.
+ *
+ * What it replaces in the reference (paths relative to /root/reference/):
+ *   - the per-read-group job  runOneThread(), marker branch   programs/src/secphase.c:156-219
+ *     handed to the thread pool by  tpool_add_work(tm, runOneThread, arg_cp)   secphase.c:303
+ *     with the parameter bag  work_arg_t   programs/submodules/tpool/tpool.h:26-55;
+ *   - everything that job calls: ptCigarIt_* (cigar_it.c), ptAlignment_init_coordinates
+ *     (ptAlignment.c:42-95), the ptMarker_* pipeline (ptMarker.c), htslib's probaln_glocal()
+ *     (call site ptMarker.c:754-757) and get_best_record_index (ptAlignment.c:137-177).
+ * The reference has no FFI/plugin API; this ABI is the batch form of that one job type: many
+ * read groups per call instead of one job per group, plain pointers and sizes only.
+ *
+ * Threading: one sp_ctx per GPU, driven by one host thread.  Results come back in submission
+ * order so that the caller can emit out.log deterministically; the tie-break random draws of
+ * get_best_record_index (ptAlignment.c:156-171: glibc rand(), never seeded) are replayed on the
+ * host in that order (sp_wait), bit-compatible with glibc's TYPE_3 generator seeded with 1.
+ *
+ * Error behaviour: every int function returns 0 on success or a negative SP_E* code; nothing
+ * calls exit().  sp_last_error() returns a thread-local message.  There is NO CPU fallback: all
+ * entry points that compute fail with SP_ENODEV when no CUDA device is usable.
+ */
+#ifndef SECPHASE_B200_H
+#define SECPHASE_B200_H
+#include <stdint.h>
+#include "sp_flat_batch.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_OK 0
+#define SP_EINVAL (-1)   /* bad argument / malformed batch */
+#define SP_ENODEV (-2)   /* no usable CUDA device */
+#define SP_ECUDA (-3)    /* CUDA runtime error (message in sp_last_error) */
+#define SP_ENOMEM (-4)
+#define SP_ESTATE (-5)   /* call sequence error (e.g. wait on an idle slot) */
+#define SP_EUNSUPPORTED (-6) /* CIGAR N/P ops (undefined in the reference, cigar_it.c:225-291) */
+#define SP_ECAPACITY (-7) /* an internal per-group bound was exceeded even after the retry */
+
+#define SP_MAX_ALN_PER_GROUP 10 /* secphase.c:286 */
+#define SP_N_SLOTS 3            /* batches in flight per context */
+
+/* Scalars of work_arg_t (tpool.h:26-55), same names and meaning. */
+typedef struct sp_params {
+    int32_t baq_flag;        /* -q */
+    int32_t consensus;       /* -c */
+    int32_t indel_threshold; /* -t */
+    int32_t min_q;           /* -m */
+    int32_t min_score;       /* -n */
+    int32_t set_q;           /* -s */
+    int32_t flank_margin;    /* -F (default 500) */
+    double prim_margin_score;  /* -p */
+    double prim_margin_random; /* -r */
+    double conf_d;             /* -d */
+    double conf_e;             /* -e */
+    double conf_b;             /* -b */
+} sp_params;
+
+/* defaults of secphase.c:420-449 */
+void sp_params_default(sp_params *p);
+/* presets of secphase.c:477-504; name is "hifi" or "ont"; overwrites the preset fields only */
+int sp_params_preset(sp_params *p, const char *name);
+
+typedef struct sp_ctx sp_ctx;
+
+sp_ctx *sp_create(const sp_params *p, int cuda_device); /* NULL on error */
+void sp_destroy(sp_ctx *ctx);
+const char *sp_last_error(void);
+const char *sp_version(void);
+
+/* Reference assembly, once per context; copied to HBM as 1 byte/base codes A,C,G,T -> 0..3,
+ * everything else -> 4 (seq_nt16_int[seq_nt16_table[c]], ptMarker.c:744).  Replaces the
+ * per-job fai_load + per-block fai_fetch (secphase.c:101, ptMarker.c:736-744).
+ * Contig order must be the BAM header's tid order. */
+int sp_set_reference_ascii(sp_ctx *ctx, int32_t n_contigs, const char *const *seqs, const int64_t *lens);
+int sp_set_reference_codes(sp_ctx *ctx, int32_t n_contigs, const uint8_t *codes, const int64_t *contig_off);
+
+#define SP_MARKER_W 6 /* alignment_idx, read_pos_f, base_idx, base_q, is_match, ref_pos (ptMarker.h:34-41) */
+#define SP_BLOCK_W 6  /* rfs, rfe, sqs, sqe, rds_f, rde_f (ptBlock.h:23-38) */
+#define SP_GROUP_W 10 /* best_idx, prim_idx, n_init, n_after_allmm, n_filled, n_after_ins, margin_eff,
+                         n_consensus_blocks, n_final, scored */
+#define SP_HMM_W 8    /* global alignment index, l_ref, l_query, par_bw, block index, first row slot,
+                         n_rows, reserved */
+
+typedef struct sp_result {
+    int32_t n_groups;
+    int32_t n_alns;
+    const int32_t *group;      /* [n_groups][SP_GROUP_W] */
+    const double *score;       /* [n_alns]  alignment->score after calc_alignment_score */
+    const int32_t *extent;     /* [n_alns][4] rfs, rfe, rds_f, rde_f (ptAlignment.h:26-36) */
+    const int64_t *marker_off; /* [n_groups+1] */
+    const int32_t *marker;     /* final markers, [marker_off[n_groups]][SP_MARKER_W] */
+    /* work statistics of this batch */
+    int64_t hmm_instances;
+    int64_t hmm_cells;         /* band cells, SURVEY.md 8(d) definition */
+    int64_t h2d_bytes, d2h_bytes;
+    float ms_total;            /* CUDA-event time H2D start -> D2H end on the slot's stream */
+    float ms_hmm;              /* CUDA-event time of the BAQ-HMM kernels only */
+    float ms_stage[8];         /* h2d, walk, markers, blocks, emit+sort, hmm, score, d2h */
+    int32_t gpu_launches;      /* kernels launched for this batch */
+} sp_result;
+
+/* Asynchronous: packs the groups into the slot's pinned staging buffer, then enqueues
+ * H2D copy -> kernels -> D2H copy on the slot's stream.  slot in [0, SP_N_SLOTS). */
+int sp_submit(sp_ctx *ctx, const sp_flat_batch *batch, int slot);
+/* Blocks until the slot's batch is complete, replays the tie-break RNG for its groups and fills
+ * *out; the pointers stay valid until the next sp_submit on the same slot. */
+int sp_wait(sp_ctx *ctx, int slot, sp_result *out);
+
+/* --- device-resident variant used to time the kernels alone (bench `value`): the batch is
+ * uploaded once with sp_upload, sp_run_resident enqueues kernels only. */
+int sp_upload(sp_ctx *ctx, const sp_flat_batch *batch, int slot);
+int sp_run_resident(sp_ctx *ctx, int slot);
+
+/* --- intermediate tables of the last completed batch of a slot (parity tests). `what`:
+ *   0 markers before BAQ   [n][SP_MARKER_W], off per group
+ *   1 markers after BAQ    [n][SP_MARKER_W], off per group
+ *   2 consensus blocks     [n][SP_BLOCK_W],  off per alignment
+ *   3 HMM instances        [n][SP_HMM_W],    off = NULL
+ *   4 HMM marker rows      [n][4] = instance, row t, state, q ; off = NULL
+ * Returns the number of rows, or a negative error.  Pointers are host memory owned by ctx. */
+int64_t sp_debug_table(sp_ctx *ctx, int slot, int what, const int32_t **rows, const int64_t **off);
+
+/* --- the HMM alone, batch form of probaln_glocal(ref,l_ref,query,l_query,iqual,&conf,state,q)
+ * (call site ptMarker.c:755-757) for uniform iqual == set_q.  All pointers are HOST memory.
+ * For instance j: ref codes ref_pool[ref_off[j] .. +l_ref[j]), query codes likewise, band
+ * parameter conf.bw = par_bw[j].  Only the query rows listed in rows[row_off[j]..row_off[j+1])
+ * (0-based t, ascending) are evaluated by the MAP step; state_out/q_out/pmax_out are indexed
+ * like rows.  pmax_out (normalised max posterior) may be NULL. */
+int sp_hmm_batch(sp_ctx *ctx, int32_t n, const uint8_t *ref_pool, const int64_t *ref_off, const int32_t *l_ref,
+                 const uint8_t *query_pool, const int64_t *query_off, const int32_t *l_query,
+                 const int32_t *par_bw, const int64_t *row_off, const int32_t *rows, int32_t *state_out,
+                 uint8_t *q_out, double *pmax_out, float *ms_kernel);
+
+/* FP64 pipe micro-benchmark for the roofline denominator: register-resident
+ * chains of DFMA (mode 0) or alternating DADD/DMUL (mode 1).  Returns instructions/second
+ * (per thread-instruction, i.e. lane-ops/s) in *ops_per_s. */
+int sp_fp64_peak(sp_ctx *ctx, int mode, double *ops_per_s, float *ms);
+
+/* Emulation of glibc rand() (TYPE_3, seed 1) used for the tie-breaks; exposed for tests. */
+void sp_rng_seed(sp_ctx *ctx, unsigned seed);
+int sp_rng_next(sp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

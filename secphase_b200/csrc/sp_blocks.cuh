@@ -1,0 +1,399 @@
+// sp_blocks.cuh -- stage K3: consensus blocks of one read group and the HMM work list.
+//
+// Restates, for one read group,
+//   needs_to_find_blocks      (ptMarker.c:649-667)
+//   find_flanking_blocks      (ptMarker.c:446-484)   via set_flanking_blocks 487-492
+//   intersect_by_rd_f         (ptMarker.c:398-435)
+//   correct_conf_blocks       (ptMarker.c:495-647)   intersection + projection to seq/ref coords
+//   the x0.8 margin loop      (secphase.c:162-169)
+// and the control flow of
+//   calc_local_baq            (ptMarker.c:670-809)   which blocks run probaln_glocal, which
+//                                                    markers are zeroed / keep raw quality
+// The projection walks the stored op table (SpOp) instead of re-tokenising the cs tag.
+#pragma once
+#include "sp_common.h"
+#include "sp_markers.cuh"
+#include "sp_walk.cuh"
+
+struct SpIv {  // interval in read-forward coordinates
+    int32_t s, e;
+};
+
+SP_HD void sp_sort_blocks_by_rds(SpBlock *b, int n) {
+    for (int i = 1; i < n; i++) {
+        SpBlock x = b[i];
+        int j = i - 1;
+        while (j >= 0 && b[j].rds_f > x.rds_f) {
+            b[j + 1] = b[j];
+            j--;
+        }
+        b[j + 1] = x;
+    }
+}
+SP_HD void sp_sort_blocks_by_sqs(SpBlock *b, int n) {
+    for (int i = 1; i < n; i++) {
+        SpBlock x = b[i];
+        int j = i - 1;
+        while (j >= 0 && b[j].sqs > x.sqs) {
+            b[j + 1] = b[j];
+            j--;
+        }
+        b[j + 1] = x;
+    }
+}
+
+// intersect_by_rd_f, ptMarker.c:398-435 (strict comparisons kept).  get2(j) reads list 2.
+template <class Get2>
+SP_HD int sp_intersect(const SpIv *l1, int n1, Get2 get2, int n2, SpIv *out, int cap, int *err) {
+    if (n1 == 0 || n2 == 0) return 0;
+    int j = 0, m = 0;
+    bool have2 = true;
+    SpIv b2 = get2(0);
+    for (int i = 0; i < n1; i++) {
+        const SpIv b1 = l1[i];
+        while (have2 && b2.e < b1.s) {
+            j++;
+            have2 = j < n2;
+            if (have2) b2 = get2(j);
+        }
+        while (have2 && b2.s < b1.e) {
+            if (m < cap) {
+                out[m].s = sp_max(b1.s, b2.s);
+                out[m].e = sp_min(b1.e, b2.e);
+            } else {
+                *err |= SP_GERR_BLOCK_CAP;
+            }
+            m++;
+            if (b2.e <= b1.e) {
+                j++;
+                have2 = j < n2;
+                if (have2) b2 = get2(j);
+            } else {
+                break;
+            }
+        }
+    }
+    return m <= cap ? m : cap;
+}
+
+struct SpBlockWork {
+    SpIv *cons_a, *cons_b, *flank;  // [cap] each
+    SpBlock *ab;                    // [n][cap] per-alignment block lists
+    int32_t *nb;                    // [n]
+    int cap;
+};
+
+// correct_conf_blocks (ptMarker.c:495-647) preceded by set_flanking_blocks (487-492).
+SP_HD int sp_correct_conf_blocks(const SpGroupAlnView &G, int P, const int32_t *gpos, int margin,
+                                 int indel_threshold, SpBlockWork &W, int *err) {
+    const int n = G.n, cap = W.cap;
+    // --- intersect the alignments' confident blocks (495-507)
+    sp_sort_blocks_by_rds(W.ab, W.nb[0]);
+    SpIv *cur = W.cons_a, *nxt = W.cons_b;
+    int nc = W.nb[0];
+    for (int k = 0; k < nc; k++) {
+        cur[k].s = W.ab[k].rds_f;
+        cur[k].e = W.ab[k].rde_f;
+    }
+    for (int i = 1; i < n; i++) {
+        SpBlock *bi = W.ab + (int64_t) i * cap;
+        sp_sort_blocks_by_rds(bi, W.nb[i]);
+        nc = sp_intersect(cur, nc, [&](int j) { SpIv v; v.s = bi[j].rds_f; v.e = bi[j].rde_f; return v; },
+                          W.nb[i], nxt, cap, err);
+        SpIv *t = cur; cur = nxt; nxt = t;
+    }
+    // --- intersect with every alignment's flanking blocks (508-514; find_flanking_blocks 446-484)
+    for (int i = 0; i < n; i++) {
+        const SpAlnInfo &ai = G.info[G.a0 + i];
+        int nf = 0;
+        if (P > 0) {
+            int start = sp_max(ai.rds_f, gpos[0] - margin);
+            int end = sp_min(ai.rde_f, gpos[0] + margin);
+            const int64_t total = (int64_t) P * n;  // the marker list holds n entries per position
+            for (int64_t idx = 1; idx < total; idx++) {
+                const int p = gpos[idx / n];
+                const int cs = sp_max(ai.rds_f, p - margin);
+                const int ce = sp_min(ai.rde_f, p + margin);
+                if (cs < end) {
+                    end = ce;
+                } else {
+                    if (nf < cap) { W.flank[nf].s = start; W.flank[nf].e = end; } else *err |= SP_GERR_BLOCK_CAP;
+                    nf++;
+                    start = cs;
+                    end = ce;
+                }
+            }
+            if (nf < cap) { W.flank[nf].s = start; W.flank[nf].e = end; } else *err |= SP_GERR_BLOCK_CAP;
+            nf++;
+            if (nf > cap) nf = cap;
+        }
+        const SpIv *fl = W.flank;
+        nc = sp_intersect(cur, nc, [&](int j) { return fl[j]; }, nf, nxt, cap, err);
+        SpIv *t = cur; cur = nxt; nxt = t;
+    }
+    if (nc == 0) {  // 515-523
+        for (int i = 0; i < n; i++) W.nb[i] = 0;
+        return 0;
+    }
+    // --- project the consensus blocks into each alignment's seq/ref coordinates (528-643)
+    for (int i = 0; i < n; i++) {
+        const int a = G.a0 + i;
+        const bool rev = (G.flag[a] & SP_FREVERSE) != 0;
+        const SpOp *ops = G.ops + G.ops_off[a];
+        const int n_ops = G.info[a].n_ops;
+        SpBlock *out = W.ab + (int64_t) i * cap;
+        int m = 0;
+        int j = rev ? nc - 1 : 0;
+        bool have = true, del_flag = false;
+        int b_s, b_e;
+        int rfs = 0, rfe = 0, sqs = 0, sqe = 0;  // the reference leaves these uninitialised
+        if (rev) { b_s = -cur[j].e; b_e = -cur[j].s; } else { b_s = cur[j].s; b_e = cur[j].e; }
+        for (int o = 0; o < n_ops; o++) {
+            const SpOpView v = sp_op_view(ops, o, rev);
+            int c_s, c_e;
+            if (rev) { c_s = -v.rde_f; c_e = -v.rds_f; } else { c_s = v.rds_f; c_e = v.rde_f; }
+            if (sp_op_is_match(v.op) || v.op == SP_CINS) {
+                const bool ins = v.op == SP_CINS;
+                while (have && b_e <= c_e) {
+                    if (c_s <= b_s && !(del_flag && c_s == b_s)) {
+                        rfs = ins ? v.rfs : v.rfs + (b_s - c_s);
+                        sqs = v.sqs + (b_s - c_s);
+                    }
+                    rfe = ins ? v.rfe : v.rfs + (b_e - c_s);
+                    sqe = v.sqs + (b_e - c_s);
+                    if (m < cap) {
+                        SpBlock nb;
+                        nb.rfs = rfs; nb.rfe = rfe; nb.sqs = sqs; nb.sqe = sqe;
+                        nb.rds_f = cur[j].s; nb.rde_f = cur[j].e;
+                        out[m] = nb;
+                    } else {
+                        *err |= SP_GERR_BLOCK_CAP;
+                    }
+                    m++;
+                    if (rev && j > 0) {
+                        j--;
+                        b_s = -cur[j].e; b_e = -cur[j].s;
+                    } else if (!rev && j < nc - 1) {
+                        j++;
+                        b_s = cur[j].s; b_e = cur[j].e;
+                    } else {
+                        have = false;
+                    }
+                }
+                if (!have) break;
+                if (c_s <= b_s && b_s <= c_e && !(del_flag && c_s == b_s)) {
+                    rfs = ins ? v.rfs : v.rfs + (b_s - c_s);
+                    sqs = v.sqs + (b_s - c_s);
+                }
+                del_flag = false;
+            } else if (v.op == SP_CDEL) {
+                // 615-625 only writes prev_block->rfe of the temporary consensus list (no effect, Q6)
+                if (have && b_s == c_s && v.len <= indel_threshold) {
+                    del_flag = true;
+                    rfs = v.rfs;
+                    sqs = v.sqs;
+                }
+            }
+        }
+        if (m > cap) m = cap;
+        sp_sort_blocks_by_sqs(out, m);
+        W.nb[i] = m;
+    }
+    return nc;
+}
+
+// needs_to_find_blocks, ptMarker.c:649-667
+SP_HD bool sp_needs_to_find_blocks(const SpBlockWork &W, int n, int threshold) {
+    bool flag = false;
+    for (int j = 0; j < n; j++) {
+        if (W.nb[j] == 0) return true;
+        const SpBlock *b = W.ab + (int64_t) j * W.cap;
+        for (int i = 0; i < W.nb[j]; i++)
+            if ((b[i].sqe - b[i].sqs) > threshold || (b[i].rfe - b[i].rfs) > threshold) flag = true;
+    }
+    return flag;
+}
+
+// The loop of secphase.c:161-169.  On entry W.ab/nb hold the confident blocks of the walk.
+// Returns conf_blocks_length (defined as 1 when the loop never runs, quirk Q1); *margin_out
+// receives the effective flank margin.
+SP_HD int sp_consensus_loop(const SpConst &C, const SpGroupAlnView &G, int P, const int32_t *gpos, SpBlockWork &W,
+                            int *margin_out, int *err) {
+    int margin = C.flank_margin;
+    int conf_len = 1;
+    while (C.consensus && sp_needs_to_find_blocks(W, G.n, SP_MAX_BLOCK_LEN)) {
+        margin = (int) (margin * 0.8);  // "flank_margin_eff *= 0.8" on an int
+        conf_len = sp_correct_conf_blocks(G, P, gpos, margin, C.indel_threshold, W, err);
+        if (conf_len == 0) break;
+    }
+    *margin_out = margin;
+    return conf_len;
+}
+
+// ---------------------------------------------------------------------------------------
+// calc_local_baq control flow for ONE alignment (ptMarker.c:670-809).  RES_RAW: the marker
+// keeps its raw quality; RES_ZERO: qual[base_idx] = 0 (709-720, 797-806); RES_SETQ: inside an HMM
+// window but not under an M/=/X op, bq stays set_q (763-764); >=0: index of the SpRow whose HMM
+// state/q decides (772-786).
+enum { SP_RES_RAW = -1, SP_RES_ZERO = -2, SP_RES_SETQ = -3 };
+
+SP_HD int sp_hmm_bw(int l_ref, int l_query, int par_bw) {  // band half-width probaln_glocal derives
+    int bw = l_ref > l_query ? l_ref : l_query;
+    if (bw > par_bw) bw = par_bw;
+    int d = l_ref - l_query;
+    if (d < 0) d = -d;
+    if (bw < d) bw = d;
+    return bw;
+}
+SP_HD int64_t sp_hmm_cells(int l_ref, int l_query, int bw) {
+    int64_t cells = 0;
+    // rows 1..l_query, columns max(1,i-bw)..min(l_ref,i+bw)
+    for (int i = 1; i <= l_query; i++) {
+        int beg = i - bw > 1 ? i - bw : 1;
+        int end = i + bw < l_ref ? i + bw : l_ref;
+        if (end >= beg) cells += end - beg + 1;
+    }
+    return cells;
+}
+
+struct SpEmitCounts {
+    int32_t n_items, n_rows;
+    int64_t cells;
+    int64_t s_doubles;  // sum over items of (l_query + 2)
+    int32_t max_bw;
+    int32_t class_count[5];
+};
+
+SP_HD int sp_band_class(int bw) { return bw <= 22 ? 0 : bw <= 30 ? 1 : bw <= 62 ? 2 : bw <= 120 ? 3 : 4; }
+SP_HD int sp_class_width(int cls) { return cls == 0 ? 46 : cls == 1 ? 62 : cls == 2 ? 126 : cls == 3 ? 242 : 0; }
+
+template <bool EMIT>
+SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, int P, const SpEntry *entries,
+                             const SpBlock *blocks, int n_blocks, int64_t ref_base, int64_t entry_base,
+                             SpEmitCounts &cnt, int32_t *res, SpItem *items, int item_base, SpRow *rows,
+                             int row_base) {
+    const int n = G.n, a = G.a0 + i;
+    const bool rev = (G.flag[a] & SP_FREVERSE) != 0;
+    const SpOp *ops = G.ops + G.ops_off[a];
+    const int n_ops = G.info[a].n_ops;
+    // marker cursor over this alignment's entries in list order (reverse strand: backwards)
+    int j = rev ? P - 1 : 0;
+    const int jstep = rev ? -1 : 1;
+#define SP_MK_VALID(jj) ((jj) >= 0 && (jj) < P)
+#define SP_MK_BASE(jj) (entries[(int64_t) (jj) * n + i].base_idx)
+    // iterator state "constructed, not advanced" (cigar_it.c:24-31)
+    int o = -1;
+    int it_sqs = 0, it_sqe = -1, it_rfs = 0, it_rfe = -1, it_op = -1, it_len = 0;
+    bool it_init = false;
+    auto it_next = [&]() -> int {
+        if (o + 1 >= n_ops) return 0;
+        o++;
+        SpOpView v = sp_op_view(ops, o, rev);
+        it_sqs = v.sqs; it_sqe = v.sqe; it_rfs = v.rfs; it_rfe = v.rfe; it_op = v.op; it_len = v.len;
+        return v.len;
+    };
+    if (!it_init) {
+        // before the first next(): sqs=0, sqe=-1, rfs=pos, rfe=pos-1; pos == rfs of the first op
+        it_rfs = n_ops > 0 ? ops[0].rfs : 0;
+        it_rfe = it_rfs - 1;
+        it_init = true;
+    }
+    for (int b = 0; b < n_blocks; b++) {
+        const SpBlock blk = blocks[b];
+        while (it_sqe < blk.sqs || it_rfe < blk.rfs) {
+            if (it_next() == 0) break;
+        }
+        while (SP_MK_VALID(j) && SP_MK_BASE(j) < blk.sqs + SP_BLOCK_MARGIN) {
+            if (blk.sqs <= SP_MK_BASE(j)) {
+                if (EMIT) res[entry_base + (int64_t) j * n + i] = SP_RES_ZERO;
+            }
+            j += jstep;
+        }
+        if (SP_MK_VALID(j) && SP_MK_BASE(j) <= blk.sqe - SP_BLOCK_MARGIN && blk.sqs + SP_BLOCK_MARGIN <= SP_MK_BASE(j)) {
+            const int l_query = blk.sqe - blk.sqs + 1;
+            const int l_ref = blk.rfe - blk.rfs + 1;
+            int dlen = l_ref - l_query;
+            if (dlen < 0) dlen = -dlen;
+            const int par_bw = (int) (dlen + C.conf_b);  // ptMarker.c:754, int + double -> int
+            const int bw = sp_hmm_bw(l_ref, l_query, par_bw);
+            const int item_idx = item_base + cnt.n_items;
+            const int first_row = row_base + cnt.n_rows;
+            int n_rows = 0;
+            // rows: this alignment's markers with base_idx in [sqs+10, sqe-11]; sqe-10 is written by the
+            // HMM and then zeroed again (800-803), so it needs no row.
+            int jj = j;
+            // the bq loop, ptMarker.c:767-785
+            while (it_sqs <= blk.sqe || it_rfs <= blk.rfe) {
+                int x = it_rfs - blk.rfs;
+                x = x < 0 ? 0 : x;
+                int y = it_sqs - blk.sqs;
+                y = y < 0 ? 0 : y;
+                if (sp_op_is_match(it_op)) {
+                    const int len = sp_min(it_len, sp_min(it_sqe, blk.sqe) - sp_max(it_sqs, blk.sqs) + 1);
+                    // markers with t in [y, y+len)
+                    while (SP_MK_VALID(jj) && SP_MK_BASE(jj) - blk.sqs < y) jj += jstep;
+                    while (SP_MK_VALID(jj) && SP_MK_BASE(jj) - blk.sqs < y + len) {
+                        const int t = SP_MK_BASE(jj) - blk.sqs;
+                        if (t >= SP_BLOCK_MARGIN && t < l_query - SP_BLOCK_MARGIN - 1) {
+                            if (EMIT) {
+                                SpRow r;
+                                r.item = item_idx;
+                                r.t = t;
+                                r.entry = (int32_t) (entry_base + (int64_t) jj * n + i);
+                                r.expected = x + (t - y);
+                                r.state = 0;
+                                r.q = 0;
+                                r.pmax = 0.0;
+                                rows[first_row + n_rows] = r;
+                                res[entry_base + (int64_t) jj * n + i] = first_row + n_rows;
+                            }
+                            n_rows++;
+                        }
+                        jj += jstep;
+                    }
+                }
+                if (it_sqe <= blk.sqe || it_rfe <= blk.rfe) {
+                    if (it_next() == 0) break;
+                } else {
+                    break;
+                }
+            }
+            if (EMIT) {
+                // markers of the write-back range that no M/=/X op visited keep bq = set_q (763-764):
+                // no HMM row is needed for them
+                int j2 = j;
+                while (SP_MK_VALID(j2) && SP_MK_BASE(j2) <= blk.sqe - SP_BLOCK_MARGIN - 1) {
+                    const int64_t e = entry_base + (int64_t) j2 * n + i;
+                    if (SP_MK_BASE(j2) - blk.sqs >= SP_BLOCK_MARGIN && res[e] == SP_RES_RAW) res[e] = SP_RES_SETQ;
+                    j2 += jstep;
+                }
+                SpItem it;
+                it.ref_off = ref_base + blk.rfs;
+                it.aln = a;
+                it.blk = b;
+                it.l_ref = l_ref;
+                it.l_query = l_query;
+                it.q_sqs = blk.sqs;
+                it.par_bw = par_bw;
+                it.row0 = first_row;
+                it.n_rows = n_rows;
+                it.query_off = -1;
+                items[item_idx] = it;
+            }
+            cnt.n_items += 1;
+            cnt.n_rows += n_rows;
+            cnt.cells += sp_hmm_cells(l_ref, l_query, bw);
+            cnt.s_doubles += l_query + 2;
+            if (bw > cnt.max_bw) cnt.max_bw = bw;
+            cnt.class_count[sp_band_class(bw)] += 1;
+        }
+        while (SP_MK_VALID(j) && SP_MK_BASE(j) <= blk.sqe) {
+            if (blk.sqe - SP_BLOCK_MARGIN <= SP_MK_BASE(j)) {
+                if (EMIT) res[entry_base + (int64_t) j * n + i] = SP_RES_ZERO;
+            }
+            j += jstep;
+        }
+    }
+#undef SP_MK_VALID
+#undef SP_MK_BASE
+}

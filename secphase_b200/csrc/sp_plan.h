@@ -1,0 +1,228 @@
+// sp_plan.h -- host-side batch planning shared by the launcher (sp_api.cu) and tests/hostsim.
+//
+// Everything the kernels write has a size that depends on the data (refined ops, markers,
+// blocks).  The host knows cheap upper bounds from the record text alone and lays the
+// per-alignment / per-group tables out with prefix sums, so kernels never allocate:
+//   refined ops      <= n_cigar + (token start characters of the cs/MD text) + 1
+//   initial markers  <= number of '*' in cs  (mismatched bases)   / upper-case letters in MD
+//   confident blocks <= 1 + (#I/D longer than the indel threshold) + (#clip ops)
+//   positions P      <= sum of the group's initial markers
+//   consensus blocks <= P + sum(confident blocks) + 2n + 8   ("tight"; intersecting k interval
+//                       lists can in theory exceed it -> kernels flag SP_GERR_BLOCK_CAP and the
+//                       launcher re-plans that batch with the provable bound  n*P + sum(cb))
+// Also holds the host-evaluated constants (float sub-expressions, libm tables) and the glibc
+// rand() emulation used for the tie-breaks of get_best_record_index (ptAlignment.c:156-171).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/secphase_b200.h"
+#include "sp_common.h"
+
+struct SpPlan {
+    int32_t G = 0, A = 0;
+    std::vector<int32_t> aln_grp;   // [A] group of each alignment
+    std::vector<int64_t> ops_off;   // [A+1]; each table has cap+1 slots (sentinel)
+    std::vector<int64_t> imk_off;   // [A+1]
+    std::vector<int32_t> cb_cap;    // [A]
+    std::vector<int64_t> gpos_off;  // [G+1] positions
+    std::vector<int64_t> gent_off;  // [G+1] entries (n per position)
+    std::vector<int64_t> gblk_off;  // [G+1] SpBlock workspace: n lists of gblk_cap[g]
+    std::vector<int64_t> giv_off;   // [G+1] SpIv workspace: 3 lists of gblk_cap[g]
+    std::vector<int32_t> gblk_cap;  // [G]
+    int64_t total_ops = 0, total_imk = 0, total_pos = 0, total_ent = 0, total_blk = 0, total_iv = 0;
+};
+
+// returns SP_OK or a negative error
+inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_caps, SpPlan &pl) {
+    const int G = b->n_groups, A = b->n_alns;
+    if (G < 0 || A < 0) return SP_EINVAL;
+    pl.G = G;
+    pl.A = A;
+    pl.aln_grp.assign((size_t) A, 0);
+    pl.ops_off.assign((size_t) A + 1, 0);
+    pl.imk_off.assign((size_t) A + 1, 0);
+    pl.cb_cap.assign((size_t) A, 0);
+    pl.gpos_off.assign((size_t) G + 1, 0);
+    pl.gent_off.assign((size_t) G + 1, 0);
+    pl.gblk_off.assign((size_t) G + 1, 0);
+    pl.giv_off.assign((size_t) G + 1, 0);
+    pl.gblk_cap.assign((size_t) G, 0);
+    int64_t ops = 0, imk = 0, pos = 0, ent = 0, blk = 0, iv = 0;
+    for (int g = 0; g < G; g++) {
+        const int a0 = b->grp_aln_off[g], a1 = b->grp_aln_off[g + 1];
+        const int n = a1 - a0;
+        if (n < 1 || n > SP_MAX_ALN_PER_GROUP || a0 < 0 || a1 > A) return SP_EINVAL;
+        int64_t msum = 0, cbsum = 0;
+        for (int a = a0; a < a1; a++) {
+            pl.aln_grp[(size_t) a] = g;
+            const int nc = b->n_cigar[a];
+            if (nc < 1) return SP_EINVAL;
+            const uint32_t *cig = b->cigar_pool + b->cigar_off[a];
+            int cb = 1;
+            for (int k = 0; k < nc; k++) {
+                const int op = (int) (cig[k] & 15), len = (int) (cig[k] >> 4);
+                if (op == SP_CSOFT || op == SP_CHARD) cb++;
+                else if ((op == SP_CINS || op == SP_CDEL) && len > indel_threshold) cb++;
+                else if (op == SP_CREF_SKIP || op == SP_CPAD || op > SP_CDIFF) return SP_EUNSUPPORTED;
+            }
+            const char *t = b->tag_pool + b->tag_off[a];
+            const int64_t tl = b->tag_off[a + 1] - b->tag_off[a];
+            const int kind = b->tag_kind ? b->tag_kind[a] : 0;
+            int64_t ntok = 0, nmis = 0;
+            if (kind == 0) {
+                for (int64_t k = 0; k < tl; k++) {
+                    const char c = t[k];
+                    nmis += (c == '*');
+                    ntok += (c == ':') | (c == '*') | (c == '+') | (c == '-');
+                }
+            } else {
+                for (int64_t k = 0; k < tl; k++) {
+                    const char c = t[k];
+                    const bool up = (c >= 'A' && c <= 'Z');
+                    nmis += up;
+                    ntok += up | (c == '^') | (c >= '0' && c <= '9');
+                }
+            }
+            pl.ops_off[(size_t) a] = ops;
+            ops += nc + ntok + 2;  // +1 spare, +1 sentinel
+            pl.imk_off[(size_t) a] = imk;
+            imk += nmis;
+            pl.cb_cap[(size_t) a] = cb;
+            msum += nmis;
+            cbsum += cb;
+        }
+        const int64_t P = msum;
+        int64_t cap = safe_caps ? (int64_t) n * P + cbsum + 2 * n + 8 : P + cbsum + 2 * n + 8;
+        if (cap > 0x3fffffff) return SP_ENOMEM;
+        pl.gblk_cap[(size_t) g] = (int32_t) cap;
+        pl.gpos_off[(size_t) g] = pos;
+        pos += P;
+        pl.gent_off[(size_t) g] = ent;
+        ent += P * n;
+        pl.gblk_off[(size_t) g] = blk;
+        blk += cap * n;
+        pl.giv_off[(size_t) g] = iv;
+        iv += cap * 3;
+    }
+    pl.ops_off[(size_t) A] = ops;
+    pl.imk_off[(size_t) A] = imk;
+    pl.gpos_off[(size_t) G] = pos;
+    pl.gent_off[(size_t) G] = ent;
+    pl.gblk_off[(size_t) G] = blk;
+    pl.giv_off[(size_t) G] = iv;
+    pl.total_ops = ops;
+    pl.total_imk = imk;
+    pl.total_pos = pos;
+    pl.total_ent = ent;
+    pl.total_blk = blk;
+    pl.total_iv = iv;
+    return SP_OK;
+}
+
+// ---- constants the device must not derive itself (host libm / C float semantics) ------------
+inline void sp_fill_const(const sp_params &p, SpConst &C) {
+    memset(&C, 0, sizeof(C));
+    C.baq_flag = p.baq_flag;
+    C.consensus = p.consensus;
+    C.indel_threshold = p.indel_threshold;
+    C.min_q = p.min_q;
+    C.set_q = p.set_q;
+    C.flank_margin = p.flank_margin;
+    C.conf_b = p.conf_b;
+    // probaln_par_t conf = {conf_d, conf_e, conf_bw} narrows to float (ptMarker.c:680)
+    const float d = (float) p.conf_d, e = (float) p.conf_e;
+    volatile float one_m_2d = 1 - d - d;  // htslib evaluates (1 - c->d - c->d) in float
+    volatile float one_m_d = 1 - d;
+    volatile float one_m_e = 1 - e;
+    C.m0f = (double) one_m_2d;
+    C.omd_f = (double) one_m_d;
+    C.omd_ff = one_m_d;
+    C.d_f = d;
+    C.d_d = (double) d;
+    C.ome_f = (double) one_m_e;
+    C.e_d = (double) e;
+    // qual[i] = g_qual2prob[iqual[i]] with g_qual2prob[q] = (float) pow(10, -q/10.)
+    const float qf = (float) pow(10, -(p.set_q & 255) / 10.);
+    C.em_match = 1. - qf;
+    C.em_mis = qf * .33333333333;
+    // q thresholds: f(t) = (int)(-4.343*log(t) + .499) is non-increasing in t; qthr[n] is the
+    // largest double t with f(t) >= n, found by bisection over the bit patterns of (0, 1].
+    for (int n = 1; n <= 101; n++) {
+        uint64_t lo = 1, hi = 0x3ff0000000000000ull;  // smallest subnormal .. 1.0
+        // invariant: f(lo) >= n (true for the smallest positive double: -4.343*log(4.9e-324) ~ 3235)
+        while (lo < hi) {
+            uint64_t mid = lo + (hi - lo + 1) / 2;
+            double t;
+            memcpy(&t, &mid, 8);
+            int k = (int) (-4.343 * log(t) + .499);
+            if (k >= n) lo = mid; else hi = mid - 1;
+        }
+        memcpy(&C.qthr[n], &lo, 8);
+    }
+    C.qthr[0] = 1.0;
+    for (int q = 0; q < 256; q++) {
+        // reverse_quality(uint8_t q), ptMarker.c:298-304
+        double rq;
+        if (q >= 93) rq = 0;
+        else if (q == 0) rq = 93;
+        else {
+            double pr = 1 - pow(10, (double) q / -10);
+            rq = -10 * log(pr);
+        }
+        C.sc_match[q] = -1 * rq;
+        C.sc_mis[q] = -1 * q - 10 * log(3);
+    }
+}
+
+// ---- glibc rand() (TYPE_3 additive feedback, r[i] = r[i-3] + r[i-31]), bit-compatible -------
+struct SpRng {
+    int32_t r[34];
+    uint32_t ring[31];  // the 31 most recent 32-bit sums
+    int idx = 0;
+    void seed(unsigned s) {
+        if (s == 0) s = 1;
+        int32_t t[344 + 31];
+        t[0] = (int32_t) s;
+        for (int i = 1; i < 31; i++) {
+            int64_t v = (16807LL * t[i - 1]) % 2147483647;
+            if (v < 0) v += 2147483647;
+            t[i] = (int32_t) v;
+        }
+        for (int i = 31; i < 34; i++) t[i] = t[i - 31];
+        for (int i = 34; i < 344; i++) t[i] = (int32_t) ((uint32_t) t[i - 31] + (uint32_t) t[i - 3]);
+        for (int i = 0; i < 31; i++) ring[i] = (uint32_t) t[344 - 31 + i];
+        idx = 0;
+    }
+    int next() {
+        // ring[(idx + j) % 31] holds o[k-31+j]; new = o[k-31] + o[k-3]
+        uint32_t v = ring[idx % 31] + ring[(idx + 28) % 31];
+        ring[idx % 31] = v;
+        idx = (idx + 1) % 31;
+        return (int) (v >> 1);
+    }
+};
+
+// get_best_record_index, ptAlignment.c:137-177, given the device's deterministic part.
+inline int sp_finalize_best(SpRng &rng, int n, const double *score, int prim_idx, int max_idx, int tie_mask,
+                            double prim_margin, double min_score, double prim_margin_random) {
+    if (n == 1) return 0;
+    double max_score = max_idx >= 0 ? score[max_idx] : -1.7976931348623157e308;
+    double prim_score = prim_idx >= 0 ? score[prim_idx] : -1.7976931348623157e308;
+    int ties[SP_MAX_ALN_PER_GROUP], nt = 0;
+    for (int i = 0; i < n; i++)
+        if (tie_mask & (1 << i)) ties[nt++] = i;
+    if (nt > 1) max_idx = ties[rng.next() % nt];
+    const int rnd = rng.next() % 2;
+    // "abs(max_score - prim_score)" is the INTEGER abs (ptAlignment.c:172): the double is
+    // truncated to int first (cvttsd2si semantics on the reference's x86-64 build).
+    double diff = max_score - prim_score;
+    int di = (diff >= 2147483648.0 || diff < -2147483648.0 || diff != diff) ? (int) 0x80000000 : (int) diff;
+    int ad = di < 0 ? (int) (0u - (unsigned) di) : di;
+    if ((double) ad < prim_margin_random) return rnd == 0 ? prim_idx : max_idx;
+    if (prim_idx == -1 || max_score <= (prim_score + prim_margin) || max_score < min_score) return prim_idx;
+    return max_idx;
+}

@@ -1,0 +1,118 @@
+// sp_score.cuh -- stage K5: BAQ write-back at the markers, low-quality filter, scores, selection.
+//
+// Restates, for one read group,
+//   the bq[] rule and write-back of calc_local_baq   (ptMarker.c:763-786)  at marker bases only
+//   calc_update_baq_all's marker update              (ptMarker.c:823-830)
+//   filter_lowq_markers                              (ptMarker.c:110-153)
+//   calc_alignment_score / reverse_quality           (ptMarker.c:307-325, 298-304)
+//   the deterministic part of get_best_record_index  (ptAlignment.c:137-177)
+// log()/pow() never run on the device: the two score terms come from 256-entry tables the host
+// fills with its own libm (SpConst::sc_match / sc_mis), the device only performs the IEEE adds
+// in list order, which is what makes alignment->score bit-identical.
+#pragma once
+#include "sp_blocks.cuh"
+#include "sp_common.h"
+
+struct SpGroupOut {  // per group, device -> host
+    int32_t best_pre;   // result of ptAlignment.c:175 given max_idx = first maximum (before tie-break RNG)
+    int32_t prim_idx;
+    int32_t n_init, n_after_allmm, n_filled, n_after_ins;
+    int32_t margin_eff, conf_len, n_final, scored;
+    int32_t max_idx;    // first secondary with the maximal score (ptAlignment.c:149-153)
+    int32_t tie_mask;   // secondaries with score >= max (ptAlignment.c:157-163)
+    int32_t err;
+    int32_t fin_off;    // start of this group's rows in the compact final-marker table
+    int32_t pad0, pad1;
+};
+
+// BAQ of one marker entry after calc_update_baq_all
+SP_HD int sp_resolve_q(const SpConst &C, const SpEntry &e, int res, const SpRow *rows) {
+    if (res == SP_RES_RAW) return e.q;
+    if (res == SP_RES_ZERO) return 0;
+    int bq;
+    if (res == SP_RES_SETQ) {
+        bq = C.set_q;
+    } else {
+        const SpRow r = rows[res];
+        if (((r.state & 3) != 0) || ((r.state >> 2) != r.expected)) bq = 0;
+        else bq = e.q < r.q ? e.q : r.q;
+    }
+    return bq < 94 ? bq : 93;
+}
+
+// entries are updated in place (q := BAQ), then compacted to the final list in fin[] as
+// SP_MARKER_W-wide rows.  Returns the number of final rows.
+SP_HD int sp_score_group(const SpConst &C, const SpGroupAlnView &G, int P, const int32_t *gpos, SpEntry *entries,
+                         const int32_t *res, const SpRow *rows, bool scored, double *score, int32_t *fin,
+                         int32_t *baq_dbg) {
+    const int n = G.n;
+    for (int i = 0; i < n; i++) score[i] = 0.0;
+    int nf = 0;
+    for (int p = 0; p < P; p++) {
+        int mq = 100;  // ptMarker.c:119
+        if (scored && C.baq_flag) {
+            for (int i = 0; i < n; i++) {
+                SpEntry &e = entries[(int64_t) p * n + i];
+                e.q = sp_resolve_q(C, e, res[(int64_t) p * n + i], rows);
+            }
+        }
+        if (baq_dbg) {
+            for (int i = 0; i < n; i++) baq_dbg[(int64_t) p * n + i] = entries[(int64_t) p * n + i].q;
+        }
+        bool keep = true;
+        if (scored) {
+            for (int i = 0; i < n; i++) {
+                const int q = entries[(int64_t) p * n + i].q;
+                if (mq > q) mq = q;
+            }
+            keep = mq > C.min_q;
+        }
+        if (!keep) continue;
+        for (int i = 0; i < n; i++) {
+            const SpEntry e = entries[(int64_t) p * n + i];
+            const int q = scored ? mq : e.q;
+            int32_t *row = fin + (int64_t) nf * 6;
+            row[0] = i;
+            row[1] = gpos[p];
+            row[2] = e.base_idx;
+            row[3] = q;
+            row[4] = e.flags & 1;
+            row[5] = e.ref_pos;
+            nf++;
+            if (scored) {
+                const int qi = q & 255;  // reverse_quality takes a uint8_t
+                score[i] = SP_DADD(score[i], (e.flags & 1) ? C.sc_match[qi] : C.sc_mis[qi]);
+            }
+        }
+    }
+    return nf;
+}
+
+// deterministic part of get_best_record_index, ptAlignment.c:137-177
+SP_HD void sp_select(const SpGroupAlnView &G, const double *score, double prim_margin, double min_score,
+                     SpGroupOut *out) {
+    const int n = G.n;
+    double max_score = -1.7976931348623157e308, prim_score = -1.7976931348623157e308;
+    int max_idx = -1, prim_idx = -1;
+    for (int i = 0; i < n; i++) {
+        if ((G.flag[G.a0 + i] & SP_FSECONDARY) == 0) {
+            prim_idx = i;
+            prim_score = score[i];
+        } else if (max_score < score[i]) {
+            max_idx = i;
+            max_score = score[i];
+        }
+    }
+    int mask = 0;
+    for (int i = 0; i < n; i++)
+        if (((G.flag[G.a0 + i] & SP_FSECONDARY) != 0) && (max_score <= score[i])) mask |= 1 << i;
+    out->prim_idx = prim_idx;
+    out->max_idx = max_idx;
+    out->tie_mask = mask;
+    if (n == 1) {
+        out->best_pre = 0;
+        return;
+    }
+    out->best_pre = (prim_idx == -1 || max_score <= (prim_score + prim_margin) || max_score < min_score) ? prim_idx
+                                                                                                        : max_idx;
+}

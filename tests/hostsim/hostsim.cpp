@@ -1,0 +1,309 @@
+// tests/hostsim/hostsim.cpp -- TEST HARNESS ONLY, not part of the product.
+//
+// The GPU-less build container cannot execute kernels, so the device stage logic
+// (secphase_b200/csrc/sp_*.cuh, written as SP_HD functions) is compiled here with g++ and run
+// thread-by-thread in plain loops, with the same table layout the CUDA launcher uses.  This
+// lets `pytest -m "not gpu"` diff the kernels' logic against the CPU oracle on thousands of
+// fuzzed read groups before any GPU time is spent.  libsecphase_b200.so never contains or calls
+// this file; the product path fails loudly without a CUDA device.
+//
+// Build: g++ -O2 -ffp-contract=off -fPIC -shared (see tests/conftest.py).
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../secphase_b200/csrc/sp_blocks.cuh"
+#include "../../secphase_b200/csrc/sp_common.h"
+#include "../../secphase_b200/csrc/sp_hmm.cuh"
+#include "../../secphase_b200/csrc/sp_markers.cuh"
+#include "../../secphase_b200/csrc/sp_plan.h"
+#include "../../secphase_b200/csrc/sp_score.cuh"
+#include "../../secphase_b200/csrc/sp_walk.cuh"
+
+struct HsOut {
+    std::vector<int32_t> group;   // [G][SP_GROUP_W]
+    std::vector<double> score;    // [A]
+    std::vector<int32_t> extent;  // [A][4]
+    std::vector<int32_t> mk[3];   // pre, baq, final [.][6]
+    std::vector<int64_t> mk_off[3];
+    std::vector<int32_t> blocks;  // [.][6]
+    std::vector<int64_t> block_off;
+    std::vector<int32_t> items;  // [.][SP_HMM_W]
+    std::vector<int32_t> rows;   // [.][4] item, t, state, q
+    int64_t cells = 0;
+    int32_t err = 0;
+};
+
+extern "C" {
+
+HsOut *hs_out_create() { return new HsOut(); }
+void hs_out_destroy(HsOut *o) { delete o; }
+
+#define HS_GET(name, field, T)                         \
+    const T *name(const HsOut *o, int64_t *n) {        \
+        *n = (int64_t) o->field.size();                \
+        return o->field.data();                        \
+    }
+HS_GET(hs_group, group, int32_t)
+HS_GET(hs_score, score, double)
+HS_GET(hs_extent, extent, int32_t)
+HS_GET(hs_blocks, blocks, int32_t)
+HS_GET(hs_block_off, block_off, int64_t)
+HS_GET(hs_items, items, int32_t)
+HS_GET(hs_rows, rows, int32_t)
+const int32_t *hs_markers(const HsOut *o, int st, int64_t *n) { *n = (int64_t) o->mk[st].size(); return o->mk[st].data(); }
+const int64_t *hs_marker_off(const HsOut *o, int st, int64_t *n) { *n = (int64_t) o->mk_off[st].size(); return o->mk_off[st].data(); }
+int64_t hs_cells(const HsOut *o) { return o->cells; }
+int32_t hs_err(const HsOut *o) { return o->err; }
+
+void hs_fill_const(const sp_params *p, SpConst *C) { sp_fill_const(*p, *C); }
+int hs_sizeof_const() { return (int) sizeof(SpConst); }
+
+// glibc rand() emulation checks
+void *hs_rng_create(unsigned seed) { SpRng *r = new SpRng(); r->seed(seed); return r; }
+int hs_rng_next(void *r) { return ((SpRng *) r)->next(); }
+void hs_rng_destroy(void *r) { delete (SpRng *) r; }
+
+// The HMM alone (same contract as sp_hmm_batch, one instance).
+int hs_hmm(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *query, int l_query, int par_bw,
+           const int32_t *rows_t, int n_rows, int32_t *state, uint8_t *q, double *pmax, double *s_out) {
+    SpConst C;
+    sp_fill_const(*p, C);
+    int bw = sp_hmm_bw(l_ref, l_query, par_bw);
+    int W = 2 * bw + 2;
+    std::vector<double> band((size_t) W * 3, 0.0);
+    std::vector<uint32_t> code((size_t) W, 0);
+    std::vector<double> s((size_t) l_query + 2, 0.0);
+    std::vector<double> fsave((size_t) n_rows * 2 * (2 * bw + 1) + 2, 0.0);
+    std::vector<SpRow> rows((size_t) (n_rows > 0 ? n_rows : 1));
+    for (int i = 0; i < n_rows; i++) {
+        rows[i].item = 0; rows[i].t = rows_t[i]; rows[i].entry = -1; rows[i].expected = 0;
+        rows[i].state = 0; rows[i].q = 0; rows[i].pmax = 0;
+    }
+    SpHmmIn in;
+    in.ref = ref; in.qbytes = query; in.qseq4 = nullptr; in.q0 = 0;
+    in.l_ref = l_ref; in.l_query = l_query; in.par_bw = par_bw;
+    SpBand<1> B;
+    B.row = band.data(); B.code = code.data(); B.W = W;
+    sp_hmm_instance<1, 1>(C, in, B, s.data(), fsave.data(), 2 * (2 * bw + 1), rows.data(), n_rows);
+    for (int i = 0; i < n_rows; i++) {
+        state[i] = rows[i].state;
+        q[i] = (uint8_t) rows[i].q;
+        if (pmax) pmax[i] = rows[i].pmax;
+    }
+    if (s_out) memcpy(s_out, s.data(), sizeof(double) * ((size_t) l_query + 2));
+    return 0;
+}
+
+// Whole marker path for a batch; ref_codes: concatenated contigs (codes 0..4), contig_off[n+1].
+int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
+           int n_contigs, int safe_caps, unsigned rng_seed, HsOut *out) {
+    (void) n_contigs;
+    SpConst C;
+    sp_fill_const(*p, C);
+    SpPlan pl;
+    int rc = sp_make_plan(b, p->indel_threshold, safe_caps != 0, pl);
+    if (rc != SP_OK) return rc;
+    const int G = pl.G, A = pl.A;
+    // 16-byte padded copy of the tag pool (SpByteReader reads aligned 16-byte words)
+    const int64_t tag_bytes = b->tag_off[A];
+    std::vector<uint8_t> tagbuf((size_t) tag_bytes + 32, 0);
+    uint8_t *tag_pool = tagbuf.data();
+    while (((uintptr_t) tag_pool) & 15) tag_pool++;
+    memcpy(tag_pool, b->tag_pool, (size_t) tag_bytes);
+
+    std::vector<SpOp> ops((size_t) pl.total_ops + 1);
+    std::vector<SpInitMarker> imk((size_t) pl.total_imk + 1);
+    std::vector<SpAlnInfo> info((size_t) A);
+    std::vector<SpBlock> blk((size_t) pl.total_blk + 1);
+    std::vector<SpIv> iv((size_t) pl.total_iv + 1);
+    std::vector<int32_t> nb((size_t) A, 0);
+    std::vector<int32_t> gpos((size_t) pl.total_pos + 1);
+    std::vector<SpEntry> ent((size_t) pl.total_ent + 1);
+    std::vector<int32_t> res((size_t) pl.total_ent + 1, SP_RES_RAW);
+    std::vector<int32_t> baq((size_t) pl.total_ent + 1, 0);
+    std::vector<int32_t> fin((size_t) pl.total_ent * 6 + 6);
+    std::vector<SpGroupOut> gout((size_t) G);
+    std::vector<int32_t> gP((size_t) G, 0);
+    std::vector<double> score((size_t) A, 0.0);
+    std::vector<SpEmitCounts> gcnt((size_t) G);
+
+    // K1: one "thread" per alignment; confident blocks land in the group's block workspace
+    for (int a = 0; a < A; a++) {
+        const int g = pl.aln_grp[a];
+        const int i = a - b->grp_aln_off[g];
+        SpBlock *cb = blk.data() + pl.gblk_off[g] + (int64_t) i * pl.gblk_cap[g];
+        sp_walk_alignment(C.indel_threshold, C.min_q, b->flag[a], b->pos[a], b->l_qseq[a], b->n_cigar[a],
+                          b->cigar_pool + b->cigar_off[a], tag_pool, b->tag_off[a], b->tag_off[a + 1],
+                          b->tag_kind ? b->tag_kind[a] : 0, b->qual_pool + b->qual_off[a],
+                          ops.data() + pl.ops_off[a], (int) (pl.ops_off[a + 1] - pl.ops_off[a] - 1),
+                          imk.data() + pl.imk_off[a], (int) (pl.imk_off[a + 1] - pl.imk_off[a]), cb,
+                          pl.gblk_cap[g], &info[a]);
+        nb[a] = info[a].n_cb;
+    }
+    auto view = [&](int g) {
+        SpGroupAlnView V;
+        V.a0 = b->grp_aln_off[g];
+        V.n = b->grp_aln_off[g + 1] - V.a0;
+        V.flag = b->flag;
+        V.l_qseq = b->l_qseq;
+        V.qual_off = b->qual_off;
+        V.qual_pool = b->qual_pool;
+        V.info = info.data();
+        V.ops_off = pl.ops_off.data();
+        V.ops = ops.data();
+        V.imk_off = pl.imk_off.data();
+        V.imk = imk.data();
+        return V;
+    };
+    out->mk_off[0].push_back(0);
+    // K2 + K3 (consensus + count pass): one "thread" per group
+    for (int g = 0; g < G; g++) {
+        SpGroupAlnView V = view(g);
+        SpGroupOut &o = gout[g];
+        memset(&o, 0, sizeof(o));
+        int err = 0;
+        for (int i = 0; i < V.n; i++) err |= info[V.a0 + i].err;
+        int32_t counts[4];
+        int P = sp_group_markers(V, gpos.data() + pl.gpos_off[g], ent.data() + pl.gent_off[g],
+                                 (int) (pl.gpos_off[g + 1] - pl.gpos_off[g]), counts, &err);
+        gP[g] = P;
+        o.n_init = counts[0]; o.n_after_allmm = counts[1]; o.n_filled = counts[2]; o.n_after_ins = counts[3];
+        for (int pi = 0; pi < P; pi++)
+            for (int i = 0; i < V.n; i++) {
+                const SpEntry &e = ent[pl.gent_off[g] + (int64_t) pi * V.n + i];
+                int32_t row[6] = {i, gpos[pl.gpos_off[g] + pi], e.base_idx, e.q, e.flags & 1, e.ref_pos};
+                out->mk[0].insert(out->mk[0].end(), row, row + 6);
+            }
+        out->mk_off[0].push_back((int64_t) out->mk[0].size() / 6);
+        SpBlockWork W;
+        W.cap = pl.gblk_cap[g];
+        W.ab = blk.data() + pl.gblk_off[g];
+        W.nb = nb.data() + V.a0;
+        W.cons_a = iv.data() + pl.giv_off[g];
+        W.cons_b = W.cons_a + W.cap;
+        W.flank = W.cons_b + W.cap;
+        int margin = C.flank_margin, conf_len = 1;
+        bool scored = false;
+        SpEmitCounts cnt;
+        memset(&cnt, 0, sizeof(cnt));
+        if (P > 0) {
+            conf_len = sp_consensus_loop(C, V, P, gpos.data() + pl.gpos_off[g], W, &margin, &err);
+            if (conf_len > 0 || !C.consensus) {
+                scored = true;
+                if (C.baq_flag) {
+                    for (int i = 0; i < V.n; i++) {
+                        const int a = V.a0 + i;
+                        sp_emit_alignment<false>(C, V, i, P, ent.data() + pl.gent_off[g],
+                                                 W.ab + (int64_t) i * W.cap, W.nb[i], contig_off[b->tid[a]],
+                                                 pl.gent_off[g] - pl.gent_off[g], cnt, nullptr, nullptr, 0, nullptr, 0);
+                    }
+                }
+            }
+        }
+        if (P == 0)  // the reference never builds confident blocks for a group without markers (secphase.c:161)
+            for (int i = 0; i < V.n; i++) W.nb[i] = 0;
+        gcnt[g] = cnt;
+        o.margin_eff = margin;
+        o.conf_len = conf_len;
+        o.scored = scored ? 1 : 0;
+        o.err = err;
+    }
+    // scan
+    std::vector<int32_t> item_off((size_t) G + 1, 0), row_off((size_t) G + 1, 0);
+    for (int g = 0; g < G; g++) {
+        item_off[g + 1] = item_off[g] + gcnt[g].n_items;
+        row_off[g + 1] = row_off[g] + gcnt[g].n_rows;
+        out->cells += gcnt[g].cells;
+    }
+    std::vector<SpItem> items((size_t) item_off[G] + 1);
+    std::vector<SpRow> rows((size_t) row_off[G] + 1);
+    // emit
+    for (int g = 0; g < G; g++) {
+        SpGroupAlnView V = view(g);
+        if (!gout[g].scored || !C.baq_flag) continue;
+        SpEmitCounts cnt;
+        memset(&cnt, 0, sizeof(cnt));
+        for (int i = 0; i < V.n; i++) {
+            const int a = V.a0 + i;
+            sp_emit_alignment<true>(C, V, i, gP[g], ent.data() + pl.gent_off[g],
+                                    blk.data() + pl.gblk_off[g] + (int64_t) i * pl.gblk_cap[g], nb[a],
+                                    contig_off[b->tid[a]], 0, cnt, res.data() + pl.gent_off[g], items.data(),
+                                    item_off[g], rows.data(), row_off[g]);
+        }
+        if (cnt.n_items != gcnt[g].n_items || cnt.n_rows != gcnt[g].n_rows) out->err |= 0x100;
+    }
+    // K4: one "lane" per item
+    for (int it = 0; it < item_off[G]; it++) {
+        const SpItem &I = items[it];
+        const int bw = sp_hmm_bw(I.l_ref, I.l_query, I.par_bw);
+        const int W = 2 * bw + 2;
+        std::vector<double> band((size_t) W * 3, 0.0);
+        std::vector<uint32_t> code((size_t) W, 0);
+        std::vector<double> s((size_t) I.l_query + 2, 0.0);
+        std::vector<double> fsave((size_t) I.n_rows * 2 * (2 * bw + 1) + 2, 0.0);
+        SpHmmIn in;
+        in.ref = ref_codes + I.ref_off;
+        in.qbytes = nullptr;
+        in.qseq4 = b->seq_pool + b->seq_off[I.aln];
+        in.q0 = I.q_sqs;
+        in.l_ref = I.l_ref; in.l_query = I.l_query; in.par_bw = I.par_bw;
+        SpBand<1> B;
+        B.row = band.data(); B.code = code.data(); B.W = W;
+        sp_hmm_instance<1, 1>(C, in, B, s.data(), fsave.data(), 2 * (2 * bw + 1), rows.data() + I.row0, I.n_rows);
+        int32_t irow[SP_HMM_W] = {I.aln, I.l_ref, I.l_query, I.par_bw, I.blk, I.row0, I.n_rows, 0};
+        out->items.insert(out->items.end(), irow, irow + SP_HMM_W);
+    }
+    for (int r = 0; r < row_off[G]; r++) {
+        int32_t rr[4] = {rows[r].item, rows[r].t, rows[r].state, rows[r].q};
+        out->rows.insert(out->rows.end(), rr, rr + 4);
+    }
+    // K5 + host finalisation
+    SpRng rng;
+    rng.seed(rng_seed);
+    out->mk_off[1].push_back(0);
+    out->mk_off[2].push_back(0);
+    out->block_off.push_back(0);
+    for (int g = 0; g < G; g++) {
+        SpGroupAlnView V = view(g);
+        SpGroupOut &o = gout[g];
+        const int P = gP[g];
+        int nf = sp_score_group(C, V, P, gpos.data() + pl.gpos_off[g], ent.data() + pl.gent_off[g],
+                                res.data() + pl.gent_off[g], rows.data(), o.scored != 0, score.data() + V.a0,
+                                fin.data() + pl.gent_off[g] * 6, baq.data() + pl.gent_off[g]);
+        o.n_final = nf;
+        sp_select(V, score.data() + V.a0, p->prim_margin_score, (double) p->min_score, &o);
+        int best = sp_finalize_best(rng, V.n, score.data() + V.a0, o.prim_idx, o.max_idx, o.tie_mask,
+                                    p->prim_margin_score, (double) p->min_score, p->prim_margin_random);
+        int32_t grow[SP_GROUP_W] = {best, o.prim_idx, o.n_init, o.n_after_allmm, o.n_filled, o.n_after_ins,
+                                    o.margin_eff, o.conf_len, o.n_final, o.scored};
+        out->group.insert(out->group.end(), grow, grow + SP_GROUP_W);
+        out->err |= o.err;
+        for (int pi = 0; pi < P; pi++)
+            for (int i = 0; i < V.n; i++) {
+                const SpEntry &e = ent[pl.gent_off[g] + (int64_t) pi * V.n + i];
+                int32_t row[6] = {i, gpos[pl.gpos_off[g] + pi], e.base_idx, baq[pl.gent_off[g] + (int64_t) pi * V.n + i],
+                                  e.flags & 1, e.ref_pos};
+                out->mk[1].insert(out->mk[1].end(), row, row + 6);
+            }
+        out->mk_off[1].push_back((int64_t) out->mk[1].size() / 6);
+        out->mk[2].insert(out->mk[2].end(), fin.data() + pl.gent_off[g] * 6, fin.data() + pl.gent_off[g] * 6 + (int64_t) nf * 6);
+        out->mk_off[2].push_back((int64_t) out->mk[2].size() / 6);
+        for (int i = 0; i < V.n; i++) {
+            const int a = V.a0 + i;
+            out->score.push_back(score[a]);
+            int32_t ex[4] = {info[a].rfs, info[a].rfe, info[a].rds_f, info[a].rde_f};
+            out->extent.insert(out->extent.end(), ex, ex + 4);
+            const SpBlock *bl = blk.data() + pl.gblk_off[g] + (int64_t) i * pl.gblk_cap[g];
+            for (int k = 0; k < nb[a]; k++) {
+                int32_t br[6] = {bl[k].rfs, bl[k].rfe, bl[k].sqs, bl[k].sqe, bl[k].rds_f, bl[k].rde_f};
+                out->blocks.insert(out->blocks.end(), br, br + 6);
+            }
+            out->block_off.push_back((int64_t) out->blocks.size() / 6);
+        }
+    }
+    return 0;
+}
+}  // extern "C"

@@ -1,0 +1,129 @@
+"""ctypes binding of tests/hostsim/libhostsim.so -- TEST HARNESS ONLY (see hostsim.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from tools.flatbatch import CFlatBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+LIB = os.path.join(_HERE, "libhostsim.so")
+SRC = os.path.join(_HERE, "hostsim.cpp")
+CSRC = os.path.join(_ROOT, "secphase_b200", "csrc")
+
+
+class SpParams(C.Structure):
+    _fields_ = [
+        ("baq_flag", C.c_int32), ("consensus", C.c_int32), ("indel_threshold", C.c_int32),
+        ("min_q", C.c_int32), ("min_score", C.c_int32), ("set_q", C.c_int32), ("flank_margin", C.c_int32),
+        ("prim_margin_score", C.c_double), ("prim_margin_random", C.c_double),
+        ("conf_d", C.c_double), ("conf_e", C.c_double), ("conf_b", C.c_double),
+    ]
+
+
+def build(force=False):
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    newest = max(os.path.getmtime(p) for p in deps)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+                               "-o", LIB, SRC])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.hs_out_create.restype = C.c_void_p
+        L.hs_out_destroy.argtypes = [C.c_void_p]
+        L.hs_run.argtypes = [C.POINTER(CFlatBatch), C.POINTER(SpParams), C.c_void_p, C.c_void_p, C.c_int,
+                             C.c_int, C.c_uint, C.c_void_p]
+        L.hs_run.restype = C.c_int
+        for name, rt in [("group", C.c_int32), ("score", C.c_double), ("extent", C.c_int32),
+                         ("blocks", C.c_int32), ("block_off", C.c_int64), ("items", C.c_int32), ("rows", C.c_int32)]:
+            f = getattr(L, "hs_" + name)
+            f.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+            f.restype = C.POINTER(rt)
+        L.hs_markers.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.hs_markers.restype = C.POINTER(C.c_int32)
+        L.hs_marker_off.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.hs_marker_off.restype = C.POINTER(C.c_int64)
+        L.hs_cells.argtypes = [C.c_void_p]
+        L.hs_cells.restype = C.c_int64
+        L.hs_err.argtypes = [C.c_void_p]
+        L.hs_err.restype = C.c_int32
+        L.hs_hmm.argtypes = [C.POINTER(SpParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_hmm.restype = C.c_int
+        L.hs_rng_create.argtypes = [C.c_uint]
+        L.hs_rng_create.restype = C.c_void_p
+        L.hs_rng_next.argtypes = [C.c_void_p]
+        L.hs_rng_next.restype = C.c_int
+        L.hs_rng_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _take(ptr, n, width, dt):
+    if n == 0:
+        return np.zeros((0, width) if width > 1 else (0,), dtype=dt)
+    a = np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dt, copy=True)
+    return a.reshape(-1, width) if width > 1 else a
+
+
+def params_from_oracle(op):
+    return SpParams(**{k: getattr(op, k) for k, _ in SpParams._fields_})
+
+
+def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1):
+    L = lib()
+    out = L.hs_out_create()
+    try:
+        cb = batch.as_c()
+        ref_codes = np.ascontiguousarray(ref_codes, np.uint8)
+        contig_off = np.ascontiguousarray(contig_off, np.int64)
+        rc = L.hs_run(C.byref(cb), C.byref(params), ref_codes.ctypes.data, contig_off.ctypes.data,
+                      len(contig_off) - 1, 1 if safe_caps else 0, seed, out)
+        if rc != 0:
+            raise RuntimeError(f"hs_run failed: {rc}")
+        n = C.c_int64()
+        r = {"kind": "hostsim"}
+        r["groups"] = _take(L.hs_group(out, C.byref(n)), n.value, 10, np.int32)
+        r["scores"] = _take(L.hs_score(out, C.byref(n)), n.value, 1, np.float64)
+        r["extents"] = _take(L.hs_extent(out, C.byref(n)), n.value, 4, np.int32)
+        r["blocks"] = _take(L.hs_blocks(out, C.byref(n)), n.value, 6, np.int32)
+        r["block_off"] = _take(L.hs_block_off(out, C.byref(n)), n.value, 1, np.int64)
+        r["items"] = _take(L.hs_items(out, C.byref(n)), n.value, 8, np.int32)
+        r["rows"] = _take(L.hs_rows(out, C.byref(n)), n.value, 4, np.int32)
+        for st, nm in enumerate(("markers_pre", "markers_baq", "markers_final")):
+            r[nm] = _take(L.hs_markers(out, st, C.byref(n)), n.value, 6, np.int32)
+            r[nm + "_off"] = _take(L.hs_marker_off(out, st, C.byref(n)), n.value, 1, np.int64)
+        r["cells"] = int(L.hs_cells(out))
+        r["err"] = int(L.hs_err(out))
+        return r
+    finally:
+        L.hs_out_destroy(out)
+
+
+def hmm(params, ref, query, par_bw, rows_t, want_s=False):
+    L = lib()
+    ref = np.ascontiguousarray(ref, np.uint8)
+    query = np.ascontiguousarray(query, np.uint8)
+    rows_t = np.ascontiguousarray(rows_t, np.int32)
+    n = len(rows_t)
+    state = np.zeros(n, np.int32)
+    q = np.zeros(n, np.uint8)
+    pmax = np.zeros(n, np.float64)
+    s = np.zeros(len(query) + 2, np.float64)
+    rc = L.hs_hmm(C.byref(params), ref.ctypes.data, len(ref), query.ctypes.data, len(query), par_bw,
+                  rows_t.ctypes.data, n, state.ctypes.data, q.ctypes.data, pmax.ctypes.data, s.ctypes.data)
+    assert rc == 0
+    out = dict(state=state, q=q, pmax=pmax)
+    if want_s:
+        out["s"] = s
+    return out

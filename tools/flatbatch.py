@@ -18,7 +18,7 @@ class CFlatBatch(C.Structure):
         ("n_alns", C.c_int32),
         ("grp_aln_off", _I32P),
         ("qname_off", _I64P),
-        ("qname_pool", C.c_char_p),
+        ("qname_pool", _U8P),
         ("flag", _I32P),
         ("tid", _I32P),
         ("pos", _I32P),
@@ -30,7 +30,7 @@ class CFlatBatch(C.Structure):
         ("seq_off", _I64P),
         ("qual_off", _I64P),
         ("cigar_pool", _U32P),
-        ("tag_pool", C.c_char_p),
+        ("tag_pool", _U8P),
         ("seq_pool", _U8P),
         ("qual_pool", _U8P),
     ]
@@ -75,13 +75,13 @@ class FlatBatch:
         qual_off = arr(v.qual_off, na + 1, np.int64)
         return cls(
             grp_aln_off=grp, qname_off=qoff,
-            qname_pool=arr(C.cast(v.qname_pool, _U8P), int(qoff[-1]), np.uint8),
+            qname_pool=arr(v.qname_pool, int(qoff[-1]), np.uint8),
             flag=arr(v.flag, na, np.int32), tid=arr(v.tid, na, np.int32), pos=arr(v.pos, na, np.int32),
             l_qseq=arr(v.l_qseq, na, np.int32), n_cigar=arr(v.n_cigar, na, np.int32),
             tag_kind=arr(v.tag_kind, na, np.int32) if v.tag_kind else np.zeros(na, np.int32),
             cigar_off=cig_off, tag_off=tag_off, seq_off=seq_off, qual_off=qual_off,
             cigar_pool=arr(v.cigar_pool, int(cig_off[-1]), np.uint32),
-            tag_pool=arr(C.cast(v.tag_pool, _U8P), int(tag_off[-1]), np.uint8),
+            tag_pool=arr(v.tag_pool, int(tag_off[-1]), np.uint8),
             seq_pool=arr(v.seq_pool, int(seq_off[-1]), np.uint8),
             qual_pool=arr(v.qual_pool, int(qual_off[-1]), np.uint8),
         )
@@ -93,10 +93,7 @@ class FlatBatch:
         for name, dt in _FIELDS:
             a = getattr(self, name)
             ftype = dict(CFlatBatch._fields_)[name]
-            if ftype is C.c_char_p:
-                setattr(s, name, C.cast(a.ctypes.data, C.c_char_p))
-            else:
-                setattr(s, name, C.cast(a.ctypes.data, ftype))
+            setattr(s, name, C.cast(a.ctypes.data, ftype))
         s._keep = self
         return s
 
