@@ -97,7 +97,7 @@ typedef struct sp_result {
     int64_t h2d_bytes, d2h_bytes;
     float ms_total;            /* CUDA-event time H2D start -> D2H end on the slot's stream */
     float ms_hmm;              /* CUDA-event time of the BAQ-HMM kernels only */
-    float ms_stage[8];         /* h2d, walk, markers, blocks, emit+sort, hmm, score, d2h */
+    float ms_stage[8];         /* h2d, walk, group (markers+blocks+count), emit+sort, hmm, score, d2h, 0 */
     int32_t gpu_launches;      /* kernels launched for this batch */
 } sp_result;
 

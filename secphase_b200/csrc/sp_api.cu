@@ -1,0 +1,898 @@
+// sp_api.cu -- C ABI of libsecphase_b200.so (see include/secphase_b200.h) and the launcher
+// that drives the kernels of sp_kernels.cuh.  Host side only plans, packs into pinned staging,
+// enqueues, and turns the device results into the reference's tables; there is no CPU
+// implementation of the hot path in this library.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/secphase_b200.h"
+#include "sp_kernels.cuh"
+#include "sp_plan.h"
+
+static thread_local char g_err[512] = "";
+static void set_err(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            set_err("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,  \
+                    cudaGetErrorString(e_));                                                  \
+            return SP_ECUDA;                                                                  \
+        }                                                                                     \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SP_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cap = 0;
+            set_err("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return SP_ENOMEM;
+        }
+        cap = want;
+        return SP_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SP_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) {
+            cap = 0;
+            set_err("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+            return SP_ENOMEM;
+        }
+        cap = want;
+        return SP_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+enum { EV_START = 0, EV_H2D, EV_WALK, EV_GROUP, EV_EMIT, EV_HMM, EV_SCORE, EV_END, EV_N };
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_N] = {};
+    PinBuf h_in;    // staged batch (one H2D copy)
+    DevBuf d_in;
+    size_t in_bytes = 0;
+    SpPlan plan;
+    bool safe_caps = false;
+    // device work tables
+    DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, item_off, row_off, sdbl_off, score,
+        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals;
+    // host results
+    PinBuf h_tot, h_gout, h_score, h_info, h_fin;
+    SpBatchPtrs P;
+    SpTotals tot;     // after the mid-pipeline read-back
+    int state = 0;    // 0 idle, 1 uploaded, 2 in flight, 3 done
+    bool want_d2h = true;
+    bool debug = false;
+    int launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    // host tables handed out by sp_wait / sp_debug_table
+    std::vector<int32_t> r_group, r_extent, r_marker, dbg_rows;
+    std::vector<int64_t> r_marker_off, dbg_off;
+    std::vector<double> r_score;
+};
+
+struct sp_ctx {
+    int device = 0;
+    sp_params par;
+    SpConst hC;
+    DevBuf dC;
+    DevBuf ref;          // codes
+    DevBuf contig_off;   // int64[n+1]
+    std::vector<int64_t> h_contig_off;
+    int n_contigs = 0;
+    Slot slot[SP_N_SLOTS];
+    SpRng rng;
+    bool debug_tables = false;
+    int sm_count = 0;
+    size_t max_smem = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *sp_last_error(void) { return g_err; }
+const char *sp_version(void) { return "secphase_b200 0.1 (sm_100a)"; }
+
+void sp_params_default(sp_params *p) {  // secphase.c:420-449
+    p->baq_flag = 0;
+    p->consensus = 0;
+    p->indel_threshold = 10;
+    p->min_q = 10;
+    p->min_score = -10;
+    p->set_q = 40;
+    p->flank_margin = 500;
+    p->prim_margin_score = 40;
+    p->prim_margin_random = 0;
+    p->conf_d = 1e-4;
+    p->conf_e = 0.1;
+    p->conf_b = 20;
+}
+
+int sp_params_preset(sp_params *p, const char *name) {  // secphase.c:477-504
+    if (!p || !name) return SP_EINVAL;
+    const bool hifi = strcmp(name, "hifi") == 0, ont = strcmp(name, "ont") == 0;
+    if (!hifi && !ont) {
+        set_err("unknown preset '%s'", name);
+        return SP_EINVAL;
+    }
+    p->baq_flag = 1;
+    p->consensus = 1;
+    p->indel_threshold = hifi ? 10 : 20;
+    p->conf_d = hifi ? 1e-4 : 1e-3;
+    p->conf_e = 0.1;
+    p->conf_b = 20;
+    p->min_q = 10;
+    p->set_q = hifi ? 40 : 20;
+    p->prim_margin_score = hifi ? 40 : 20;
+    p->prim_margin_random = 0;
+    p->min_score = -10;
+    return SP_OK;
+}
+
+sp_ctx *sp_create(const sp_params *p, int cuda_device) {
+    if (!p) {
+        set_err("sp_create: params is NULL");
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_err("no usable CUDA device (%s); libsecphase_b200 has no CPU path", cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (cuda_device < 0 || cuda_device >= ndev) {
+        set_err("cuda_device %d out of range (0..%d)", cuda_device, ndev - 1);
+        return nullptr;
+    }
+    if (cudaSetDevice(cuda_device) != cudaSuccess) {
+        set_err("cudaSetDevice(%d) failed", cuda_device);
+        return nullptr;
+    }
+    sp_ctx *c = new sp_ctx();
+    c->device = cuda_device;
+    c->par = *p;
+    sp_fill_const(*p, c->hC);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cuda_device);
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem = prop.sharedMemPerBlockOptin;
+    if (c->dC.ensure(sizeof(SpConst)) != SP_OK ||
+        cudaMemcpy(c->dC.p, &c->hC, sizeof(SpConst), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_err("sp_create: could not upload constants");
+        delete c;
+        return nullptr;
+    }
+    if (cudaFuncSetAttribute(k_hmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
+        set_err("sp_create: cudaFuncSetAttribute(k_hmm) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    for (int s = 0; s < SP_N_SLOTS; s++) {
+        cudaStreamCreateWithFlags(&c->slot[s].stream, cudaStreamNonBlocking);
+        for (int k = 0; k < EV_N; k++) cudaEventCreate(&c->slot[s].ev[k]);
+    }
+    c->rng.seed(1);
+    return c;
+}
+
+void sp_destroy(sp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < SP_N_SLOTS; s++) {
+        Slot &S = c->slot[s];
+        DevBuf *bufs[] = {&S.d_in, &S.ops, &S.imk, &S.info, &S.blk, &S.iv, &S.nb, &S.gpos, &S.ent, &S.res, &S.baq,
+                          &S.gP, &S.gout, &S.gcnt, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
+                          &S.fin, &S.items, &S.rows, &S.order, &S.bins, &S.class_start, &S.s_pool, &S.fsave,
+                          &S.gband, &S.totals};
+        for (DevBuf *b : bufs) b->release();
+        PinBuf *pins[] = {&S.h_in, &S.h_tot, &S.h_gout, &S.h_score, &S.h_info, &S.h_fin};
+        for (PinBuf *b : pins) b->release();
+        for (int k = 0; k < EV_N; k++)
+            if (S.ev[k]) cudaEventDestroy(S.ev[k]);
+        if (S.stream) cudaStreamDestroy(S.stream);
+    }
+    c->dC.release();
+    c->ref.release();
+    c->contig_off.release();
+    delete c;
+}
+
+void sp_rng_seed(sp_ctx *c, unsigned seed) { c->rng.seed(seed); }
+int sp_rng_next(sp_ctx *c) { return c->rng.next(); }
+
+int sp_set_reference_codes(sp_ctx *c, int32_t n, const uint8_t *codes, const int64_t *off) {
+    if (!c || n < 1 || !codes || !off) return SP_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const int64_t total = off[n];
+    int rc = c->ref.ensure((size_t) total + 64);
+    if (rc) return rc;
+    rc = c->contig_off.ensure(sizeof(int64_t) * (size_t) (n + 1));
+    if (rc) return rc;
+    CK(cudaMemcpy(c->ref.p, codes, (size_t) total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->contig_off.p, off, sizeof(int64_t) * (size_t) (n + 1), cudaMemcpyHostToDevice));
+    c->h_contig_off.assign(off, off + n + 1);
+    c->n_contigs = n;
+    return SP_OK;
+}
+
+int sp_set_reference_ascii(sp_ctx *c, int32_t n, const char *const *seqs, const int64_t *lens) {
+    if (!c || n < 1 || !seqs || !lens) return SP_EINVAL;
+    CK(cudaSetDevice(c->device));
+    std::vector<int64_t> off((size_t) n + 1, 0);
+    for (int i = 0; i < n; i++) off[(size_t) i + 1] = off[(size_t) i] + lens[i];
+    const int64_t total = off[(size_t) n];
+    int rc = c->ref.ensure((size_t) total + 64);
+    if (rc) return rc;
+    rc = c->contig_off.ensure(sizeof(int64_t) * (size_t) (n + 1));
+    if (rc) return rc;
+    // stage the ASCII text through a bounce buffer and encode on the device
+    const size_t chunk = (size_t) 64 << 20;
+    DevBuf tmp;
+    rc = tmp.ensure(chunk);
+    if (rc) return rc;
+    for (int i = 0; i < n; i++) {
+        for (int64_t o = 0; o < lens[i]; o += (int64_t) chunk) {
+            const int64_t m = lens[i] - o < (int64_t) chunk ? lens[i] - o : (int64_t) chunk;
+            CK(cudaMemcpy(tmp.p, seqs[i] + o, (size_t) m, cudaMemcpyHostToDevice));
+            k_encode_ref<<<1024, 256>>>(tmp.as<uint8_t>(), c->ref.as<uint8_t>() + off[(size_t) i] + o, m);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+        }
+    }
+    tmp.release();
+    CK(cudaMemcpy(c->contig_off.p, off.data(), sizeof(int64_t) * (size_t) (n + 1), cudaMemcpyHostToDevice));
+    c->h_contig_off = off;
+    c->n_contigs = n;
+    return SP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// staging layout: every section 256-byte aligned inside one pinned buffer / one device buffer
+struct Section {
+    size_t off, bytes;
+};
+struct InLayout {
+    Section grp_aln_off, flag, tid, pos, l_qseq, n_cigar, tag_kind, aln_grp, gblk_cap;
+    Section cigar_off, tag_off, seq_off, qual_off, ops_off, imk_off, gpos_off, gent_off, gblk_off, giv_off;
+    Section cigar_pool, tag_pool, seq_pool, qual_pool;
+    size_t total;
+};
+
+static InLayout make_layout(const sp_flat_batch *b, const SpPlan &pl) {
+    InLayout L;
+    size_t o = 0;
+    auto add = [&](Section &s, size_t bytes) {
+        s.off = o;
+        s.bytes = bytes;
+        o = align_up(o + bytes + 16, 256);  // +16: SpByteReader may read one aligned 16-byte word past the end
+    };
+    const size_t G = (size_t) pl.G, A = (size_t) pl.A;
+    add(L.grp_aln_off, 4 * (G + 1));
+    add(L.flag, 4 * A); add(L.tid, 4 * A); add(L.pos, 4 * A); add(L.l_qseq, 4 * A); add(L.n_cigar, 4 * A);
+    add(L.tag_kind, 4 * A); add(L.aln_grp, 4 * A); add(L.gblk_cap, 4 * G);
+    add(L.cigar_off, 8 * (A + 1)); add(L.tag_off, 8 * (A + 1)); add(L.seq_off, 8 * (A + 1)); add(L.qual_off, 8 * (A + 1));
+    add(L.ops_off, 8 * (A + 1)); add(L.imk_off, 8 * (A + 1));
+    add(L.gpos_off, 8 * (G + 1)); add(L.gent_off, 8 * (G + 1)); add(L.gblk_off, 8 * (G + 1)); add(L.giv_off, 8 * (G + 1));
+    add(L.cigar_pool, 4 * (size_t) b->cigar_off[A]);
+    add(L.tag_pool, (size_t) b->tag_off[A]);
+    add(L.seq_pool, (size_t) b->seq_off[A]);
+    add(L.qual_pool, (size_t) b->qual_off[A]);
+    L.total = o;
+    return L;
+}
+
+static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
+    int rc = sp_make_plan(b, c->par.indel_threshold, S.safe_caps, S.plan);
+    if (rc != SP_OK) {
+        set_err("malformed batch (code %d): groups need 1..%d alignments, CIGAR ops limited to MIDSH=X", rc,
+                SP_MAX_ALN_PER_GROUP);
+        return rc;
+    }
+    const SpPlan &pl = S.plan;
+    for (int a = 0; a < pl.A; a++) {
+        if (b->tid[a] < 0 || b->tid[a] >= c->n_contigs) {
+            set_err("alignment %d: tid %d outside the reference table (%d contigs)", a, b->tid[a], c->n_contigs);
+            return SP_EINVAL;
+        }
+    }
+    InLayout L = make_layout(b, pl);
+    rc = S.h_in.ensure(L.total);
+    if (rc) return rc;
+    rc = S.d_in.ensure(L.total);
+    if (rc) return rc;
+    uint8_t *h = S.h_in.as<uint8_t>();
+    const size_t G = (size_t) pl.G, A = (size_t) pl.A;
+    auto put = [&](const Section &s, const void *src) { if (s.bytes) memcpy(h + s.off, src, s.bytes); };
+    put(L.grp_aln_off, b->grp_aln_off);
+    put(L.flag, b->flag); put(L.tid, b->tid); put(L.pos, b->pos); put(L.l_qseq, b->l_qseq); put(L.n_cigar, b->n_cigar);
+    if (b->tag_kind) put(L.tag_kind, b->tag_kind); else memset(h + L.tag_kind.off, 0, L.tag_kind.bytes);
+    put(L.aln_grp, pl.aln_grp.data()); put(L.gblk_cap, pl.gblk_cap.data());
+    put(L.cigar_off, b->cigar_off); put(L.tag_off, b->tag_off); put(L.seq_off, b->seq_off); put(L.qual_off, b->qual_off);
+    put(L.ops_off, pl.ops_off.data()); put(L.imk_off, pl.imk_off.data());
+    put(L.gpos_off, pl.gpos_off.data()); put(L.gent_off, pl.gent_off.data());
+    put(L.gblk_off, pl.gblk_off.data()); put(L.giv_off, pl.giv_off.data());
+    put(L.cigar_pool, b->cigar_pool); put(L.tag_pool, b->tag_pool); put(L.seq_pool, b->seq_pool);
+    put(L.qual_pool, b->qual_pool);
+    memset(h + L.tag_pool.off + L.tag_pool.bytes, 0, 16);
+    S.in_bytes = L.total;
+
+    // device work tables
+    const bool dbg = c->debug_tables;
+    S.debug = dbg;
+    if ((rc = S.ops.ensure(sizeof(SpOp) * (size_t) (pl.total_ops + 1)))) return rc;
+    if ((rc = S.imk.ensure(sizeof(SpInitMarker) * (size_t) (pl.total_imk + 1)))) return rc;
+    if ((rc = S.info.ensure(sizeof(SpAlnInfo) * (A + 1)))) return rc;
+    if ((rc = S.blk.ensure(sizeof(SpBlock) * (size_t) (pl.total_blk + 1)))) return rc;
+    if ((rc = S.iv.ensure(sizeof(SpIv) * (size_t) (pl.total_iv + 1)))) return rc;
+    if ((rc = S.nb.ensure(4 * (A + 1)))) return rc;
+    if ((rc = S.gpos.ensure(4 * (size_t) (pl.total_pos + 1)))) return rc;
+    if ((rc = S.ent.ensure(sizeof(SpEntry) * (size_t) (pl.total_ent + 1)))) return rc;
+    if ((rc = S.res.ensure(4 * (size_t) (pl.total_ent + 1)))) return rc;
+    if (dbg && (rc = S.baq.ensure(4 * (size_t) (pl.total_ent + 1)))) return rc;
+    if ((rc = S.gP.ensure(4 * (G + 1)))) return rc;
+    if ((rc = S.gout.ensure(sizeof(SpGroupOut) * (G + 1)))) return rc;
+    if ((rc = S.gcnt.ensure(sizeof(SpEmitCounts) * (G + 1)))) return rc;
+    if ((rc = S.item_off.ensure(4 * (G + 2)))) return rc;
+    if ((rc = S.row_off.ensure(4 * (G + 2)))) return rc;
+    if ((rc = S.sdbl_off.ensure(8 * (G + 2)))) return rc;
+    if ((rc = S.score.ensure(8 * (A + 1)))) return rc;
+    if ((rc = S.fin_wide.ensure(24 * (size_t) (pl.total_ent + 1)))) return rc;
+    if ((rc = S.fin.ensure(24 * (size_t) (pl.total_ent + 1)))) return rc;
+    if ((rc = S.totals.ensure(sizeof(SpTotals)))) return rc;
+    if ((rc = S.bins.ensure(4 * (size_t) ((SP_N_CLASSES + 1) * SP_SORT_LBINS)))) return rc;
+    if ((rc = S.class_start.ensure(4 * (SP_N_CLASSES + 3)))) return rc;
+    if ((rc = S.h_tot.ensure(sizeof(SpTotals)))) return rc;
+    if ((rc = S.h_gout.ensure(sizeof(SpGroupOut) * (G + 1)))) return rc;
+    if ((rc = S.h_score.ensure(8 * (A + 1)))) return rc;
+    if ((rc = S.h_info.ensure(sizeof(SpAlnInfo) * (A + 1)))) return rc;
+
+    uint8_t *d = S.d_in.as<uint8_t>();
+    SpBatchPtrs &P = S.P;
+    memset(&P, 0, sizeof(P));
+    P.G = pl.G;
+    P.A = pl.A;
+#define DP(T, sec) reinterpret_cast<const T *>(d + L.sec.off)
+    P.grp_aln_off = DP(int32_t, grp_aln_off); P.flag = DP(int32_t, flag); P.tid = DP(int32_t, tid);
+    P.pos = DP(int32_t, pos); P.l_qseq = DP(int32_t, l_qseq); P.n_cigar = DP(int32_t, n_cigar);
+    P.tag_kind = DP(int32_t, tag_kind); P.aln_grp = DP(int32_t, aln_grp); P.gblk_cap = DP(int32_t, gblk_cap);
+    P.cigar_off = DP(int64_t, cigar_off); P.tag_off = DP(int64_t, tag_off); P.seq_off = DP(int64_t, seq_off);
+    P.qual_off = DP(int64_t, qual_off); P.ops_off = DP(int64_t, ops_off); P.imk_off = DP(int64_t, imk_off);
+    P.gpos_off = DP(int64_t, gpos_off); P.gent_off = DP(int64_t, gent_off); P.gblk_off = DP(int64_t, gblk_off);
+    P.giv_off = DP(int64_t, giv_off);
+    P.cigar_pool = DP(uint32_t, cigar_pool); P.tag_pool = DP(uint8_t, tag_pool); P.seq_pool = DP(uint8_t, seq_pool);
+    P.qual_pool = DP(uint8_t, qual_pool);
+#undef DP
+    P.ops = S.ops.as<SpOp>(); P.imk = S.imk.as<SpInitMarker>(); P.info = S.info.as<SpAlnInfo>();
+    P.blk = S.blk.as<SpBlock>(); P.iv = S.iv.as<SpIv>(); P.nb = S.nb.as<int32_t>(); P.gpos = S.gpos.as<int32_t>();
+    P.ent = S.ent.as<SpEntry>(); P.res = S.res.as<int32_t>(); P.baq = dbg ? S.baq.as<int32_t>() : nullptr;
+    P.gP = S.gP.as<int32_t>(); P.gout = S.gout.as<SpGroupOut>(); P.gcnt = S.gcnt.as<SpEmitCounts>();
+    P.item_off = S.item_off.as<int32_t>(); P.row_off = S.row_off.as<int32_t>(); P.sdbl_off = S.sdbl_off.as<int64_t>();
+    P.score = S.score.as<double>(); P.fin_wide = S.fin_wide.as<int32_t>(); P.fin = S.fin.as<int32_t>();
+    P.ref = c->ref.as<uint8_t>(); P.contig_off = c->contig_off.as<int64_t>(); P.n_contigs = c->n_contigs;
+    return SP_OK;
+}
+
+// enqueue kernels for the batch staged in S (device copy already enqueued or resident)
+static int run_pipeline(sp_ctx *c, Slot &S) {
+    cudaStream_t st = S.stream;
+    const SpBatchPtrs &P = S.P;
+    const SpConst *dC = c->dC.as<SpConst>();
+    S.launches = 0;
+    CK(cudaMemsetAsync(S.totals.p, 0, sizeof(SpTotals), st));
+    CK(cudaMemsetAsync(S.res.p, 0xff, 4 * (size_t) (S.plan.total_ent + 1), st));  // SP_RES_RAW == -1
+    if (P.A > 0) {
+        k_walk<<<(P.A + 127) / 128, 128, 0, st>>>(P, dC);
+        S.launches++;
+    }
+    CK(cudaEventRecord(S.ev[EV_WALK], st));
+    if (P.G > 0) {
+        k_group<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC);
+        S.launches++;
+    }
+    k_scan_groups<<<1, 1024, 0, st>>>(P, S.totals.as<SpTotals>());
+    S.launches++;
+    CK(cudaEventRecord(S.ev[EV_GROUP], st));
+    // the one mid-pipeline read-back: instance / row / band totals size the HMM launch
+    CK(cudaMemcpyAsync(S.h_tot.p, S.totals.p, sizeof(SpTotals), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    S.tot = *S.h_tot.as<SpTotals>();
+    const SpTotals &T = S.tot;
+    int rc;
+    if ((rc = S.items.ensure(sizeof(SpItem) * (size_t) (T.n_items + 1)))) return rc;
+    if ((rc = S.rows.ensure(sizeof(SpRow) * (size_t) (T.n_rows + 1)))) return rc;
+    if ((rc = S.order.ensure(4 * (size_t) (T.n_items + 1)))) return rc;
+    if ((rc = S.s_pool.ensure(8 * (size_t) (T.s_doubles + 2)))) return rc;
+    const int64_t fs_stride = 2 * (2 * (int64_t) T.max_bw + 1);
+    if ((rc = S.fsave.ensure(8 * (size_t) ((int64_t) T.n_rows * fs_stride + 2)))) return rc;
+    if (P.G > 0 && T.n_items > 0) {
+        k_emit<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC, S.items.as<SpItem>(), S.rows.as<SpRow>());
+        const int nbins = (SP_N_CLASSES + 1) * SP_SORT_LBINS;
+        CK(cudaMemsetAsync(S.bins.p, 0, 4 * (size_t) nbins, st));
+        k_sort_hist<<<(T.n_items + 255) / 256, 256, 0, st>>>(S.items.as<SpItem>(), T.n_items, S.bins.as<int32_t>());
+        k_sort_scan<<<1, 1024, 0, st>>>(S.bins.as<int32_t>(), nbins, S.class_start.as<int32_t>());
+        k_sort_scatter<<<(T.n_items + 255) / 256, 256, 0, st>>>(S.items.as<SpItem>(), T.n_items, S.bins.as<int32_t>(),
+                                                                  S.order.as<int32_t>());
+        S.launches += 4;
+    }
+    CK(cudaEventRecord(S.ev[EV_EMIT], st));
+    if (T.n_items > 0) {
+        int first = 0;
+        for (int cls = 0; cls < SP_N_CLASSES; cls++) {
+            const int cnt = T.class_count[cls];
+            if (cnt == 0) continue;
+            int W = sp_class_cells(cls);
+            double *gband = nullptr;
+            size_t smem = 0;
+            const int nblk = (cnt + 31) / 32;
+            if (W == 0 || (size_t) W * 28 * 32 > c->max_smem) {
+                W = 2 * T.max_bw + 2;
+                if ((rc = S.gband.ensure((size_t) nblk * ((size_t) W * 28 * 32)))) return rc;
+                gband = S.gband.as<double>();
+            } else {
+                smem = (size_t) W * 28 * 32;
+            }
+            k_hmm<<<nblk, 32, smem, st>>>(dC, S.items.as<SpItem>(), S.order.as<int32_t>(), first, cnt, W, P.ref, nullptr,
+                                          P.seq_pool, P.seq_off, S.s_pool.as<double>(), S.fsave.as<double>(),
+                                          fs_stride, S.rows.as<SpRow>(), gband);
+            S.launches++;
+            first += cnt;
+        }
+    }
+    CK(cudaEventRecord(S.ev[EV_HMM], st));
+    if (P.G > 0) {
+        k_score<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC, S.rows.as<SpRow>(), c->par.prim_margin_score,
+                                                (double) c->par.min_score, S.totals.as<SpTotals>());
+        S.launches++;
+    }
+    CK(cudaEventRecord(S.ev[EV_SCORE], st));
+    CK(cudaGetLastError());
+    return SP_OK;
+}
+
+static int enqueue_results(Slot &S) {
+    cudaStream_t st = S.stream;
+    const size_t G = (size_t) S.P.G, A = (size_t) S.P.A;
+    CK(cudaMemcpyAsync(S.h_tot.p, S.totals.p, sizeof(SpTotals), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(S.h_gout.p, S.gout.p, sizeof(SpGroupOut) * G, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(S.h_score.p, S.score.p, 8 * A, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(S.h_info.p, S.info.p, sizeof(SpAlnInfo) * A, cudaMemcpyDeviceToHost, st));
+    S.d2h_bytes = (int64_t) (sizeof(SpTotals) + sizeof(SpGroupOut) * G + 8 * A + sizeof(SpAlnInfo) * A);
+    return SP_OK;
+}
+
+extern "C" {
+
+int sp_submit(sp_ctx *c, const sp_flat_batch *b, int slot) {
+    if (!c || !b || slot < 0 || slot >= SP_N_SLOTS) return SP_EINVAL;
+    if (c->n_contigs == 0) {
+        set_err("sp_submit before sp_set_reference_*");
+        return SP_ESTATE;
+    }
+    CK(cudaSetDevice(c->device));
+    Slot &S = c->slot[slot];
+    if (S.state == 2) {
+        set_err("slot %d still in flight; call sp_wait first", slot);
+        return SP_ESTATE;
+    }
+    S.safe_caps = false;
+    int rc = stage_batch(c, S, b);
+    if (rc) return rc;
+    CK(cudaEventRecord(S.ev[EV_START], S.stream));
+    CK(cudaMemcpyAsync(S.d_in.p, S.h_in.p, S.in_bytes, cudaMemcpyHostToDevice, S.stream));
+    CK(cudaEventRecord(S.ev[EV_H2D], S.stream));
+    S.h2d_bytes = (int64_t) S.in_bytes;
+    rc = run_pipeline(c, S);
+    if (rc) return rc;
+    rc = enqueue_results(S);
+    if (rc) return rc;
+    S.state = 2;
+    S.want_d2h = true;
+    return SP_OK;
+}
+
+int sp_upload(sp_ctx *c, const sp_flat_batch *b, int slot) {
+    if (!c || !b || slot < 0 || slot >= SP_N_SLOTS) return SP_EINVAL;
+    if (c->n_contigs == 0) return SP_ESTATE;
+    CK(cudaSetDevice(c->device));
+    Slot &S = c->slot[slot];
+    S.safe_caps = false;
+    int rc = stage_batch(c, S, b);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(S.d_in.p, S.h_in.p, S.in_bytes, cudaMemcpyHostToDevice, S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+    S.h2d_bytes = 0;
+    S.state = 1;
+    return SP_OK;
+}
+
+int sp_run_resident(sp_ctx *c, int slot) {
+    if (!c || slot < 0 || slot >= SP_N_SLOTS) return SP_EINVAL;
+    CK(cudaSetDevice(c->device));
+    Slot &S = c->slot[slot];
+    if (S.state == 0) {
+        set_err("slot %d has no uploaded batch", slot);
+        return SP_ESTATE;
+    }
+    CK(cudaEventRecord(S.ev[EV_START], S.stream));
+    CK(cudaEventRecord(S.ev[EV_H2D], S.stream));
+    int rc = run_pipeline(c, S);
+    if (rc) return rc;
+    rc = enqueue_results(S);
+    if (rc) return rc;
+    S.state = 2;
+    return SP_OK;
+}
+
+int sp_wait(sp_ctx *c, int slot, sp_result *out) {
+    if (!c || slot < 0 || slot >= SP_N_SLOTS || !out) return SP_EINVAL;
+    CK(cudaSetDevice(c->device));
+    Slot &S = c->slot[slot];
+    if (S.state != 2) {
+        set_err("slot %d has nothing in flight", slot);
+        return SP_ESTATE;
+    }
+    CK(cudaStreamSynchronize(S.stream));
+    SpTotals T = *S.h_tot.as<SpTotals>();
+    // second, exact-size copy: the compact final-marker table
+    int rc = S.h_fin.ensure(24 * (size_t) (T.fin_rows + 1));
+    if (rc) return rc;
+    if (T.fin_rows > 0)
+        CK(cudaMemcpyAsync(S.h_fin.p, S.fin.p, 24 * (size_t) T.fin_rows, cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaEventRecord(S.ev[EV_END], S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+    S.d2h_bytes += 24 * (int64_t) T.fin_rows;
+    S.state = 3;
+    if (T.err & SP_GERR_BADOP) {
+        set_err("batch contains CIGAR operations the reference does not define (N/P)");
+        return SP_EUNSUPPORTED;
+    }
+    if (T.err & (SP_GERR_BLOCK_CAP | SP_GERR_MARKER_CAP | SP_GERR_OP_CAP)) {
+        set_err("internal table bound exceeded (flags %d)", T.err);
+        return SP_ECAPACITY;
+    }
+    const int G = S.P.G, A = S.P.A;
+    const SpGroupOut *go = S.h_gout.as<SpGroupOut>();
+    const double *sc = S.h_score.as<double>();
+    const SpAlnInfo *inf = S.h_info.as<SpAlnInfo>();
+    const int32_t *fin = S.h_fin.as<int32_t>();
+    const int32_t *gao = S.h_in.as<int32_t>();  // grp_aln_off is the first staged section
+    S.r_group.resize((size_t) G * SP_GROUP_W);
+    S.r_marker_off.resize((size_t) G + 1);
+    S.r_marker.resize((size_t) T.fin_rows * SP_MARKER_W);
+    S.r_score.assign(sc, sc + A);
+    S.r_extent.resize((size_t) A * 4);
+    for (int a = 0; a < A; a++) {
+        S.r_extent[(size_t) a * 4 + 0] = inf[a].rfs;
+        S.r_extent[(size_t) a * 4 + 1] = inf[a].rfe;
+        S.r_extent[(size_t) a * 4 + 2] = inf[a].rds_f;
+        S.r_extent[(size_t) a * 4 + 3] = inf[a].rde_f;
+    }
+    int64_t mo = 0;
+    for (int g = 0; g < G; g++) {
+        const SpGroupOut &o = go[g];
+        const int a0 = gao[g], n = gao[g + 1] - a0;
+        // tie-break RNG replay in submission order (ptAlignment.c:156-171)
+        const int best = sp_finalize_best(c->rng, n, sc + a0, o.prim_idx, o.max_idx, o.tie_mask,
+                                          c->par.prim_margin_score, (double) c->par.min_score,
+                                          c->par.prim_margin_random);
+        int32_t *row = &S.r_group[(size_t) g * SP_GROUP_W];
+        row[0] = best; row[1] = o.prim_idx; row[2] = o.n_init; row[3] = o.n_after_allmm; row[4] = o.n_filled;
+        row[5] = o.n_after_ins; row[6] = o.margin_eff; row[7] = o.conf_len; row[8] = o.n_final; row[9] = o.scored;
+        S.r_marker_off[(size_t) g] = mo;
+        if (o.n_final > 0)
+            memcpy(&S.r_marker[(size_t) mo * SP_MARKER_W], fin + (size_t) o.fin_off * 6, 24 * (size_t) o.n_final);
+        mo += o.n_final;
+    }
+    S.r_marker_off[(size_t) G] = mo;
+    memset(out, 0, sizeof(*out));
+    out->n_groups = G;
+    out->n_alns = A;
+    out->group = S.r_group.data();
+    out->score = S.r_score.data();
+    out->extent = S.r_extent.data();
+    out->marker_off = S.r_marker_off.data();
+    out->marker = S.r_marker.data();
+    out->hmm_instances = T.n_items;
+    out->hmm_cells = T.cells;
+    out->h2d_bytes = S.h2d_bytes;
+    out->d2h_bytes = S.d2h_bytes;
+    out->gpu_launches = S.launches;
+    float ms = 0;
+    const int order[8] = {EV_START, EV_H2D, EV_WALK, EV_GROUP, EV_EMIT, EV_HMM, EV_SCORE, EV_END};
+    for (int k = 0; k < 7; k++) {
+        ms = 0;
+        cudaEventElapsedTime(&ms, S.ev[order[k]], S.ev[order[k + 1]]);
+        out->ms_stage[k] = ms;
+    }
+    out->ms_stage[7] = 0;
+    cudaEventElapsedTime(&ms, S.ev[EV_START], S.ev[EV_END]);
+    out->ms_total = ms;
+    out->ms_hmm = out->ms_stage[4];
+    return SP_OK;
+}
+
+int64_t sp_debug_table(sp_ctx *c, int slot, int what, const int32_t **rows_out, const int64_t **off_out) {
+    if (!c || slot < 0 || slot >= SP_N_SLOTS) return SP_EINVAL;
+    if (what == -1) {  // switch: keep the post-BAQ qualities of later batches
+        c->debug_tables = true;
+        return 0;
+    }
+    if (!rows_out) return SP_EINVAL;
+    if (cudaSetDevice(c->device) != cudaSuccess) return SP_ECUDA;
+    Slot &S = c->slot[slot];
+    if (S.state != 3) {
+        set_err("sp_debug_table: slot %d has no completed batch", slot);
+        return SP_ESTATE;
+    }
+    const SpPlan &pl = S.plan;
+    const int G = pl.G, A = pl.A;
+    const int32_t *gao = S.h_in.as<int32_t>();
+    S.dbg_rows.clear();
+    S.dbg_off.clear();
+    if (off_out) *off_out = nullptr;
+#define D2H(vec, T, buf, count)                                                                            \
+    std::vector<T> vec((size_t) (count) + 1);                                                              \
+    if ((count) > 0 && cudaMemcpy(vec.data(), (buf).p, sizeof(T) * (size_t) (count), cudaMemcpyDeviceToHost) != cudaSuccess) \
+        return SP_ECUDA;
+    if (what == 0 || what == 1) {
+        if (what == 1 && !S.debug) {
+            set_err("post-BAQ table needs sp_debug_table(ctx,0,-1,...) before the submit");
+            return SP_ESTATE;
+        }
+        D2H(gP, int32_t, S.gP, G);
+        D2H(gpos, int32_t, S.gpos, pl.total_pos);
+        D2H(ent, SpEntry, S.ent, pl.total_ent);
+        std::vector<int32_t> baq;
+        if (what == 1) {
+            baq.resize((size_t) pl.total_ent + 1);
+            if (pl.total_ent > 0 &&
+                cudaMemcpy(baq.data(), S.baq.p, 4 * (size_t) pl.total_ent, cudaMemcpyDeviceToHost) != cudaSuccess)
+                return SP_ECUDA;
+        }
+        S.dbg_off.push_back(0);
+        for (int g = 0; g < G; g++) {
+            const int n = gao[g + 1] - gao[g];
+            for (int p = 0; p < gP[(size_t) g]; p++)
+                for (int i = 0; i < n; i++) {
+                    const size_t e = (size_t) pl.gent_off[(size_t) g] + (size_t) p * n + i;
+                    const int32_t row[6] = {i, gpos[(size_t) pl.gpos_off[(size_t) g] + p], ent[e].base_idx,
+                                            what == 1 ? baq[e] : ent[e].q, ent[e].flags & 1, ent[e].ref_pos};
+                    S.dbg_rows.insert(S.dbg_rows.end(), row, row + 6);
+                }
+            S.dbg_off.push_back((int64_t) S.dbg_rows.size() / 6);
+        }
+        *rows_out = S.dbg_rows.data();
+        if (off_out) *off_out = S.dbg_off.data();
+        return (int64_t) S.dbg_rows.size() / 6;
+    }
+    if (what == 2) {
+        D2H(nb, int32_t, S.nb, A);
+        D2H(blk, SpBlock, S.blk, pl.total_blk);
+        S.dbg_off.push_back(0);
+        for (int g = 0; g < G; g++) {
+            const int a0 = gao[g], n = gao[g + 1] - a0;
+            for (int i = 0; i < n; i++) {
+                const SpBlock *bl = blk.data() + pl.gblk_off[(size_t) g] + (int64_t) i * pl.gblk_cap[(size_t) g];
+                for (int k = 0; k < nb[(size_t) (a0 + i)]; k++) {
+                    const int32_t row[6] = {bl[k].rfs, bl[k].rfe, bl[k].sqs, bl[k].sqe, bl[k].rds_f, bl[k].rde_f};
+                    S.dbg_rows.insert(S.dbg_rows.end(), row, row + 6);
+                }
+                S.dbg_off.push_back((int64_t) S.dbg_rows.size() / 6);
+            }
+        }
+        *rows_out = S.dbg_rows.data();
+        if (off_out) *off_out = S.dbg_off.data();
+        return (int64_t) S.dbg_rows.size() / 6;
+    }
+    if (what == 3) {
+        D2H(items, SpItem, S.items, S.tot.n_items);
+        for (int k = 0; k < S.tot.n_items; k++) {
+            const SpItem &I = items[(size_t) k];
+            const int32_t row[SP_HMM_W] = {I.aln, I.l_ref, I.l_query, I.par_bw, I.blk, I.row0, I.n_rows, 0};
+            S.dbg_rows.insert(S.dbg_rows.end(), row, row + SP_HMM_W);
+        }
+        *rows_out = S.dbg_rows.data();
+        return S.tot.n_items;
+    }
+    if (what == 4) {
+        D2H(rows, SpRow, S.rows, S.tot.n_rows);
+        for (int k = 0; k < S.tot.n_rows; k++) {
+            const int32_t row[4] = {rows[(size_t) k].item, rows[(size_t) k].t, rows[(size_t) k].state, rows[(size_t) k].q};
+            S.dbg_rows.insert(S.dbg_rows.end(), row, row + 4);
+        }
+        *rows_out = S.dbg_rows.data();
+        return S.tot.n_rows;
+    }
+#undef D2H
+    return SP_EINVAL;
+}
+
+int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *ref_off, const int32_t *l_ref,
+                 const uint8_t *query_pool, const int64_t *query_off, const int32_t *l_query, const int32_t *par_bw,
+                 const int64_t *row_off, const int32_t *rows_t, int32_t *state_out, uint8_t *q_out, double *pmax_out,
+                 float *ms_kernel) {
+    if (!c || n < 0 || !ref_pool || !ref_off || !l_ref || !query_pool || !query_off || !l_query || !par_bw ||
+        !row_off || !rows_t || !state_out || !q_out)
+        return SP_EINVAL;
+    if (n == 0) return SP_OK;
+    CK(cudaSetDevice(c->device));
+    // instance + row tables
+    std::vector<SpItem> items((size_t) n);
+    const int64_t n_rows = row_off[n];
+    std::vector<SpRow> rows((size_t) n_rows + 1);
+    int64_t ref_total = 0, q_total = 0, s_total = 0;
+    int max_bw = 0;
+    int cls_count[SP_N_CLASSES] = {0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < n; j++) {
+        if (l_ref[j] <= 0 || l_query[j] <= 0) {
+            set_err("sp_hmm_batch: instance %d has an empty sequence", j);
+            return SP_EINVAL;
+        }
+        SpItem &I = items[(size_t) j];
+        I.ref_off = ref_off[j];
+        I.aln = -1;
+        I.blk = 0;
+        I.l_ref = l_ref[j];
+        I.l_query = l_query[j];
+        I.q_sqs = 0;
+        I.par_bw = par_bw[j];
+        I.row0 = (int32_t) row_off[j];
+        I.n_rows = (int32_t) (row_off[j + 1] - row_off[j]);
+        I.query_off = query_off[j];
+        I.s_off = s_total;
+        s_total += l_query[j] + 2;
+        if (ref_off[j] + l_ref[j] > ref_total) ref_total = ref_off[j] + l_ref[j];
+        if (query_off[j] + l_query[j] > q_total) q_total = query_off[j] + l_query[j];
+        const int bw = sp_hmm_bw(I.l_ref, I.l_query, I.par_bw);
+        if (bw > max_bw) max_bw = bw;
+        if (I.n_rows > 0) cls_count[sp_band_class6(bw)]++;
+        for (int64_t r = row_off[j]; r < row_off[j + 1]; r++) {
+            SpRow &R = rows[(size_t) r];
+            R.item = j;
+            R.t = rows_t[r];
+            R.entry = -1;
+            R.expected = 0;
+            R.state = 0;
+            R.q = 0;
+            R.pmax = 0;
+            if (R.t < 0 || R.t >= I.l_query || (r > row_off[j] && rows_t[r] <= rows_t[r - 1])) {
+                set_err("sp_hmm_batch: rows of instance %d must be ascending and inside [0,l_query)", j);
+                return SP_EINVAL;
+            }
+        }
+    }
+    Slot &S = c->slot[0];
+    cudaStream_t st = S.stream;
+    DevBuf d_ref, d_q;
+    int rc;
+    if ((rc = d_ref.ensure((size_t) ref_total + 16))) return rc;
+    if ((rc = d_q.ensure((size_t) q_total + 16))) return rc;
+    if ((rc = S.items.ensure(sizeof(SpItem) * (size_t) n))) return rc;
+    if ((rc = S.rows.ensure(sizeof(SpRow) * (size_t) (n_rows + 1)))) return rc;
+    if ((rc = S.order.ensure(4 * (size_t) n))) return rc;
+    if ((rc = S.s_pool.ensure(8 * (size_t) (s_total + 2)))) return rc;
+    const int64_t fs_stride = 2 * (2 * (int64_t) max_bw + 1);
+    if ((rc = S.fsave.ensure(8 * (size_t) (n_rows * fs_stride + 2)))) return rc;
+    if ((rc = S.bins.ensure(4 * (size_t) ((SP_N_CLASSES + 1) * SP_SORT_LBINS)))) return rc;
+    if ((rc = S.class_start.ensure(4 * (SP_N_CLASSES + 3)))) return rc;
+    CK(cudaMemcpyAsync(d_ref.p, ref_pool, (size_t) ref_total, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_q.p, query_pool, (size_t) q_total, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.items.p, items.data(), sizeof(SpItem) * (size_t) n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.rows.p, rows.data(), sizeof(SpRow) * (size_t) n_rows, cudaMemcpyHostToDevice, st));
+    const int nbins = (SP_N_CLASSES + 1) * SP_SORT_LBINS;
+    CK(cudaMemsetAsync(S.bins.p, 0, 4 * (size_t) nbins, st));
+    k_sort_hist<<<(n + 255) / 256, 256, 0, st>>>(S.items.as<SpItem>(), n, S.bins.as<int32_t>());
+    k_sort_scan<<<1, 1024, 0, st>>>(S.bins.as<int32_t>(), nbins, S.class_start.as<int32_t>());
+    k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(S.items.as<SpItem>(), n, S.bins.as<int32_t>(), S.order.as<int32_t>());
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    CK(cudaEventRecord(e0, st));
+    int first = 0;
+    for (int cls = 0; cls < SP_N_CLASSES; cls++) {
+        const int cnt = cls_count[cls];
+        if (cnt == 0) continue;
+        int W = sp_class_cells(cls);
+        double *gband = nullptr;
+        size_t smem = 0;
+        const int nblk = (cnt + 31) / 32;
+        if (W == 0 || (size_t) W * 28 * 32 > c->max_smem) {
+            W = 2 * max_bw + 2;
+            if ((rc = S.gband.ensure((size_t) nblk * ((size_t) W * 28 * 32)))) return rc;
+            gband = S.gband.as<double>();
+        } else {
+            smem = (size_t) W * 28 * 32;
+        }
+        k_hmm<<<nblk, 32, smem, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(), first, cnt, W,
+                                      d_ref.as<uint8_t>(), d_q.as<uint8_t>(), nullptr, nullptr, S.s_pool.as<double>(),
+                                      S.fsave.as<double>(), fs_stride, S.rows.as<SpRow>(), gband);
+        first += cnt;
+    }
+    CK(cudaEventRecord(e1, st));
+    CK(cudaMemcpyAsync(rows.data(), S.rows.p, sizeof(SpRow) * (size_t) n_rows, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (ms_kernel) cudaEventElapsedTime(ms_kernel, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    for (int64_t r = 0; r < n_rows; r++) {
+        state_out[r] = rows[(size_t) r].state;
+        q_out[r] = (uint8_t) rows[(size_t) r].q;
+        if (pmax_out) pmax_out[r] = rows[(size_t) r].pmax;
+    }
+    d_ref.release();
+    d_q.release();
+    return SP_OK;
+}
+
+int sp_fp64_peak(sp_ctx *c, int mode, double *ops_per_s, float *ms_out) {
+    if (!c || !ops_per_s) return SP_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const int blocks = c->sm_count * 8, threads = 256, iters = 1 << 16;
+    DevBuf out;
+    int rc = out.ensure(8 * (size_t) blocks * threads);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_fp64_peak<<<blocks, threads>>>(out.as<double>(), 1024, mode);  // warm-up
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, threads>>>(out.as<double>(), iters, mode);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    out.release();
+    *ops_per_s = (double) blocks * threads * 8.0 * iters / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return SP_OK;
+}
+
+}  // extern "C"

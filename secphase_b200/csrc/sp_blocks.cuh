@@ -261,17 +261,14 @@ struct SpEmitCounts {
     int64_t cells;
     int64_t s_doubles;  // sum over items of (l_query + 2)
     int32_t max_bw;
-    int32_t class_count[5];
+    int32_t class_count[SP_N_CLASSES];  // instances with at least one marker row, per band class
 };
-
-SP_HD int sp_band_class(int bw) { return bw <= 22 ? 0 : bw <= 30 ? 1 : bw <= 62 ? 2 : bw <= 120 ? 3 : 4; }
-SP_HD int sp_class_width(int cls) { return cls == 0 ? 46 : cls == 1 ? 62 : cls == 2 ? 126 : cls == 3 ? 242 : 0; }
 
 template <bool EMIT>
 SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, int P, const SpEntry *entries,
                              const SpBlock *blocks, int n_blocks, int64_t ref_base, int64_t entry_base,
                              SpEmitCounts &cnt, int32_t *res, SpItem *items, int item_base, SpRow *rows,
-                             int row_base) {
+                             int row_base, int64_t s_base) {
     const int n = G.n, a = G.a0 + i;
     const bool rev = (G.flag[a] & SP_FREVERSE) != 0;
     const SpOp *ops = G.ops + G.ops_off[a];
@@ -378,6 +375,7 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
                 it.row0 = first_row;
                 it.n_rows = n_rows;
                 it.query_off = -1;
+                it.s_off = s_base + cnt.s_doubles;
                 items[item_idx] = it;
             }
             cnt.n_items += 1;
@@ -385,7 +383,7 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
             cnt.cells += sp_hmm_cells(l_ref, l_query, bw);
             cnt.s_doubles += l_query + 2;
             if (bw > cnt.max_bw) cnt.max_bw = bw;
-            cnt.class_count[sp_band_class(bw)] += 1;
+            if (n_rows > 0) cnt.class_count[sp_band_class6(bw)] += 1;
         }
         while (SP_MK_VALID(j) && SP_MK_BASE(j) <= blk.sqe) {
             if (blk.sqe - SP_BLOCK_MARGIN <= SP_MK_BASE(j)) {

@@ -63,6 +63,7 @@ struct SpItem {  // one probaln_glocal call of calc_local_baq, ptMarker.c:725-75
     int32_t row0;     // first marker-row slot
     int32_t n_rows;
     int64_t query_off;  // stand-alone API: offset into a byte-per-base query pool; pipeline: -1
+    int64_t s_off;      // this instance's slice of the scaling-factor pool (l_query+2 doubles)
 };
 
 struct SpRow {  // one query row whose MAP state/q is consumed (a marker inside an HMM window)
@@ -100,6 +101,12 @@ struct SpConst {
 
 // group status bits
 enum { SP_GERR_BLOCK_CAP = 1, SP_GERR_MARKER_CAP = 2, SP_GERR_OP_CAP = 4, SP_GERR_BADOP = 8 };
+
+// Band classes of the HMM kernel: instances of one class share a launch (same shared-memory
+// footprint); cells = circular band cells per lane (>= 2*bw+2); class 5 is sized per launch.
+#define SP_N_CLASSES 6
+SP_HD int sp_band_class6(int bw) { return bw <= 20 ? 0 : bw <= 22 ? 1 : bw <= 30 ? 2 : bw <= 62 ? 3 : bw <= 120 ? 4 : 5; }
+SP_HD int sp_class_cells(int cls) { return cls == 0 ? 42 : cls == 1 ? 46 : cls == 2 ? 62 : cls == 3 ? 126 : cls == 4 ? 242 : 0; }
 
 SP_HD int sp_min(int a, int b) { return a < b ? a : b; }
 SP_HD int sp_max(int a, int b) { return b < a ? a : b; }

@@ -1,0 +1,373 @@
+// sp_kernels.cuh -- __global__ kernels of the marker-mode scoring pipeline (sm_100a).
+//
+//   k_walk            K1  thread per alignment     CIGAR/cs walk -> op table, extents, markers, confident blocks
+//   k_group           K2+K3 thread per read group  marker merge/filter, consensus-block loop, HMM count pass
+//   k_scan_groups         one CTA                  exclusive scans -> per-group item/row/s offsets + totals
+//   k_emit            K3b thread per read group    HMM instances + marker rows (deterministic placement)
+//   k_sort_*              counting sort of instances by (band class, length) for lock-step warps
+//   k_hmm             K4  lane per HMM instance    the FP64 forward/backward kernel (sp_hmm.cuh)
+//   k_score           K5  thread per read group    BAQ at markers, filter, scores, selection
+// No tensor cores: none of this is a dense contraction.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sp_blocks.cuh"
+#include "sp_common.h"
+#include "sp_hmm.cuh"
+#include "sp_markers.cuh"
+#include "sp_score.cuh"
+#include "sp_walk.cuh"
+
+#define SP_SORT_LBINS 2048
+
+struct SpTotals {  // device-side counters of one batch, read back once mid-pipeline
+    int32_t n_items, n_rows;
+    int64_t cells;
+    int64_t s_doubles;
+    int32_t max_bw, pad;
+    int32_t class_count[SP_N_CLASSES];
+    int32_t fin_rows;  // compact final-marker rows reserved so far
+    int32_t err;
+};
+
+struct SpBatchPtrs {
+    int32_t G, A;
+    // uploaded
+    const int32_t *grp_aln_off, *flag, *tid, *pos, *l_qseq, *n_cigar, *tag_kind, *aln_grp, *gblk_cap;
+    const int64_t *cigar_off, *tag_off, *seq_off, *qual_off, *ops_off, *imk_off, *gpos_off, *gent_off, *gblk_off,
+        *giv_off;
+    const uint32_t *cigar_pool;
+    const uint8_t *tag_pool, *seq_pool, *qual_pool;
+    // device work tables
+    SpOp *ops;
+    SpInitMarker *imk;
+    SpAlnInfo *info;
+    SpBlock *blk;
+    SpIv *iv;
+    int32_t *nb;
+    int32_t *gpos;
+    SpEntry *ent;
+    int32_t *res;
+    int32_t *baq;      // optional (debug)
+    int32_t *gP;
+    SpGroupOut *gout;
+    SpEmitCounts *gcnt;
+    int32_t *item_off, *row_off;
+    int64_t *sdbl_off;
+    double *score;
+    int32_t *fin_wide;  // [total_ent][6] worst-case placement
+    int32_t *fin;       // compact
+    // reference
+    const uint8_t *ref;
+    const int64_t *contig_off;
+    int32_t n_contigs;
+};
+
+__device__ __forceinline__ SpGroupAlnView sp_make_view(const SpBatchPtrs &B, int g) {
+    SpGroupAlnView V;
+    V.a0 = B.grp_aln_off[g];
+    V.n = B.grp_aln_off[g + 1] - V.a0;
+    V.flag = B.flag;
+    V.l_qseq = B.l_qseq;
+    V.qual_off = B.qual_off;
+    V.qual_pool = B.qual_pool;
+    V.info = B.info;
+    V.ops_off = B.ops_off;
+    V.ops = B.ops;
+    V.imk_off = B.imk_off;
+    V.imk = B.imk;
+    return V;
+}
+
+__global__ void __launch_bounds__(128) k_walk(SpBatchPtrs B, const SpConst *__restrict__ Cp) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= B.A) return;
+    const int g = B.aln_grp[a];
+    const int i = a - B.grp_aln_off[g];
+    const int cap = B.gblk_cap[g];
+    SpBlock *cb = B.blk + B.gblk_off[g] + (int64_t) i * cap;
+    SpAlnInfo info;
+    sp_walk_alignment(Cp->indel_threshold, Cp->min_q, B.flag[a], B.pos[a], B.l_qseq[a], B.n_cigar[a],
+                      B.cigar_pool + B.cigar_off[a], B.tag_pool, B.tag_off[a], B.tag_off[a + 1],
+                      B.tag_kind[a], B.qual_pool + B.qual_off[a], B.ops + B.ops_off[a],
+                      (int) (B.ops_off[a + 1] - B.ops_off[a] - 1), B.imk + B.imk_off[a],
+                      (int) (B.imk_off[a + 1] - B.imk_off[a]), cb, cap, &info);
+    B.info[a] = info;
+    B.nb[a] = info.n_cb;
+}
+
+__global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__restrict__ Cp) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B.G) return;
+    const SpConst &C = *Cp;
+    SpGroupAlnView V = sp_make_view(B, g);
+    SpGroupOut o;
+    memset(&o, 0, sizeof(o));
+    int err = 0;
+    for (int i = 0; i < V.n; i++) err |= B.info[V.a0 + i].err;
+    int32_t counts[4];
+    int32_t *gpos = B.gpos + B.gpos_off[g];
+    SpEntry *ent = B.ent + B.gent_off[g];
+    const int P = sp_group_markers(V, gpos, ent, (int) (B.gpos_off[g + 1] - B.gpos_off[g]), counts, &err);
+    B.gP[g] = P;
+    o.n_init = counts[0];
+    o.n_after_allmm = counts[1];
+    o.n_filled = counts[2];
+    o.n_after_ins = counts[3];
+    SpBlockWork W;
+    W.cap = B.gblk_cap[g];
+    W.ab = B.blk + B.gblk_off[g];
+    W.nb = B.nb + V.a0;
+    W.cons_a = B.iv + B.giv_off[g];
+    W.cons_b = W.cons_a + W.cap;
+    W.flank = W.cons_b + W.cap;
+    int margin = C.flank_margin, conf_len = 1;
+    bool scored = false;
+    SpEmitCounts cnt;
+    memset(&cnt, 0, sizeof(cnt));
+    if (P > 0) {
+        conf_len = sp_consensus_loop(C, V, P, gpos, W, &margin, &err);
+        if (conf_len > 0 || !C.consensus) {
+            scored = true;
+            if (C.baq_flag) {
+                for (int i = 0; i < V.n; i++) {
+                    const int a = V.a0 + i;
+                    sp_emit_alignment<false>(C, V, i, P, ent, W.ab + (int64_t) i * W.cap, W.nb[i],
+                                             B.contig_off[B.tid[a]], 0, cnt, nullptr, nullptr, 0, nullptr, 0, 0);
+                }
+            }
+        }
+    } else {
+        for (int i = 0; i < V.n; i++) W.nb[i] = 0;  // secphase.c:161: no markers, no confident blocks
+    }
+    B.gcnt[g] = cnt;
+    o.margin_eff = margin;
+    o.conf_len = conf_len;
+    o.scored = scored ? 1 : 0;
+    o.err = err;
+    B.gout[g] = o;
+}
+
+// exclusive scans over groups (one CTA of 1024 threads); also accumulates the batch totals
+__global__ void __launch_bounds__(1024) k_scan_groups(SpBatchPtrs B, SpTotals *tot) {
+    __shared__ int32_t s_items[1024], s_rows[1024];
+    __shared__ int64_t s_sd[1024], s_cells[1024];
+    __shared__ int32_t s_cls[SP_N_CLASSES], s_maxbw;
+    const int t = threadIdx.x, G = B.G;
+    const int per = (G + 1023) / 1024;
+    const int g0 = t * per, g1 = min(G, g0 + per);
+    if (t < SP_N_CLASSES) s_cls[t] = 0;
+    if (t == 0) s_maxbw = 0;
+    __syncthreads();
+    int32_t li = 0, lr = 0, lbw = 0;
+    int64_t ls = 0, lc = 0;
+    int32_t lcls[SP_N_CLASSES] = {0, 0, 0, 0, 0, 0};
+    for (int g = g0; g < g1; g++) {
+        const SpEmitCounts c = B.gcnt[g];
+        li += c.n_items;
+        lr += c.n_rows;
+        ls += c.s_doubles;
+        lc += c.cells;
+        lbw = max(lbw, c.max_bw);
+        for (int k = 0; k < SP_N_CLASSES; k++) lcls[k] += c.class_count[k];
+    }
+    s_items[t] = li;
+    s_rows[t] = lr;
+    s_sd[t] = ls;
+    s_cells[t] = lc;
+    atomicMax(&s_maxbw, lbw);
+    for (int k = 0; k < SP_N_CLASSES; k++)
+        if (lcls[k]) atomicAdd(&s_cls[k], lcls[k]);
+    __syncthreads();
+    // Hillis-Steele inclusive scan
+    for (int d = 1; d < 1024; d <<= 1) {
+        int32_t a = 0, b = 0;
+        int64_t c = 0, e = 0;
+        if (t >= d) { a = s_items[t - d]; b = s_rows[t - d]; c = s_sd[t - d]; e = s_cells[t - d]; }
+        __syncthreads();
+        s_items[t] += a; s_rows[t] += b; s_sd[t] += c; s_cells[t] += e;
+        __syncthreads();
+    }
+    int32_t bi = s_items[t] - li, br = s_rows[t] - lr;
+    int64_t bs = s_sd[t] - ls;
+    for (int g = g0; g < g1; g++) {
+        const SpEmitCounts c = B.gcnt[g];
+        B.item_off[g] = bi;
+        B.row_off[g] = br;
+        B.sdbl_off[g] = bs;
+        bi += c.n_items;
+        br += c.n_rows;
+        bs += c.s_doubles;
+    }
+    if (t == 1023) {
+        tot->n_items = s_items[1023];
+        tot->n_rows = s_rows[1023];
+        tot->s_doubles = s_sd[1023];
+        tot->cells = s_cells[1023];
+        tot->max_bw = s_maxbw;
+        for (int k = 0; k < SP_N_CLASSES; k++) tot->class_count[k] = s_cls[k];
+        B.item_off[G] = s_items[1023];
+        B.row_off[G] = s_rows[1023];
+        B.sdbl_off[G] = s_sd[1023];
+    }
+}
+
+__global__ void __launch_bounds__(64) k_emit(SpBatchPtrs B, const SpConst *__restrict__ Cp, SpItem *items, SpRow *rows) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B.G) return;
+    const SpConst &C = *Cp;
+    const SpGroupOut o = B.gout[g];
+    if (!o.scored || !C.baq_flag) return;
+    SpGroupAlnView V = sp_make_view(B, g);
+    SpEmitCounts cnt;
+    memset(&cnt, 0, sizeof(cnt));
+    const int cap = B.gblk_cap[g];
+    for (int i = 0; i < V.n; i++) {
+        const int a = V.a0 + i;
+        sp_emit_alignment<true>(C, V, i, B.gP[g], B.ent + B.gent_off[g], B.blk + B.gblk_off[g] + (int64_t) i * cap,
+                                B.nb[a], B.contig_off[B.tid[a]], 0, cnt, B.res + B.gent_off[g], items,
+                                B.item_off[g], rows, B.row_off[g], B.sdbl_off[g]);
+    }
+}
+
+// ---- instance ordering: key = class * LBINS + (LBINS-1 - min(l_query, LBINS-1)) --------------
+__device__ __forceinline__ int sp_item_key(const SpItem &it) {
+    const int bw = sp_hmm_bw(it.l_ref, it.l_query, it.par_bw);
+    const int lq = it.l_query < SP_SORT_LBINS - 1 ? it.l_query : SP_SORT_LBINS - 1;
+    const int cls = it.n_rows > 0 ? sp_band_class6(bw) : SP_N_CLASSES;  // row-less instances are not run
+    return cls * SP_SORT_LBINS + (SP_SORT_LBINS - 1 - lq);
+}
+__global__ void k_sort_hist(const SpItem *items, int n, int32_t *bins) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&bins[sp_item_key(items[i])], 1);
+}
+// exclusive scan over (SP_N_CLASSES+1)*LBINS bins, one CTA; class_start[c] = first slot of class c
+__global__ void __launch_bounds__(1024) k_sort_scan(int32_t *bins, int nbins, int32_t *class_start) {
+    __shared__ int32_t s[1024];
+    const int t = threadIdx.x;
+    const int per = (nbins + 1023) / 1024;
+    const int b0 = t * per, b1 = min(nbins, b0 + per);
+    int32_t l = 0;
+    for (int b = b0; b < b1; b++) l += bins[b];
+    s[t] = l;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        int32_t a = t >= d ? s[t - d] : 0;
+        __syncthreads();
+        s[t] += a;
+        __syncthreads();
+    }
+    int32_t run = s[t] - l;
+    for (int b = b0; b < b1; b++) {
+        const int32_t c = bins[b];
+        bins[b] = run;
+        if (b % SP_SORT_LBINS == 0) class_start[b / SP_SORT_LBINS] = run;
+        run += c;
+    }
+    if (t == 1023) class_start[SP_N_CLASSES + 1] = s[1023];
+}
+__global__ void k_sort_scatter(const SpItem *items, int n, int32_t *bins, int32_t *order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[atomicAdd(&bins[sp_item_key(items[i])], 1)] = i;
+}
+
+// ---- K4 ---------------------------------------------------------------------------------
+// One warp per CTA, one HMM instance per lane.  Dynamic shared memory: W*3*32 doubles of band
+// state followed by W*32 uint32 reference codes (lane-interleaved).  For the widest class the
+// band lives in global memory instead (gband != nullptr).
+__global__ void __launch_bounds__(32) k_hmm(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
+                                            const int32_t *__restrict__ order, int first, int count, int W,
+                                            const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qbytes,
+                                            const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,
+                                            double *__restrict__ s_pool, double *__restrict__ fsave, int64_t fs_stride,
+                                            SpRow *rows, double *gband) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x;
+    const int slot = blockIdx.x * 32 + lane;
+    if (slot >= count) return;
+    const SpItem it = items[order ? order[first + slot] : first + slot];
+    SpBand<32> B;
+    if (gband) {
+        double *base = gband + (int64_t) blockIdx.x * ((int64_t) W * 3 * 32 + (int64_t) W * 16);
+        B.row = base + lane;
+        B.code = reinterpret_cast<uint32_t *>(base + (int64_t) W * 3 * 32) + lane;
+    } else {
+        B.row = smem + lane;
+        B.code = reinterpret_cast<uint32_t *>(smem + W * 3 * 32) + lane;
+    }
+    B.W = W;
+    SpHmmIn in;
+    in.ref = ref + it.ref_off;
+    if (it.query_off >= 0) {
+        in.qbytes = qbytes;
+        in.qseq4 = nullptr;
+        in.q0 = it.query_off;
+    } else {
+        in.qbytes = nullptr;
+        in.qseq4 = seq_pool + seq_off[it.aln];
+        in.q0 = it.q_sqs;
+    }
+    in.l_ref = it.l_ref;
+    in.l_query = it.l_query;
+    in.par_bw = it.par_bw;
+    sp_hmm_instance<32, 1>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
+                           rows + it.row0, it.n_rows);
+}
+
+__global__ void __launch_bounds__(64) k_score(SpBatchPtrs B, const SpConst *__restrict__ Cp, const SpRow *rows,
+                                              double prim_margin, double min_score, SpTotals *tot) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B.G) return;
+    const SpConst &C = *Cp;
+    SpGroupAlnView V = sp_make_view(B, g);
+    SpGroupOut o = B.gout[g];
+    int32_t *wide = B.fin_wide + B.gent_off[g] * 6;
+    const int nf = sp_score_group(C, V, B.gP[g], B.gpos + B.gpos_off[g], B.ent + B.gent_off[g],
+                                  B.res + B.gent_off[g], rows, o.scored != 0, B.score + V.a0, wide,
+                                  B.baq ? B.baq + B.gent_off[g] : nullptr);
+    o.n_final = nf;
+    sp_select(V, B.score + V.a0, prim_margin, min_score, &o);
+    const int off = atomicAdd(&tot->fin_rows, nf);
+    o.fin_off = off;
+    int32_t *dst = B.fin + (int64_t) off * 6;
+    for (int k = 0; k < nf * 6; k++) dst[k] = wide[k];
+    if (o.err) atomicOr(&tot->err, o.err);
+    B.gout[g] = o;
+}
+
+// ---- reference encoding: ASCII -> codes 0..4 (seq_nt16_int[seq_nt16_table[c]], ptMarker.c:744)
+__global__ void k_encode_ref(const uint8_t *__restrict__ ascii, uint8_t *__restrict__ codes, int64_t n) {
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const uint8_t c = ascii[i];
+        uint8_t v = 4;
+        switch (c) {
+            case 'A': case 'a': case '0': v = 0; break;
+            case 'C': case 'c': case '1': v = 1; break;
+            case 'G': case 'g': case '2': v = 2; break;
+            case 'T': case 't': case '3': v = 3; break;
+            default: v = 4;
+        }
+        codes[i] = v;
+    }
+}
+
+// ---- FP64 pipe micro-benchmark (roofline denominator) -----------------------------------
+__global__ void k_fp64_peak(double *out, int iters, int mode) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 1.0000001, c = 1e-9;
+    if (mode == 0) {
+        for (int i = 0; i < iters; i++) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        }
+    } else {
+        for (int i = 0; i < iters; i++) {
+            a0 = __dmul_rn(a0, m); a1 = __dadd_rn(a1, c); a2 = __dmul_rn(a2, m); a3 = __dadd_rn(a3, c);
+            a4 = __dmul_rn(a4, m); a5 = __dadd_rn(a5, c); a6 = __dmul_rn(a6, m); a7 = __dadd_rn(a7, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}

@@ -12,6 +12,7 @@
 #pragma once
 #include "sp_blocks.cuh"
 #include "sp_common.h"
+#include "sp_hmm.cuh"
 
 struct SpGroupOut {  // per group, device -> host
     int32_t best_pre;   // result of ptAlignment.c:175 given max_idx = first maximum (before tie-break RNG)
@@ -40,37 +41,27 @@ SP_HD int sp_resolve_q(const SpConst &C, const SpEntry &e, int res, const SpRow 
     return bq < 94 ? bq : 93;
 }
 
-// entries are updated in place (q := BAQ), then compacted to the final list in fin[] as
-// SP_MARKER_W-wide rows.  Returns the number of final rows.
-SP_HD int sp_score_group(const SpConst &C, const SpGroupAlnView &G, int P, const int32_t *gpos, SpEntry *entries,
+// Writes the final list to fin[] as SP_MARKER_W-wide rows and returns the number of rows.
+// baq_out[P*n] (optional) receives every entry's quality after calc_update_baq_all.
+SP_HD int sp_score_group(const SpConst &C, const SpGroupAlnView &G, int P, const int32_t *gpos, const SpEntry *entries,
                          const int32_t *res, const SpRow *rows, bool scored, double *score, int32_t *fin,
-                         int32_t *baq_dbg) {
+                         int32_t *baq_out) {
     const int n = G.n;
     for (int i = 0; i < n; i++) score[i] = 0.0;
     int nf = 0;
     for (int p = 0; p < P; p++) {
+        int qv[SP_MAX_ALN_PER_GROUP_C];
         int mq = 100;  // ptMarker.c:119
-        if (scored && C.baq_flag) {
-            for (int i = 0; i < n; i++) {
-                SpEntry &e = entries[(int64_t) p * n + i];
-                e.q = sp_resolve_q(C, e, res[(int64_t) p * n + i], rows);
-            }
-        }
-        if (baq_dbg) {
-            for (int i = 0; i < n; i++) baq_dbg[(int64_t) p * n + i] = entries[(int64_t) p * n + i].q;
-        }
-        bool keep = true;
-        if (scored) {
-            for (int i = 0; i < n; i++) {
-                const int q = entries[(int64_t) p * n + i].q;
-                if (mq > q) mq = q;
-            }
-            keep = mq > C.min_q;
-        }
-        if (!keep) continue;
         for (int i = 0; i < n; i++) {
             const SpEntry e = entries[(int64_t) p * n + i];
-            const int q = scored ? mq : e.q;
+            qv[i] = (scored && C.baq_flag) ? sp_resolve_q(C, e, res[(int64_t) p * n + i], rows) : e.q;
+            if (baq_out) baq_out[(int64_t) p * n + i] = qv[i];
+            if (mq > qv[i]) mq = qv[i];
+        }
+        if (scored && !(mq > C.min_q)) continue;  // ptMarker.c:124,144 (strict)
+        for (int i = 0; i < n; i++) {
+            const SpEntry e = entries[(int64_t) p * n + i];
+            const int q = scored ? mq : qv[i];
             int32_t *row = fin + (int64_t) nf * 6;
             row[0] = i;
             row[1] = gpos[p];

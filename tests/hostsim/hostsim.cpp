@@ -198,7 +198,7 @@ int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes,
                         const int a = V.a0 + i;
                         sp_emit_alignment<false>(C, V, i, P, ent.data() + pl.gent_off[g],
                                                  W.ab + (int64_t) i * W.cap, W.nb[i], contig_off[b->tid[a]],
-                                                 pl.gent_off[g] - pl.gent_off[g], cnt, nullptr, nullptr, 0, nullptr, 0);
+                                                 0, cnt, nullptr, nullptr, 0, nullptr, 0, 0);
                     }
                 }
             }
@@ -231,7 +231,7 @@ int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes,
             sp_emit_alignment<true>(C, V, i, gP[g], ent.data() + pl.gent_off[g],
                                     blk.data() + pl.gblk_off[g] + (int64_t) i * pl.gblk_cap[g], nb[a],
                                     contig_off[b->tid[a]], 0, cnt, res.data() + pl.gent_off[g], items.data(),
-                                    item_off[g], rows.data(), row_off[g]);
+                                    item_off[g], rows.data(), row_off[g], 0);
         }
         if (cnt.n_items != gcnt[g].n_items || cnt.n_rows != gcnt[g].n_rows) out->err |= 0x100;
     }

@@ -1,0 +1,122 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the CPU oracle and committed goldens."""
+import numpy as np
+import pytest
+
+from tests.conftest import CASES, make_case, oracle_refseq
+from tools.parity import compare_results
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import secphase_b200
+    return secphase_b200
+
+
+@pytest.mark.parametrize("name,spreset,ppreset,ng,over", CASES, ids=[c[0] for c in CASES])
+def test_pipeline_bit_exact_vs_oracle(sp, oracle, name, spreset, ppreset, ng, over):
+    s, b, codes, off = make_case(spreset, ng, **over)
+    ref = oracle_refseq(oracle, s)
+    exp = oracle.run(b, oracle.preset_params(ppreset), ref, keep_hmm=False)
+    with sp.Secphase(ppreset) as eng:
+        eng.set_reference_codes(codes, off)
+        got = eng.run_debug(b)
+    bad = compare_results(exp, got, label="cuda")
+    assert not bad, "\n".join(bad)
+    assert got["hmm_instances"] == len(exp["hmm"])
+    cells = int(exp["hmm"][:, 4].astype(np.int64).sum() + (exp["hmm"][:, 5].astype(np.int64) << 31).sum())
+    assert got["hmm_cells"] == cells
+    assert got["gpu_launches"] >= 5
+
+
+def test_reference_ascii_upload_matches_codes(sp, oracle):
+    s, b, codes, off = make_case("hifi", 30, locus_len=200000, n_rate=1e-3)
+    with sp.Secphase("hifi") as e1, sp.Secphase("hifi") as e2:
+        e1.set_reference_codes(codes, off)
+        e2.set_reference_ascii([s.contig_ptr(i) for i in range(s.n_contigs)], s.lens)
+        r1, r2 = e1.run(b), e2.run(b)
+    assert np.array_equal(r1["scores"].view(np.int64), r2["scores"].view(np.int64))
+    assert np.array_equal(r1["groups"], r2["groups"])
+
+
+def test_hmm_all_rows_bit_exact_vs_port(sp, oracle):
+    """Every row's state, q and the normalised max posterior (bitwise) for random instances."""
+    rng = np.random.default_rng(11)
+    for preset in ("hifi", "ont"):
+        op = oracle.preset_params(preset)
+        refs, queries, bws, rows = [], [], [], []
+        for trial in range(160):
+            lr = int(rng.integers(1, 120)) if trial % 3 == 0 else int(rng.integers(100, 1001))
+            ref = rng.integers(0, 4, lr).astype(np.uint8)
+            q = []
+            for c in ref:
+                u = rng.random()
+                if u < 0.02:
+                    continue
+                if u < 0.04:
+                    q += [int(rng.integers(0, 4)), int(c)]
+                elif u < 0.06:
+                    q.append((int(c) + 1) % 4)
+                else:
+                    q.append(int(c))
+            if trial % 7 == 0 and len(q) > 5:
+                q[3] = 4
+            if trial % 11 == 0:
+                ref[min(5, lr - 1)] = 4
+            if not q:
+                q = [0]
+            query = np.array(q, np.uint8)
+            refs.append(ref)
+            queries.append(query)
+            bws.append(abs(lr - len(query)) + 20 if trial % 5 else int(rng.integers(1, 70)))
+            rows.append(np.arange(len(query), dtype=np.int32))
+        with sp.Secphase(preset) as eng:
+            st, qq, pm, ms = eng.hmm_batch(refs, queries, bws, rows)
+        for j in range(len(refs)):
+            iq = np.full(len(queries[j]), op.set_q, np.uint8)
+            o = oracle.probaln(refs[j], queries[j], iq, np.float32(op.conf_d), np.float32(op.conf_e), bws[j])
+            assert np.array_equal(o["state"], st[j]), (preset, j)
+            assert np.array_equal(o["q"], qq[j]), (preset, j)
+            assert np.array_equal(o["pmax"].view(np.int64), pm[j].view(np.int64)), (preset, j)
+
+
+def test_empty_and_degenerate_batches(sp, oracle):
+    s, b, codes, off = make_case("hifi", 8, locus_len=200000)
+    with sp.Secphase("hifi") as eng:
+        eng.set_reference_codes(codes, off)
+        empty = b.group_slice(0, 0)
+        r = eng.run(empty)
+        assert r["n_groups"] == 0 and len(r["scores"]) == 0
+        one = b.group_slice(3, 4)
+        r1 = eng.run(one)
+        ref = oracle_refseq(oracle, s)
+        e1 = oracle.run(one, oracle.preset_params("hifi"), ref)
+        assert np.array_equal(e1["scores"].view(np.int64), r1["scores"].view(np.int64))
+
+
+def test_slots_pipeline_in_order_matches_single_run(sp, oracle):
+    s, b, codes, off = make_case("hifi", 90, locus_len=300000)
+    with sp.Secphase("hifi") as eng:
+        eng.set_reference_codes(codes, off)
+        whole = eng.run(b)
+    with sp.Secphase("hifi") as eng:
+        eng.set_reference_codes(codes, off)
+        parts = [b.group_slice(0, 30), b.group_slice(30, 60), b.group_slice(60, 90)]
+        for k, p in enumerate(parts):
+            eng.submit(p, slot=k)
+        outs = [eng.wait(slot=k) for k in range(3)]
+    scores = np.concatenate([o["scores"] for o in outs])
+    groups = np.concatenate([o["groups"] for o in outs])
+    assert np.array_equal(scores.view(np.int64), whole["scores"].view(np.int64))
+    assert np.array_equal(groups, whole["groups"])
+
+
+def test_rng_matches_glibc(sp):
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    with sp.Secphase("hifi") as eng:
+        eng.rng_seed(1)
+        for _ in range(1000):
+            assert eng.rng_next() == libc.rand()
