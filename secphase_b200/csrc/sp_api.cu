@@ -202,7 +202,8 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
         delete c;
         return nullptr;
     }
-    if (cudaFuncSetAttribute(k_hmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_hmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
         set_err("sp_create: cudaFuncSetAttribute(k_hmm) failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
         return nullptr;
@@ -415,6 +416,45 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
     return SP_OK;
 }
 
+// K4 launches for instances already ordered by (band class, length): classes up to
+// SP_H2_MAXBW run k_hmm2 (band in shared memory, sp_hmm2.cuh); wider bands run the generic k_hmm,
+// whose band falls back to global memory when it outgrows shared memory.
+static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_count, int max_bw, const uint8_t *ref,
+                      const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride) {
+    static const int class_bw[SP_N_CLASSES] = {20, 22, 30, 62, 120, 0};
+    const SpConst *dC = c->dC.as<SpConst>();
+    int first = 0, rc;
+    for (int cls = 0; cls < SP_N_CLASSES; cls++) {
+        const int cnt = class_count[cls];
+        if (cnt == 0) continue;
+        const int nblk = (cnt + 31) / 32;
+        if (class_bw[cls] != 0 && class_bw[cls] <= SP_H2_MAXBW) {
+            const int ncell = sp_h2_cells(class_bw[cls]);
+            k_hmm2<<<nblk, 32, (size_t) ncell * 32 * 24, st>>>(dC, S.items.as<SpItem>(), S.order.as<int32_t>(), first,
+                                                               cnt, ncell, ref, qbytes, seq_pool, seq_off,
+                                                               S.s_pool.as<double>(), S.fsave.as<double>(), fs_stride,
+                                                               S.rows.as<SpRow>());
+        } else {
+            int W = sp_class_cells(cls);
+            double *gband = nullptr;
+            size_t smem = 0;
+            if (W == 0 || (size_t) W * 28 * 32 > c->max_smem) {
+                W = 2 * max_bw + 2;
+                if ((rc = S.gband.ensure((size_t) nblk * ((size_t) W * 28 * 32)))) return rc;
+                gband = S.gband.as<double>();
+            } else {
+                smem = (size_t) W * 28 * 32;
+            }
+            k_hmm<<<nblk, 32, smem, st>>>(dC, S.items.as<SpItem>(), S.order.as<int32_t>(), first, cnt, W, ref, qbytes,
+                                          seq_pool, seq_off, S.s_pool.as<double>(), S.fsave.as<double>(), fs_stride,
+                                          S.rows.as<SpRow>(), gband);
+        }
+        S.launches++;
+        first += cnt;
+    }
+    return SP_OK;
+}
+
 // enqueue kernels for the batch staged in S (device copy already enqueued or resident)
 static int run_pipeline(sp_ctx *c, Slot &S) {
     cudaStream_t st = S.stream;
@@ -460,27 +500,8 @@ static int run_pipeline(sp_ctx *c, Slot &S) {
     }
     CK(cudaEventRecord(S.ev[EV_EMIT], st));
     if (T.n_items > 0) {
-        int first = 0;
-        for (int cls = 0; cls < SP_N_CLASSES; cls++) {
-            const int cnt = T.class_count[cls];
-            if (cnt == 0) continue;
-            int W = sp_class_cells(cls);
-            double *gband = nullptr;
-            size_t smem = 0;
-            const int nblk = (cnt + 31) / 32;
-            if (W == 0 || (size_t) W * 28 * 32 > c->max_smem) {
-                W = 2 * T.max_bw + 2;
-                if ((rc = S.gband.ensure((size_t) nblk * ((size_t) W * 28 * 32)))) return rc;
-                gband = S.gband.as<double>();
-            } else {
-                smem = (size_t) W * 28 * 32;
-            }
-            k_hmm<<<nblk, 32, smem, st>>>(dC, S.items.as<SpItem>(), S.order.as<int32_t>(), first, cnt, W, P.ref, nullptr,
-                                          P.seq_pool, P.seq_off, S.s_pool.as<double>(), S.fsave.as<double>(),
-                                          fs_stride, S.rows.as<SpRow>(), gband);
-            S.launches++;
-            first += cnt;
-        }
+        if ((rc = launch_hmm(c, S, st, T.class_count, T.max_bw, P.ref, nullptr, P.seq_pool, P.seq_off, fs_stride)))
+            return rc;
     }
     CK(cudaEventRecord(S.ev[EV_HMM], st));
     if (P.G > 0) {
@@ -832,26 +853,11 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     CK(cudaEventRecord(e0, st));
-    int first = 0;
-    for (int cls = 0; cls < SP_N_CLASSES; cls++) {
-        const int cnt = cls_count[cls];
-        if (cnt == 0) continue;
-        int W = sp_class_cells(cls);
-        double *gband = nullptr;
-        size_t smem = 0;
-        const int nblk = (cnt + 31) / 32;
-        if (W == 0 || (size_t) W * 28 * 32 > c->max_smem) {
-            W = 2 * max_bw + 2;
-            if ((rc = S.gband.ensure((size_t) nblk * ((size_t) W * 28 * 32)))) return rc;
-            gband = S.gband.as<double>();
-        } else {
-            smem = (size_t) W * 28 * 32;
-        }
-        k_hmm<<<nblk, 32, smem, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(), first, cnt, W,
-                                      d_ref.as<uint8_t>(), d_q.as<uint8_t>(), nullptr, nullptr, S.s_pool.as<double>(),
-                                      S.fsave.as<double>(), fs_stride, S.rows.as<SpRow>(), gband);
-        first += cnt;
-    }
+    const int launches_before = S.launches;
+    if ((rc = launch_hmm(c, S, st, cls_count, max_bw, d_ref.as<uint8_t>(), d_q.as<uint8_t>(), nullptr, nullptr,
+                         fs_stride)))
+        return rc;
+    S.launches = launches_before;
     CK(cudaEventRecord(e1, st));
     CK(cudaMemcpyAsync(rows.data(), S.rows.p, sizeof(SpRow) * (size_t) n_rows, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -1,0 +1,358 @@
+// sp_hmm2.cuh -- stage K4, main kernel body: banded glocal forward-backward HMM (BAQ) for band
+// half-widths up to SP_H2_MAXBW, one HMM instance per lane, band in shared memory.
+//
+// Same contract and the same arithmetic as sp_hmm.cuh (htslib 1.17 probaln_glocal as called at
+// ptMarker.c:754-757): every double operation is an explicit round-to-nearest
+// IEEE add / mul / div, in the reference's order, never contracted to an FMA; the row sum and the
+// D-state recurrence stay serial chains along the band; rows are stored unscaled and multiplied by
+// 1/s on the next read (one rounding, as the reference's in-place rescale).  What changes is only
+// how the work is laid out for the SM:
+//
+//  * band-offset addressing: cell o of the buffer holds column beg(i)+o of the row written last,
+//    so neighbours are reached through compile-time immediates from one per-row base (the band
+//    origin shift sh = beg(i)-beg(i-1) is folded into that base); a permanent zero cell at o = -1
+//    and never-written cells above the band stand for the reference's zero padding;
+//  * (M,I) of a cell are one 16-byte word (LDS.128/STS.128), D a separate 8-byte plane, both
+//    lane-interleaved, hence bank-conflict free for any per-lane offset;
+//  * cells are processed U at a time: the "parallel part" of chunk c+1 (rescale, M, I, m2*M, M+I:
+//    independent across cells) is issued next to the two serial chains of chunk c (D recurrence,
+//    row sum), so the FP64 pipe always has independent work while a chain waits on its latency;
+//  * the emission term is picked from two 64-bit masks per row (match / N), built from three
+//    bit-planes of the reference codes that slide with the band: no per-cell code loads;
+//  * forward stores 1/s[i] (it needs it anyway); backward never divides.
+// Exact algebraic folds used: EI*m1 and EI*m4 hoisted (EI = 2^-2; identical unless an intermediate
+// is below 2^-1020, far under anything that reaches a posterior), y=(i>1) folded into m6,m8 for
+// row 1 ((x)*0 == e*0 + 0*bD == +0 for finite x).
+#pragma once
+#include "sp_blocks.cuh"
+#include "sp_common.h"
+#include "sp_hmm.cuh"
+
+#define SP_H2_U 4
+#define SP_H2_MAXBW 30  // 2*bw+1 <= 61 cells: the per-row emission masks are 64-bit
+
+#if defined(__CUDACC__)
+typedef double2 SpD2;
+#else
+struct alignas(16) SpD2 {
+    double x, y;
+};
+#endif
+
+// per-lane view: cell o (-1 <= o <= 2*bw+1) lives at mi[o*STRIDE], d[o*STRIDE]; all cells zero on entry
+template <int STRIDE>
+struct SpBand2 {
+    SpD2 *mi;
+    double *d;
+};
+
+SP_HD int sp_h2_cells(int bw) { return 2 * bw + 3; }  // cells -1 .. 2bw+1
+
+// rinv[i], i = 1..l_query : 1/s[i].   fsave + r*fs_stride : scaled forward (M,I) of marker row r, [o*2+{0,1}].
+template <int STRIDE>
+SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<STRIDE> B, double *rinv, double *fsave,
+                            int64_t fs_stride, SpRow *rows, int n_rows) {
+    constexpr int U = SP_H2_U;
+    const int Lr = in.l_ref, Lq = in.l_query;
+    const int bw = sp_hmm_bw(Lr, Lq, in.par_bw);
+    // transition matrix; float-typed sub-expressions were folded on the host
+    const double sM = SP_DDIV(1., (double) (2 * Lq + 2));
+    const double sI = sM;
+    const double oms = SP_DADD(1., -sM);
+    const double m0 = SP_DMUL(C.m0f, oms);
+    const double m1 = SP_DMUL(C.d_d, oms);
+    const double m2 = m1;
+    const double m3 = SP_DMUL(C.ome_f, oms);
+    const double m4 = SP_DMUL(C.e_d, oms);
+    const double m6 = C.ome_f;
+    const double m8 = C.e_d;
+    const double bM = (double) SP_FDIV(C.omd_ff, (float) Lr);
+    const double bI = (double) SP_FDIV(C.d_f, (float) Lr);
+    const double eim1 = SP_DMUL(SP_HMM_EI, m1), eim4 = SP_DMUL(SP_HMM_EI, m4);
+    const double emA = C.em_match, emB = C.em_mis;
+
+    // bit-planes of the reference codes under the band: bit o <-> ref[beg-1+o] (column beg+o)
+    uint64_t p0 = 0, p1 = 0, p2 = 0;
+    int nr = 0;  // next marker row (rows are ascending in t)
+
+    // ------------------------------------------------------------------ forward, row 1
+    int n_prev = Lr < bw + 1 ? Lr : bw + 1;
+    double s_last;
+    {
+        const int qc = sp_query_code(in, 0);
+        double sum = 0.;
+        for (int o = 0; o < n_prev; o++) {
+            const int rc = in.ref[o];
+            p0 |= (uint64_t) (rc & 1) << o;
+            p1 |= (uint64_t) ((rc >> 1) & 1) << o;
+            p2 |= (uint64_t) ((rc >> 2) & 1) << o;
+            SpD2 v;
+            v.x = SP_DMUL(sp_emis(C, rc, qc), bM);
+            v.y = SP_DMUL(SP_HMM_EI, bI);
+            B.mi[o * STRIDE] = v;
+            sum = SP_DADD(sum, SP_DADD(v.x, v.y));
+        }
+        // the reference rescales row 1 by a true division; store it scaled, later rows read it with r = 1
+        double *fs = (nr < n_rows && rows[nr].t == 0) ? fsave + (int64_t) nr * fs_stride : nullptr;
+        for (int o = 0; o < n_prev; o++) {
+            SpD2 v = B.mi[o * STRIDE];
+            v.x = SP_DDIV(v.x, sum);
+            v.y = SP_DDIV(v.y, sum);
+            B.mi[o * STRIDE] = v;
+            if (fs) { fs[o * 2 + 0] = v.x; fs[o * 2 + 1] = v.y; }
+        }
+        if (fs) nr++;  // only the stand-alone API asks for row 1
+        rinv[1] = SP_DDIV(1., sum);
+        s_last = sum;
+    }
+    // ------------------------------------------------------------------ forward, rows 2..Lq
+    double r = 1.;
+    int beg_prev = 1, end_prev = n_prev;
+    for (int i = 2; i <= Lq; i++) {
+        const int beg = i - bw > 1 ? i - bw : 1;
+        const int end = i + bw < Lr ? i + bw : Lr;
+        const int n = end - beg + 1;
+        const int sh = beg - beg_prev;
+        const int qc = sp_query_code(in, i - 1);
+        if (sh) { p0 >>= 1; p1 >>= 1; p2 >>= 1; }
+        if (end > end_prev) {  // one column enters the band on the right
+            const int rc = in.ref[end - 1];
+            p0 |= (uint64_t) (rc & 1) << (n - 1);
+            p1 |= (uint64_t) ((rc >> 1) & 1) << (n - 1);
+            p2 |= (uint64_t) ((rc >> 2) & 1) << (n - 1);
+        }
+        uint64_t mm, nn;  // bit o: reference base of column beg+o equals the query base / emission is 1 (an N)
+        if (qc > 3) { mm = 0; nn = ~(uint64_t) 0; }
+        else { mm = ((qc & 1) ? p0 : ~p0) & ((qc & 2) ? p1 : ~p1) & ~p2; nn = p2; }
+
+        // old row (i-1): M[i,o] reads old cell o-1+sh, I[i,o] reads old cell o+sh
+        const SpD2 *omi = B.mi + sh * STRIDE;
+        const double *od = B.d + sh * STRIDE;
+        double pM, pI, pD;  // scaled old cell o-1+sh (carried between cells)
+        {
+            const SpD2 a = omi[-STRIDE];
+            pM = SP_DMUL(a.x, r); pI = SP_DMUL(a.y, r); pD = SP_DMUL(od[-STRIDE], r);
+        }
+        double Mlast = 0., cD = 0., sum = 0.;
+
+        // parallel part of U cells starting at o0: everything that does not depend on this row's D chain
+        auto fwdP = [&](int o0, double (&t)[U], double (&u)[U]) {
+            const uint32_t mb = (uint32_t) (mm >> o0), nb = (uint32_t) (nn >> o0);
+            double qM[U], qI[U], qD[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const SpD2 a = omi[(o0 + j) * STRIDE];
+                const double dd = od[(o0 + j) * STRIDE];
+                qM[j] = SP_DMUL(a.x, r); qI[j] = SP_DMUL(a.y, r); qD[j] = SP_DMUL(dd, r);
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const double aM = j ? qM[j ? j - 1 : 0] : pM, aI = j ? qI[j ? j - 1 : 0] : pI,
+                             aD = j ? qD[j ? j - 1 : 0] : pD;
+                const double e = ((nb >> j) & 1) ? 1. : (((mb >> j) & 1) ? emA : emB);
+                SpD2 v;
+                v.x = SP_DMUL(e, SP_DADD(SP_DADD(SP_DMUL(m0, aM), SP_DMUL(m3, aI)), SP_DMUL(m6, aD)));
+                v.y = SP_DADD(SP_DMUL(eim1, qM[j]), SP_DMUL(eim4, qI[j]));
+                t[j] = SP_DMUL(m2, Mlast);
+                u[j] = SP_DADD(v.x, v.y);
+                B.mi[(o0 + j) * STRIDE] = v;
+                Mlast = v.x;
+            }
+            pM = qM[U - 1]; pI = qI[U - 1]; pD = qD[U - 1];
+        };
+        // the two serial chains over those U cells: D[o] = m2*M[o-1] + m8*D[o-1];  sum += (M+I)+D
+        auto fwdC = [&](int o0, const double (&t)[U], const double (&u)[U]) {
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                cD = SP_DADD(t[j], SP_DMUL(m8, cD));
+                sum = SP_DADD(sum, SP_DADD(u[j], cD));
+                B.d[(o0 + j) * STRIDE] = cD;
+            }
+        };
+        const int nfull = n / U;
+        if (nfull > 0) {
+            double tA[U], uA[U], tB[U], uB[U];
+            fwdP(0, tA, uA);
+            int c = 1;
+            for (; c + 1 < nfull; c += 2) {
+                fwdP(c * U, tB, uB);
+                fwdC((c - 1) * U, tA, uA);
+                fwdP((c + 1) * U, tA, uA);
+                fwdC(c * U, tB, uB);
+            }
+            if (c < nfull) {
+                fwdP(c * U, tB, uB);
+                fwdC((c - 1) * U, tA, uA);
+                fwdC(c * U, tB, uB);
+            } else {
+                fwdC((c - 1) * U, tA, uA);
+            }
+        }
+        for (int o = nfull * U; o < n; o++) {  // remainder cells, one at a time
+            const SpD2 a = omi[o * STRIDE];
+            const double qM = SP_DMUL(a.x, r), qI = SP_DMUL(a.y, r), qD = SP_DMUL(od[o * STRIDE], r);
+            const double e = ((nn >> o) & 1) ? 1. : (((mm >> o) & 1) ? emA : emB);
+            SpD2 v;
+            v.x = SP_DMUL(e, SP_DADD(SP_DADD(SP_DMUL(m0, pM), SP_DMUL(m3, pI)), SP_DMUL(m6, pD)));
+            v.y = SP_DADD(SP_DMUL(eim1, qM), SP_DMUL(eim4, qI));
+            cD = SP_DADD(SP_DMUL(m2, Mlast), SP_DMUL(m8, cD));
+            sum = SP_DADD(sum, SP_DADD(SP_DADD(v.x, v.y), cD));
+            B.mi[o * STRIDE] = v;
+            B.d[o * STRIDE] = cD;
+            Mlast = v.x;
+            pM = qM; pI = qI; pD = qD;
+        }
+        const double ri = SP_DDIV(1., sum);
+        rinv[i] = ri;
+        s_last = sum;
+        if (nr < n_rows && rows[nr].t + 1 == i) {  // marker row: keep the scaled forward M,I
+            double *fs = fsave + (int64_t) nr * fs_stride;
+            for (int o = 0; o < n; o++) {
+                const SpD2 a = B.mi[o * STRIDE];
+                fs[o * 2 + 0] = SP_DMUL(a.x, ri);
+                fs[o * 2 + 1] = SP_DMUL(a.y, ri);
+            }
+            nr++;
+        }
+        r = ri;
+        beg_prev = beg;
+        end_prev = end;
+        n_prev = n;
+    }
+    // s[Lq+1] = sum_k ( M'[Lq,k]*sM + I'[Lq,k]*sI ) over the band of row Lq, k ascending
+    double sLq1 = 0.;
+    for (int o = 0; o < n_prev; o++) {
+        const SpD2 a = B.mi[o * STRIDE];
+        sLq1 = SP_DADD(sLq1, SP_DADD(SP_DMUL(SP_DMUL(a.x, r), sM), SP_DMUL(SP_DMUL(a.y, r), sI)));
+    }
+    if (n_rows == 0) return;
+
+    // ------------------------------------------------------------------ backward (+ MAP at marker rows)
+    const int i_stop = rows[0].t + 1;  // nothing below the lowest marker row is consumed
+    {  // row Lq: constant inside the band, already in its final scale
+        SpD2 v;
+        v.x = SP_DDIV(SP_DDIV(sM, s_last), sLq1);
+        v.y = SP_DDIV(SP_DDIV(sI, s_last), sLq1);
+        for (int o = 0; o < n_prev; o++) B.mi[o * STRIDE] = v;
+    }
+    // MAP of one row (the state/q the reference reads at ptMarker.c:778-779)
+    auto map_row = [&](int ri, int beg, int n, double y, bool scale) {
+        const double *fs = fsave + (int64_t) ri * fs_stride;
+        double sum = 0., mx = 0.;
+        int max_k = -1;
+        for (int o = 0; o < n; o++) {
+            const SpD2 a = B.mi[o * STRIDE];
+            double bm = a.x, bi = a.y;
+            if (scale) { bm = SP_DMUL(bm, y); bi = SP_DMUL(bi, y); }
+            double z = SP_DMUL(fs[o * 2 + 0], bm);
+            if (z > mx) { mx = z; max_k = (beg + o - 1) << 2 | 0; }
+            sum = SP_DADD(sum, z);
+            z = SP_DMUL(fs[o * 2 + 1], bi);
+            if (z > mx) { mx = z; max_k = (beg + o - 1) << 2 | 1; }
+            sum = SP_DADD(sum, z);
+        }
+        mx = SP_DDIV(mx, sum);
+        rows[ri].state = max_k;
+        rows[ri].pmax = mx;
+        rows[ri].q = sp_q_from_t(C, SP_DADD(1., -mx));
+    };
+    nr = n_rows - 1;
+    if (rows[nr].t + 1 == Lq) {  // stand-alone API only (pipeline rows satisfy t <= Lq-12)
+        map_row(nr, beg_prev, n_prev, 1., false);
+        nr--;
+        if (nr < 0) return;
+    }
+    // planes re-aligned for the backward sweep: bit o <-> ref[beg+o] (the base of column beg+o+1)
+    p0 >>= 1; p1 >>= 1; p2 >>= 1;
+    int beg_next = beg_prev, end_next = end_prev;  // band of row i+1
+    for (int i = Lq - 1; i >= i_stop; i--) {
+        const int beg = i - bw > 1 ? i - bw : 1;
+        const int end = i + bw < Lr ? i + bw : Lr;
+        const int n = end - beg + 1;
+        const int sh = beg_next - beg;
+        const int qc = sp_query_code(in, i);  // query[i] (0-based) == base of row i+1
+        const double r1 = (i + 1 == Lq) ? 1. : rinv[i + 1];
+        const double m6e = i > 1 ? m6 : 0., m8e = i > 1 ? m8 : 0.;
+        if (sh) {  // one column enters the band on the left
+            const int rc = beg < Lr ? in.ref[beg] : 0;  // (the bit of column Lr+1 is never consumed)
+            p0 = (p0 << 1) | (uint64_t) (rc & 1);
+            p1 = (p1 << 1) | (uint64_t) ((rc >> 1) & 1);
+            p2 = (p2 << 1) | (uint64_t) ((rc >> 2) & 1);
+        }
+        uint64_t mm, nn;
+        if (qc > 3) { mm = 0; nn = ~(uint64_t) 0; }
+        else { mm = ((qc & 1) ? p0 : ~p0) & ((qc & 2) ? p1 : ~p1) & ~p2; nn = p2; }
+        // old row (i+1): cell o needs bI of old cell o-sh and bM of old cell o+1-sh
+        const SpD2 *omi = B.mi - sh * STRIDE;
+        double nM = (end + 1 <= end_next) ? SP_DMUL(omi[n * STRIDE].x, r1) : 0.;  // scaled bM[i+1][end+1]
+        double cD = 0.;
+
+        auto bwdP = [&](int o0, double (&X)[U], double (&bIv)[U], double (&w)[U]) {
+            const uint32_t mb = (uint32_t) (mm >> o0), nb = (uint32_t) (nn >> o0);
+            double qM[U], qI[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const SpD2 a = omi[(o0 + j) * STRIDE];
+                qM[j] = SP_DMUL(a.x, r1); qI[j] = SP_DMUL(a.y, r1);
+            }
+#pragma unroll
+            for (int j = U - 1; j >= 0; j--) {
+                const double up = (j == U - 1) ? nM : qM[j < U - 1 ? j + 1 : 0];
+                const double em = ((nb >> j) & 1) ? 1. : (((mb >> j) & 1) ? emA : emB);
+                const double e = SP_DMUL(em, up);
+                X[j] = SP_DADD(SP_DMUL(e, m0), SP_DMUL(eim1, qI[j]));
+                bIv[j] = SP_DADD(SP_DMUL(e, m3), SP_DMUL(eim4, qI[j]));
+                w[j] = SP_DMUL(e, m6e);
+            }
+            nM = qM[0];
+        };
+        auto bwdC = [&](int o0, const double (&X)[U], const double (&bIv)[U], const double (&w)[U]) {
+#pragma unroll
+            for (int j = U - 1; j >= 0; j--) {
+                SpD2 v;
+                v.x = SP_DADD(X[j], SP_DMUL(m2, cD));
+                v.y = bIv[j];
+                cD = SP_DADD(w[j], SP_DMUL(m8e, cD));
+                B.mi[(o0 + j) * STRIDE] = v;
+            }
+        };
+        const int nfull = (n - 1) / U;  // the top cell always goes through the generic single-cell code
+        for (int o = n - 1; o >= nfull * U; o--) {
+            const SpD2 a = omi[o * STRIDE];
+            const double qM = SP_DMUL(a.x, r1), qI = SP_DMUL(a.y, r1);
+            const double em = (beg + o >= Lr) ? 0. : (((nn >> o) & 1) ? 1. : (((mm >> o) & 1) ? emA : emB));
+            const double e = SP_DMUL(em, nM);
+            SpD2 v;
+            v.x = SP_DADD(SP_DADD(SP_DMUL(e, m0), SP_DMUL(eim1, qI)), SP_DMUL(m2, cD));
+            v.y = SP_DADD(SP_DMUL(e, m3), SP_DMUL(eim4, qI));
+            cD = SP_DADD(SP_DMUL(e, m6e), SP_DMUL(m8e, cD));
+            B.mi[o * STRIDE] = v;
+            nM = qM;
+        }
+        if (nfull > 0) {
+            double XA[U], IA[U], wA[U], XB[U], IB[U], wB[U];
+            int c = nfull - 1;
+            bwdP(c * U, XA, IA, wA);
+            c--;
+            for (; c - 1 >= 0; c -= 2) {
+                bwdP(c * U, XB, IB, wB);
+                bwdC((c + 1) * U, XA, IA, wA);
+                bwdP((c - 1) * U, XA, IA, wA);
+                bwdC(c * U, XB, IB, wB);
+            }
+            if (c >= 0) {
+                bwdP(c * U, XB, IB, wB);
+                bwdC((c + 1) * U, XA, IA, wA);
+                bwdC(c * U, XB, IB, wB);
+            } else {
+                bwdC((c + 1) * U, XA, IA, wA);
+            }
+        }
+        beg_next = beg;
+        end_next = end;
+        if (nr >= 0 && rows[nr].t + 1 == i) {
+            map_row(nr, beg, n, rinv[i], true);
+            nr--;
+        }
+    }
+}

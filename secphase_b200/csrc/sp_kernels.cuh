@@ -14,6 +14,7 @@
 #include "sp_blocks.cuh"
 #include "sp_common.h"
 #include "sp_hmm.cuh"
+#include "sp_hmm2.cuh"
 #include "sp_markers.cuh"
 #include "sp_score.cuh"
 #include "sp_walk.cuh"
@@ -312,6 +313,48 @@ __global__ void __launch_bounds__(32) k_hmm(const SpConst *__restrict__ Cp, cons
     in.par_bw = it.par_bw;
     sp_hmm_instance<32, 1>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
                            rows + it.row0, it.n_rows);
+}
+
+
+// Main K4 kernel (band half-width <= SP_H2_MAXBW): one warp per CTA, one HMM instance per lane,
+// band in dynamic shared memory: ncell x 32 double2 (M,I) followed by ncell x 32 double (D),
+// lane-interleaved; see sp_hmm2.cuh.
+__global__ void __launch_bounds__(32) k_hmm2(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
+                                             const int32_t *__restrict__ order, int first, int count, int ncell,
+                                             const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qbytes,
+                                             const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,
+                                             double *__restrict__ s_pool, double *__restrict__ fsave, int64_t fs_stride,
+                                             SpRow *rows) {
+    extern __shared__ double2 smem2[];
+    const int lane = threadIdx.x;
+    const int slot = blockIdx.x * 32 + lane;
+    if (slot >= count) return;
+    const SpItem it = items[order ? order[first + slot] : first + slot];
+    double2 *mi = smem2 + lane;
+    double *d = reinterpret_cast<double *>(smem2 + ncell * 32) + lane;
+    for (int c = 0; c < ncell; c++) {
+        mi[c * 32] = make_double2(0., 0.);
+        d[c * 32] = 0.;
+    }
+    SpBand2<32> B;
+    B.mi = mi + 32;  // cell -1 is the permanent zero cell
+    B.d = d + 32;
+    SpHmmIn in;
+    in.ref = ref + it.ref_off;
+    if (it.query_off >= 0) {
+        in.qbytes = qbytes;
+        in.qseq4 = nullptr;
+        in.q0 = it.query_off;
+    } else {
+        in.qbytes = nullptr;
+        in.qseq4 = seq_pool + seq_off[it.aln];
+        in.q0 = it.q_sqs;
+    }
+    in.l_ref = it.l_ref;
+    in.l_query = it.l_query;
+    in.par_bw = it.par_bw;
+    sp_hmm2_instance<32>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
+                         rows + it.row0, it.n_rows);
 }
 
 __global__ void __launch_bounds__(64) k_score(SpBatchPtrs B, const SpConst *__restrict__ Cp, const SpRow *rows,

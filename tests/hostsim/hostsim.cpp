@@ -17,6 +17,7 @@
 #include "../../secphase_b200/csrc/sp_blocks.cuh"
 #include "../../secphase_b200/csrc/sp_common.h"
 #include "../../secphase_b200/csrc/sp_hmm.cuh"
+#include "../../secphase_b200/csrc/sp_hmm2.cuh"
 #include "../../secphase_b200/csrc/sp_markers.cuh"
 #include "../../secphase_b200/csrc/sp_plan.h"
 #include "../../secphase_b200/csrc/sp_score.cuh"
@@ -94,6 +95,38 @@ int hs_hmm(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *que
         if (pmax) pmax[i] = rows[i].pmax;
     }
     if (s_out) memcpy(s_out, s.data(), sizeof(double) * ((size_t) l_query + 2));
+    return 0;
+}
+
+// Same, through the shared-memory-band kernel body (sp_hmm2.cuh); bw must be <= SP_H2_MAXBW.
+int hs_hmm2(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *query, int l_query, int par_bw,
+            const int32_t *rows_t, int n_rows, int32_t *state, uint8_t *q, double *pmax) {
+    SpConst C;
+    sp_fill_const(*p, C);
+    const int bw = sp_hmm_bw(l_ref, l_query, par_bw);
+    if (bw > SP_H2_MAXBW) return -1;
+    const int ncell = sp_h2_cells(bw);
+    std::vector<SpD2> mi((size_t) ncell);
+    std::vector<double> d((size_t) ncell, 0.0);
+    for (auto &v : mi) v.x = v.y = 0.0;
+    std::vector<double> rinv((size_t) l_query + 2, 0.0);
+    std::vector<double> fsave((size_t) n_rows * 2 * (2 * bw + 1) + 2, 0.0);
+    std::vector<SpRow> rows((size_t) (n_rows > 0 ? n_rows : 1));
+    for (int i = 0; i < n_rows; i++) {
+        rows[i].item = 0; rows[i].t = rows_t[i]; rows[i].entry = -1; rows[i].expected = 0;
+        rows[i].state = 0; rows[i].q = 0; rows[i].pmax = 0;
+    }
+    SpHmmIn in;
+    in.ref = ref; in.qbytes = query; in.qseq4 = nullptr; in.q0 = 0;
+    in.l_ref = l_ref; in.l_query = l_query; in.par_bw = par_bw;
+    SpBand2<1> B;
+    B.mi = mi.data() + 1; B.d = d.data() + 1;
+    sp_hmm2_instance<1>(C, in, B, rinv.data(), fsave.data(), 2 * (2 * bw + 1), rows.data(), n_rows);
+    for (int i = 0; i < n_rows; i++) {
+        state[i] = rows[i].state;
+        q[i] = (uint8_t) rows[i].q;
+        if (pmax) pmax[i] = rows[i].pmax;
+    }
     return 0;
 }
 
@@ -250,9 +283,19 @@ int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes,
         in.qseq4 = b->seq_pool + b->seq_off[I.aln];
         in.q0 = I.q_sqs;
         in.l_ref = I.l_ref; in.l_query = I.l_query; in.par_bw = I.par_bw;
-        SpBand<1> B;
-        B.row = band.data(); B.code = code.data(); B.W = W;
-        sp_hmm_instance<1, 1>(C, in, B, s.data(), fsave.data(), 2 * (2 * bw + 1), rows.data() + I.row0, I.n_rows);
+        if (bw <= SP_H2_MAXBW) {  // same dispatch as launch_hmm() in sp_api.cu
+            const int ncell = sp_h2_cells(bw);
+            std::vector<SpD2> mi((size_t) ncell);
+            std::vector<double> dd((size_t) ncell, 0.0);
+            for (auto &v : mi) v.x = v.y = 0.0;
+            SpBand2<1> B2;
+            B2.mi = mi.data() + 1; B2.d = dd.data() + 1;
+            sp_hmm2_instance<1>(C, in, B2, s.data(), fsave.data(), 2 * (2 * bw + 1), rows.data() + I.row0, I.n_rows);
+        } else {
+            SpBand<1> B;
+            B.row = band.data(); B.code = code.data(); B.W = W;
+            sp_hmm_instance<1, 1>(C, in, B, s.data(), fsave.data(), 2 * (2 * bw + 1), rows.data() + I.row0, I.n_rows);
+        }
         int32_t irow[SP_HMM_W] = {I.aln, I.l_ref, I.l_query, I.par_bw, I.blk, I.row0, I.n_rows, 0};
         out->items.insert(out->items.end(), irow, irow + SP_HMM_W);
     }

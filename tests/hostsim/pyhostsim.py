@@ -60,6 +60,9 @@ def lib():
         L.hs_hmm.argtypes = [C.POINTER(SpParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_hmm.restype = C.c_int
+        L.hs_hmm2.argtypes = [C.POINTER(SpParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_hmm2.restype = C.c_int
         L.hs_rng_create.argtypes = [C.c_uint]
         L.hs_rng_create.restype = C.c_void_p
         L.hs_rng_next.argtypes = [C.c_void_p]
@@ -108,6 +111,23 @@ def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1):
         return r
     finally:
         L.hs_out_destroy(out)
+
+
+def hmm2(params, ref, query, par_bw, rows_t):
+    """The shared-memory-band kernel body (sp_hmm2.cuh) on the host; None if the band is too wide for it."""
+    L = lib()
+    ref = np.ascontiguousarray(ref, np.uint8)
+    query = np.ascontiguousarray(query, np.uint8)
+    rows_t = np.ascontiguousarray(rows_t, np.int32)
+    n = len(rows_t)
+    state = np.zeros(n, np.int32)
+    q = np.zeros(n, np.uint8)
+    pmax = np.zeros(n, np.float64)
+    rc = L.hs_hmm2(C.byref(params), ref.ctypes.data, len(ref), query.ctypes.data, len(query), par_bw,
+                   rows_t.ctypes.data, n, state.ctypes.data, q.ctypes.data, pmax.ctypes.data)
+    if rc != 0:
+        return None
+    return dict(state=state, q=q, pmax=pmax)
 
 
 def hmm(params, ref, query, par_bw, rows_t, want_s=False):

@@ -36,3 +36,58 @@ def test_glibc_rand_emulation(hostsim):
         for _ in range(2000):
             assert L.hs_rng_next(r) == libc.rand()
         L.hs_rng_destroy(r)
+
+
+def _random_instances(rng, n_trials):
+    for trial in range(n_trials):
+        lr = int(rng.integers(1, 120)) if trial % 3 == 0 else int(rng.integers(100, 1001))
+        ref = rng.integers(0, 4, lr).astype(np.uint8)
+        q = []
+        for c in ref:
+            u = rng.random()
+            if u < 0.02:
+                continue
+            if u < 0.04:
+                q += [int(rng.integers(0, 4)), int(c)]
+            elif u < 0.06:
+                q.append((int(c) + 1) % 4)
+            else:
+                q.append(int(c))
+        if trial % 7 == 0 and len(q) > 5:
+            q[3] = 4
+        if trial % 11 == 0:
+            ref[min(5, lr - 1)] = 4
+        if not q:
+            q = [0]
+        query = np.array(q, np.uint8)
+        bw = abs(lr - len(query)) + 20 if trial % 5 else int(rng.integers(1, 70))
+        yield ref, query, bw
+
+
+@pytest.mark.parametrize("preset", ["hifi", "ont"])
+def test_hmm_kernel_bodies_all_rows_bit_exact_vs_port(hostsim, oracle, preset):
+    """Both K4 bodies (sp_hmm.cuh generic, sp_hmm2.cuh shared-memory band) against the restated
+    probaln_glocal: state, q and the bits of the normalised max posterior at EVERY row."""
+    rng = np.random.default_rng(5)
+    op = oracle.preset_params(preset)
+    hp = hostsim.params_from_oracle(op)
+    n2 = 0
+    for ref, query, bw in _random_instances(rng, 120):
+        rows = np.arange(len(query), dtype=np.int32)
+        iq = np.full(len(query), op.set_q, np.uint8)
+        o = oracle.probaln(ref, query, iq, np.float32(op.conf_d), np.float32(op.conf_e), bw)
+        for got in (hostsim.hmm(hp, ref, query, bw, rows), hostsim.hmm2(hp, ref, query, bw, rows)):
+            if got is None:
+                continue
+            n2 += 1
+            assert np.array_equal(o["state"], got["state"])
+            assert np.array_equal(o["q"], got["q"])
+            assert np.array_equal(o["pmax"].view(np.int64), got["pmax"].view(np.int64))
+        # sparse marker rows (the pipeline's use): same answers as the all-rows run
+        if len(query) > 30:
+            sel = np.sort(rng.choice(len(query), size=3, replace=False)).astype(np.int32)
+            g2 = hostsim.hmm2(hp, ref, query, bw, sel)
+            if g2 is not None:
+                assert np.array_equal(o["state"][sel], g2["state"])
+                assert np.array_equal(o["q"][sel], g2["q"])
+    assert n2 > 150
