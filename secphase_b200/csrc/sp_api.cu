@@ -85,8 +85,11 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 enum { EV_START = 0, EV_H2D, EV_WALK, EV_GROUP, EV_EMIT, EV_HMM, EV_SCORE, EV_END, EV_N };
 
+#define SP_N_AUX 4
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t aux[SP_N_AUX] = {};  // the HMM class launches fork onto these and join back
+    cudaEvent_t ev_fork = nullptr, ev_join[SP_N_AUX] = {};
     cudaEvent_t ev[EV_N] = {};
     PinBuf h_in;    // staged batch (one H2D copy)
     DevBuf d_in;
@@ -95,7 +98,7 @@ struct Slot {
     bool safe_caps = false;
     // device work tables
     DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, item_off, row_off, sdbl_off, score,
-        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals;
+        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter;
     // host results
     PinBuf h_tot, h_gout, h_score, h_info, h_fin;
     SpBatchPtrs P;
@@ -203,7 +206,9 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
         return nullptr;
     }
     if (cudaFuncSetAttribute(k_hmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
+        cudaFuncSetAttribute(k_hmm2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
         set_err("sp_create: cudaFuncSetAttribute(k_hmm) failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
         return nullptr;
@@ -211,6 +216,11 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
     for (int s = 0; s < SP_N_SLOTS; s++) {
         cudaStreamCreateWithFlags(&c->slot[s].stream, cudaStreamNonBlocking);
         for (int k = 0; k < EV_N; k++) cudaEventCreate(&c->slot[s].ev[k]);
+        cudaEventCreateWithFlags(&c->slot[s].ev_fork, cudaEventDisableTiming);
+        for (int k = 0; k < SP_N_AUX; k++) {
+            cudaStreamCreateWithFlags(&c->slot[s].aux[k], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&c->slot[s].ev_join[k], cudaEventDisableTiming);
+        }
     }
     c->rng.seed(1);
     return c;
@@ -225,12 +235,17 @@ void sp_destroy(sp_ctx *c) {
         DevBuf *bufs[] = {&S.d_in, &S.ops, &S.imk, &S.info, &S.blk, &S.iv, &S.nb, &S.gpos, &S.ent, &S.res, &S.baq,
                           &S.gP, &S.gout, &S.gcnt, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
                           &S.fin, &S.items, &S.rows, &S.order, &S.bins, &S.class_start, &S.s_pool, &S.fsave,
-                          &S.gband, &S.totals};
+                          &S.gband, &S.totals, &S.work_counter};
         for (DevBuf *b : bufs) b->release();
         PinBuf *pins[] = {&S.h_in, &S.h_tot, &S.h_gout, &S.h_score, &S.h_info, &S.h_fin};
         for (PinBuf *b : pins) b->release();
         for (int k = 0; k < EV_N; k++)
             if (S.ev[k]) cudaEventDestroy(S.ev[k]);
+        if (S.ev_fork) cudaEventDestroy(S.ev_fork);
+        for (int k = 0; k < SP_N_AUX; k++) {
+            if (S.ev_join[k]) cudaEventDestroy(S.ev_join[k]);
+            if (S.aux[k]) cudaStreamDestroy(S.aux[k]);
+        }
         if (S.stream) cudaStreamDestroy(S.stream);
     }
     c->dC.release();
@@ -416,42 +431,71 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
     return SP_OK;
 }
 
-// K4 launches for instances already ordered by (band class, length): classes up to
+// K4 launches for instances already ordered by (band class, length).  Classes up to
 // SP_H2_MAXBW run k_hmm2 (band in shared memory, sp_hmm2.cuh); wider bands run the generic k_hmm,
-// whose band falls back to global memory when it outgrows shared memory.
+// whose band falls back to global memory when it outgrows shared memory.  Every class is an
+// independent launch on its own auxiliary stream, widest (= fewest, slowest instances) first, so
+// that a handful of wide instances overlaps with the bulk instead of trailing it.
+template <int NW>
+static void launch_hmm2(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first, int cnt, const uint8_t *ref,
+                        const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride) {
+    const int nblk = (cnt + 31) / 32;
+    const int ncell = sp_h2_cells(sp_class_bw(cls));
+    const size_t slab = (size_t) ncell * 32 * 24;
+    int wpc = (int) (c->max_smem / slab);  // warps per CTA = band slabs per SM
+    if (wpc > 8) wpc = 8;
+    if (wpc > nblk) wpc = nblk;
+    int grid = (nblk + wpc - 1) / wpc;
+    if (grid > c->sm_count) grid = c->sm_count;
+    k_hmm2<NW><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(),
+                                                   first, cnt, ncell, ref, qbytes, seq_pool, seq_off,
+                                                   S.s_pool.as<double>(), S.fsave.as<double>(), fs_stride,
+                                                   S.rows.as<SpRow>(), S.work_counter.as<int>() + cls);
+}
+
 static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_count, int max_bw, const uint8_t *ref,
                       const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride) {
-    static const int class_bw[SP_N_CLASSES] = {20, 22, 30, 62, 120, 0};
-    const SpConst *dC = c->dC.as<SpConst>();
-    int first = 0, rc;
-    for (int cls = 0; cls < SP_N_CLASSES; cls++) {
+    int rc;
+    if ((rc = S.work_counter.ensure(sizeof(int) * SP_N_CLASSES))) return rc;
+    CK(cudaMemsetAsync(S.work_counter.p, 0, sizeof(int) * SP_N_CLASSES, st));
+    int first[SP_N_CLASSES + 1];
+    first[0] = 0;
+    for (int cls = 0; cls < SP_N_CLASSES; cls++) first[cls + 1] = first[cls] + class_count[cls];
+    CK(cudaEventRecord(S.ev_fork, st));
+    int used = 0;
+    for (int cls = SP_N_CLASSES - 1; cls >= 0; cls--) {
         const int cnt = class_count[cls];
         if (cnt == 0) continue;
-        const int nblk = (cnt + 31) / 32;
-        if (class_bw[cls] != 0 && class_bw[cls] <= SP_H2_MAXBW) {
-            const int ncell = sp_h2_cells(class_bw[cls]);
-            k_hmm2<<<nblk, 32, (size_t) ncell * 32 * 24, st>>>(dC, S.items.as<SpItem>(), S.order.as<int32_t>(), first,
-                                                               cnt, ncell, ref, qbytes, seq_pool, seq_off,
-                                                               S.s_pool.as<double>(), S.fsave.as<double>(), fs_stride,
-                                                               S.rows.as<SpRow>());
+        cudaStream_t as = S.aux[used % SP_N_AUX];
+        if (used < SP_N_AUX) CK(cudaStreamWaitEvent(as, S.ev_fork, 0));
+        used++;
+        const int bwc = sp_class_bw(cls);
+        if (bwc != 0) {
+            const int nw = sp_h2_words(bwc);
+            if (nw == 1) launch_hmm2<1>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride);
+            else if (nw == 2) launch_hmm2<2>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride);
+            else launch_hmm2<3>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride);
         } else {
-            int W = sp_class_cells(cls);
+            const int nblk = (cnt + 31) / 32;
+            int W = 2 * max_bw + 2;
             double *gband = nullptr;
-            size_t smem = 0;
-            if (W == 0 || (size_t) W * 28 * 32 > c->max_smem) {
-                W = 2 * max_bw + 2;
-                if ((rc = S.gband.ensure((size_t) nblk * ((size_t) W * 28 * 32)))) return rc;
+            size_t smem = (size_t) W * 28 * 32;
+            if (smem > c->max_smem) {
+                if ((rc = S.gband.ensure((size_t) nblk * smem))) return rc;
                 gband = S.gband.as<double>();
-            } else {
-                smem = (size_t) W * 28 * 32;
+                smem = 0;
             }
-            k_hmm<<<nblk, 32, smem, st>>>(dC, S.items.as<SpItem>(), S.order.as<int32_t>(), first, cnt, W, ref, qbytes,
-                                          seq_pool, seq_off, S.s_pool.as<double>(), S.fsave.as<double>(), fs_stride,
-                                          S.rows.as<SpRow>(), gband);
+            k_hmm<<<nblk, 32, smem, as>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(), first[cls],
+                                          cnt, W, ref, qbytes, seq_pool, seq_off, S.s_pool.as<double>(),
+                                          S.fsave.as<double>(), fs_stride, S.rows.as<SpRow>(), gband);
         }
         S.launches++;
-        first += cnt;
     }
+    for (int k = 0; k < used && k < SP_N_AUX; k++) {
+        CK(cudaEventRecord(S.ev_join[k], S.aux[k]));
+        CK(cudaStreamWaitEvent(st, S.ev_join[k], 0));
+    }
+    CK(cudaGetLastError());
     return SP_OK;
 }
 
@@ -787,7 +831,8 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
     std::vector<SpRow> rows((size_t) n_rows + 1);
     int64_t ref_total = 0, q_total = 0, s_total = 0;
     int max_bw = 0;
-    int cls_count[SP_N_CLASSES] = {0, 0, 0, 0, 0, 0};
+    int cls_count[SP_N_CLASSES];
+    for (int k = 0; k < SP_N_CLASSES; k++) cls_count[k] = 0;
     for (int j = 0; j < n; j++) {
         if (l_ref[j] <= 0 || l_query[j] <= 0) {
             set_err("sp_hmm_batch: instance %d has an empty sequence", j);
@@ -810,7 +855,7 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
         if (query_off[j] + l_query[j] > q_total) q_total = query_off[j] + l_query[j];
         const int bw = sp_hmm_bw(I.l_ref, I.l_query, I.par_bw);
         if (bw > max_bw) max_bw = bw;
-        if (I.n_rows > 0) cls_count[sp_band_class6(bw)]++;
+        if (I.n_rows > 0) cls_count[sp_band_class(bw)]++;
         for (int64_t r = row_off[j]; r < row_off[j + 1]; r++) {
             SpRow &R = rows[(size_t) r];
             R.item = j;

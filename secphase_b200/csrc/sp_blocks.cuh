@@ -383,7 +383,7 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
             cnt.cells += sp_hmm_cells(l_ref, l_query, bw);
             cnt.s_doubles += l_query + 2;
             if (bw > cnt.max_bw) cnt.max_bw = bw;
-            if (n_rows > 0) cnt.class_count[sp_band_class6(bw)] += 1;
+            if (n_rows > 0) cnt.class_count[sp_band_class(bw)] += 1;
         }
         while (SP_MK_VALID(j) && SP_MK_BASE(j) <= blk.sqe) {
             if (blk.sqe - SP_BLOCK_MARGIN <= SP_MK_BASE(j)) {

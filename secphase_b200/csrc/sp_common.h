@@ -102,11 +102,17 @@ struct SpConst {
 // group status bits
 enum { SP_GERR_BLOCK_CAP = 1, SP_GERR_MARKER_CAP = 2, SP_GERR_OP_CAP = 4, SP_GERR_BADOP = 8 };
 
-// Band classes of the HMM kernel: instances of one class share a launch (same shared-memory
-// footprint); cells = circular band cells per lane (>= 2*bw+2); class 5 is sized per launch.
-#define SP_N_CLASSES 6
-SP_HD int sp_band_class6(int bw) { return bw <= 20 ? 0 : bw <= 22 ? 1 : bw <= 30 ? 2 : bw <= 62 ? 3 : bw <= 120 ? 4 : 5; }
-SP_HD int sp_class_cells(int cls) { return cls == 0 ? 42 : cls == 1 ? 46 : cls == 2 ? 62 : cls == 3 ? 126 : cls == 4 ? 242 : 0; }
+// Band classes of the HMM kernels: instances of one class share a launch (same shared-memory
+// slab per warp).  Classes 0..SP_N_CLASSES-2 run the shared-memory-band kernel (sp_hmm2.cuh); the
+// bounds are where one more warp's slab stops fitting an SM (7,6,5,4,3,2,1 warps of 2*bw+3 cells x
+// 768 B in 227 KB).  The last class is the generic kernel (sp_hmm.cuh), sized per launch.
+#define SP_N_CLASSES 8
+SP_HD int sp_class_bw(int cls) {
+    return cls == 0 ? 20 : cls == 1 ? 22 : cls == 2 ? 27 : cls == 3 ? 36 : cls == 4 ? 48 : cls == 5 ? 62 : cls == 6 ? 94 : 0;
+}
+SP_HD int sp_band_class(int bw) {
+    return bw <= 20 ? 0 : bw <= 22 ? 1 : bw <= 27 ? 2 : bw <= 36 ? 3 : bw <= 48 ? 4 : bw <= 62 ? 5 : bw <= 94 ? 6 : 7;
+}
 
 SP_HD int sp_min(int a, int b) { return a < b ? a : b; }
 SP_HD int sp_max(int a, int b) { return b < a ? a : b; }

@@ -29,7 +29,62 @@
 #include "sp_hmm.cuh"
 
 #define SP_H2_U 4
-#define SP_H2_MAXBW 30  // 2*bw+1 <= 61 cells: the per-row emission masks are 64-bit
+#define SP_H2_MAXBW 94  // 2*bw+1 <= 189 cells: the per-row emission masks are NW <= 3 64-bit words
+SP_HD int sp_h2_words(int bw) { return (2 * bw + 1 + 63) >> 6; }
+
+// NW x 64 bits, bit o <-> band cell o.  All indexing is by unrolled compare-and-select so that the
+// words stay in registers.
+template <int NW>
+struct SpBits {
+    uint64_t w[NW];
+    SP_HD void clear() {
+#pragma unroll
+        for (int k = 0; k < NW; k++) w[k] = 0;
+    }
+    SP_HD void shr1() {
+#pragma unroll
+        for (int k = 0; k < NW; k++) w[k] = (w[k] >> 1) | (k + 1 < NW ? w[k + 1 < NW ? k + 1 : k] << 63 : 0);
+    }
+    SP_HD void shl1_in(uint64_t bit) {
+#pragma unroll
+        for (int k = NW - 1; k >= 0; k--) w[k] = (w[k] << 1) | (k ? w[k ? k - 1 : 0] >> 63 : bit);
+    }
+    SP_HD void or_bit(int pos, uint64_t bit) {
+#pragma unroll
+        for (int k = 0; k < NW; k++)
+            if ((pos >> 6) == k) w[k] |= bit << (pos & 63);
+    }
+    SP_HD uint32_t from(int o) const {  // bits o, o+1, ... of the word holding o (o multiple of 4 => 4 bits valid)
+        uint64_t x = w[0];
+#pragma unroll
+        for (int k = 1; k < NW; k++)
+            if ((o >> 6) == k) x = w[k];
+        return (uint32_t) (x >> (o & 63));
+    }
+    SP_HD bool any_below(int n) const {
+        uint64_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const int m = n - 64 * k;
+            acc |= m <= 0 ? 0 : (m >= 64 ? w[k] : (w[k] & (((uint64_t) 1 << m) - 1)));
+        }
+        return acc != 0;
+    }
+};
+
+// match / N masks of one row from the three code bit-planes and the row's query base
+template <int NW>
+SP_HD void sp_h2_row_masks(const SpBits<NW> &p0, const SpBits<NW> &p1, const SpBits<NW> &p2, int qc, SpBits<NW> &mm,
+                           SpBits<NW> &nn) {
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        if (qc > 3) { mm.w[k] = 0; nn.w[k] = ~(uint64_t) 0; }
+        else {
+            mm.w[k] = ((qc & 1) ? p0.w[k] : ~p0.w[k]) & ((qc & 2) ? p1.w[k] : ~p1.w[k]) & ~p2.w[k];
+            nn.w[k] = p2.w[k];
+        }
+    }
+}
 
 #if defined(__CUDACC__)
 typedef double2 SpD2;
@@ -49,7 +104,7 @@ struct SpBand2 {
 SP_HD int sp_h2_cells(int bw) { return 2 * bw + 3; }  // cells -1 .. 2bw+1
 
 // rinv[i], i = 1..l_query : 1/s[i].   fsave + r*fs_stride : scaled forward (M,I) of marker row r, [o*2+{0,1}].
-template <int STRIDE>
+template <int STRIDE, int NW>
 SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<STRIDE> B, double *rinv, double *fsave,
                             int64_t fs_stride, SpRow *rows, int n_rows) {
     constexpr int U = SP_H2_U;
@@ -72,7 +127,8 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
     const double emA = C.em_match, emB = C.em_mis;
 
     // bit-planes of the reference codes under the band: bit o <-> ref[beg-1+o] (column beg+o)
-    uint64_t p0 = 0, p1 = 0, p2 = 0;
+    SpBits<NW> p0, p1, p2;
+    p0.clear(); p1.clear(); p2.clear();
     int nr = 0;  // next marker row (rows are ascending in t)
 
     // ------------------------------------------------------------------ forward, row 1
@@ -83,9 +139,9 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         double sum = 0.;
         for (int o = 0; o < n_prev; o++) {
             const int rc = in.ref[o];
-            p0 |= (uint64_t) (rc & 1) << o;
-            p1 |= (uint64_t) ((rc >> 1) & 1) << o;
-            p2 |= (uint64_t) ((rc >> 2) & 1) << o;
+            p0.or_bit(o, (uint64_t) (rc & 1));
+            p1.or_bit(o, (uint64_t) ((rc >> 1) & 1));
+            p2.or_bit(o, (uint64_t) ((rc >> 2) & 1));
             SpD2 v;
             v.x = SP_DMUL(sp_emis(C, rc, qc), bM);
             v.y = SP_DMUL(SP_HMM_EI, bI);
@@ -106,24 +162,32 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         s_last = sum;
     }
     // ------------------------------------------------------------------ forward, rows 2..Lq
+    // Global reads (query base, entering reference base, next marker row) are issued one row ahead
+    // of their use so that their latency hides behind a whole row of arithmetic.
     double r = 1.;
     int beg_prev = 1, end_prev = n_prev;
+    int t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
+    int qc_next = Lq >= 2 ? sp_query_code(in, 1) : 0;
+    int rc_next = 2 + bw <= Lr ? in.ref[1 + bw] : 0;  // the column entering at row 2, if any
     for (int i = 2; i <= Lq; i++) {
         const int beg = i - bw > 1 ? i - bw : 1;
         const int end = i + bw < Lr ? i + bw : Lr;
         const int n = end - beg + 1;
         const int sh = beg - beg_prev;
-        const int qc = sp_query_code(in, i - 1);
-        if (sh) { p0 >>= 1; p1 >>= 1; p2 >>= 1; }
+        const int qc = qc_next;
+        const int rc_in = rc_next;
+        if (i < Lq) qc_next = sp_query_code(in, i);
+        if (i + 1 + bw <= Lr) rc_next = in.ref[i + bw];
+        if (sh) { p0.shr1(); p1.shr1(); p2.shr1(); }
         if (end > end_prev) {  // one column enters the band on the right
-            const int rc = in.ref[end - 1];
-            p0 |= (uint64_t) (rc & 1) << (n - 1);
-            p1 |= (uint64_t) ((rc >> 1) & 1) << (n - 1);
-            p2 |= (uint64_t) ((rc >> 2) & 1) << (n - 1);
+            p0.or_bit(n - 1, (uint64_t) (rc_in & 1));
+            p1.or_bit(n - 1, (uint64_t) ((rc_in >> 1) & 1));
+            p2.or_bit(n - 1, (uint64_t) ((rc_in >> 2) & 1));
         }
-        uint64_t mm, nn;  // bit o: reference base of column beg+o equals the query base / emission is 1 (an N)
-        if (qc > 3) { mm = 0; nn = ~(uint64_t) 0; }
-        else { mm = ((qc & 1) ? p0 : ~p0) & ((qc & 2) ? p1 : ~p1) & ~p2; nn = p2; }
+        SpBits<NW> mm, nn;  // bit o: reference base of column beg+o equals the query base / emission is 1 (an N)
+        sp_h2_row_masks(p0, p1, p2, qc, mm, nn);
+        // rows whose band holds an N (rare) take the one-cell-at-a-time code, which knows about nn
+        const bool has_n = nn.any_below(n);
 
         // old row (i-1): M[i,o] reads old cell o-1+sh, I[i,o] reads old cell o+sh
         const SpD2 *omi = B.mi + sh * STRIDE;
@@ -137,7 +201,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
 
         // parallel part of U cells starting at o0: everything that does not depend on this row's D chain
         auto fwdP = [&](int o0, double (&t)[U], double (&u)[U]) {
-            const uint32_t mb = (uint32_t) (mm >> o0), nb = (uint32_t) (nn >> o0);
+            const uint32_t mb = mm.from(o0);
             double qM[U], qI[U], qD[U];
 #pragma unroll
             for (int j = 0; j < U; j++) {
@@ -149,7 +213,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
             for (int j = 0; j < U; j++) {
                 const double aM = j ? qM[j ? j - 1 : 0] : pM, aI = j ? qI[j ? j - 1 : 0] : pI,
                              aD = j ? qD[j ? j - 1 : 0] : pD;
-                const double e = ((nb >> j) & 1) ? 1. : (((mb >> j) & 1) ? emA : emB);
+                const double e = ((mb >> j) & 1) ? emA : emB;
                 SpD2 v;
                 v.x = SP_DMUL(e, SP_DADD(SP_DADD(SP_DMUL(m0, aM), SP_DMUL(m3, aI)), SP_DMUL(m6, aD)));
                 v.y = SP_DADD(SP_DMUL(eim1, qM[j]), SP_DMUL(eim4, qI[j]));
@@ -169,7 +233,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
                 B.d[(o0 + j) * STRIDE] = cD;
             }
         };
-        const int nfull = n / U;
+        const int nfull = has_n ? 0 : n / U;
         if (nfull > 0) {
             double tA[U], uA[U], tB[U], uB[U];
             fwdP(0, tA, uA);
@@ -191,7 +255,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         for (int o = nfull * U; o < n; o++) {  // remainder cells, one at a time
             const SpD2 a = omi[o * STRIDE];
             const double qM = SP_DMUL(a.x, r), qI = SP_DMUL(a.y, r), qD = SP_DMUL(od[o * STRIDE], r);
-            const double e = ((nn >> o) & 1) ? 1. : (((mm >> o) & 1) ? emA : emB);
+            const double e = (nn.from(o) & 1) ? 1. : ((mm.from(o) & 1) ? emA : emB);
             SpD2 v;
             v.x = SP_DMUL(e, SP_DADD(SP_DADD(SP_DMUL(m0, pM), SP_DMUL(m3, pI)), SP_DMUL(m6, pD)));
             v.y = SP_DADD(SP_DMUL(eim1, qM), SP_DMUL(eim4, qI));
@@ -205,7 +269,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         const double ri = SP_DDIV(1., sum);
         rinv[i] = ri;
         s_last = sum;
-        if (nr < n_rows && rows[nr].t + 1 == i) {  // marker row: keep the scaled forward M,I
+        if (t_next + 1 == i) {  // marker row: keep the scaled forward M,I
             double *fs = fsave + (int64_t) nr * fs_stride;
             for (int o = 0; o < n; o++) {
                 const SpD2 a = B.mi[o * STRIDE];
@@ -213,6 +277,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
                 fs[o * 2 + 1] = SP_DMUL(a.y, ri);
             }
             nr++;
+            t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
         }
         r = ri;
         beg_prev = beg;
@@ -263,32 +328,46 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         if (nr < 0) return;
     }
     // planes re-aligned for the backward sweep: bit o <-> ref[beg+o] (the base of column beg+o+1)
-    p0 >>= 1; p1 >>= 1; p2 >>= 1;
+    p0.shr1(); p1.shr1(); p2.shr1();
     int beg_next = beg_prev, end_next = end_prev;  // band of row i+1
+    t_next = rows[nr].t;
+    qc_next = Lq >= 2 ? sp_query_code(in, Lq - 1) : 0;
+    {
+        const int b = Lq - 1 - bw > 1 ? Lq - 1 - bw : 1;
+        rc_next = (b != beg_prev && b < Lr) ? in.ref[b] : 0;
+    }
+    double rinv_i = Lq >= 2 ? rinv[Lq - 1] : 1.;  // 1/s[i], fetched one row before it scales row i
+    double r1 = 1.;                               // row Lq is stored in its final scale
     for (int i = Lq - 1; i >= i_stop; i--) {
         const int beg = i - bw > 1 ? i - bw : 1;
         const int end = i + bw < Lr ? i + bw : Lr;
         const int n = end - beg + 1;
         const int sh = beg_next - beg;
-        const int qc = sp_query_code(in, i);  // query[i] (0-based) == base of row i+1
-        const double r1 = (i + 1 == Lq) ? 1. : rinv[i + 1];
+        const int qc = qc_next;  // query[i] (0-based) == base of row i+1
+        const int rc_in = rc_next;
+        const double y = rinv_i;
+        if (i > i_stop) {
+            qc_next = sp_query_code(in, i - 1);
+            const int b = i - 1 - bw > 1 ? i - 1 - bw : 1;
+            rc_next = (b != beg && b < Lr) ? in.ref[b] : 0;  // (the bit of column Lr+1 is never consumed)
+            rinv_i = rinv[i - 1];
+        }
         const double m6e = i > 1 ? m6 : 0., m8e = i > 1 ? m8 : 0.;
         if (sh) {  // one column enters the band on the left
-            const int rc = beg < Lr ? in.ref[beg] : 0;  // (the bit of column Lr+1 is never consumed)
-            p0 = (p0 << 1) | (uint64_t) (rc & 1);
-            p1 = (p1 << 1) | (uint64_t) ((rc >> 1) & 1);
-            p2 = (p2 << 1) | (uint64_t) ((rc >> 2) & 1);
+            p0.shl1_in((uint64_t) (rc_in & 1));
+            p1.shl1_in((uint64_t) ((rc_in >> 1) & 1));
+            p2.shl1_in((uint64_t) ((rc_in >> 2) & 1));
         }
-        uint64_t mm, nn;
-        if (qc > 3) { mm = 0; nn = ~(uint64_t) 0; }
-        else { mm = ((qc & 1) ? p0 : ~p0) & ((qc & 2) ? p1 : ~p1) & ~p2; nn = p2; }
+        SpBits<NW> mm, nn;
+        sp_h2_row_masks(p0, p1, p2, qc, mm, nn);
+        const bool has_n = nn.any_below(n);
         // old row (i+1): cell o needs bI of old cell o-sh and bM of old cell o+1-sh
         const SpD2 *omi = B.mi - sh * STRIDE;
         double nM = (end + 1 <= end_next) ? SP_DMUL(omi[n * STRIDE].x, r1) : 0.;  // scaled bM[i+1][end+1]
         double cD = 0.;
 
         auto bwdP = [&](int o0, double (&X)[U], double (&bIv)[U], double (&w)[U]) {
-            const uint32_t mb = (uint32_t) (mm >> o0), nb = (uint32_t) (nn >> o0);
+            const uint32_t mb = mm.from(o0);
             double qM[U], qI[U];
 #pragma unroll
             for (int j = 0; j < U; j++) {
@@ -298,7 +377,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
 #pragma unroll
             for (int j = U - 1; j >= 0; j--) {
                 const double up = (j == U - 1) ? nM : qM[j < U - 1 ? j + 1 : 0];
-                const double em = ((nb >> j) & 1) ? 1. : (((mb >> j) & 1) ? emA : emB);
+                const double em = ((mb >> j) & 1) ? emA : emB;
                 const double e = SP_DMUL(em, up);
                 X[j] = SP_DADD(SP_DMUL(e, m0), SP_DMUL(eim1, qI[j]));
                 bIv[j] = SP_DADD(SP_DMUL(e, m3), SP_DMUL(eim4, qI[j]));
@@ -316,11 +395,11 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
                 B.mi[(o0 + j) * STRIDE] = v;
             }
         };
-        const int nfull = (n - 1) / U;  // the top cell always goes through the generic single-cell code
+        const int nfull = has_n ? 0 : (n - 1) / U;  // the top cell always goes through the generic single-cell code
         for (int o = n - 1; o >= nfull * U; o--) {
             const SpD2 a = omi[o * STRIDE];
             const double qM = SP_DMUL(a.x, r1), qI = SP_DMUL(a.y, r1);
-            const double em = (beg + o >= Lr) ? 0. : (((nn >> o) & 1) ? 1. : (((mm >> o) & 1) ? emA : emB));
+            const double em = (beg + o >= Lr) ? 0. : ((nn.from(o) & 1) ? 1. : ((mm.from(o) & 1) ? emA : emB));
             const double e = SP_DMUL(em, nM);
             SpD2 v;
             v.x = SP_DADD(SP_DADD(SP_DMUL(e, m0), SP_DMUL(eim1, qI)), SP_DMUL(m2, cD));
@@ -350,9 +429,11 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         }
         beg_next = beg;
         end_next = end;
-        if (nr >= 0 && rows[nr].t + 1 == i) {
-            map_row(nr, beg, n, rinv[i], true);
+        r1 = y;
+        if (t_next + 1 == i) {
+            map_row(nr, beg, n, y, true);
             nr--;
+            t_next = nr >= 0 ? rows[nr].t : -2;
         }
     }
 }

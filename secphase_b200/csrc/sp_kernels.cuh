@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(1024) k_scan_groups(SpBatchPtrs B, SpTotals *t
     __syncthreads();
     int32_t li = 0, lr = 0, lbw = 0;
     int64_t ls = 0, lc = 0;
-    int32_t lcls[SP_N_CLASSES] = {0, 0, 0, 0, 0, 0};
+    int32_t lcls[SP_N_CLASSES];
+    for (int k = 0; k < SP_N_CLASSES; k++) lcls[k] = 0;
     for (int g = g0; g < g1; g++) {
         const SpEmitCounts c = B.gcnt[g];
         li += c.n_items;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(64) k_emit(SpBatchPtrs B, const SpConst *__res
 __device__ __forceinline__ int sp_item_key(const SpItem &it) {
     const int bw = sp_hmm_bw(it.l_ref, it.l_query, it.par_bw);
     const int lq = it.l_query < SP_SORT_LBINS - 1 ? it.l_query : SP_SORT_LBINS - 1;
-    const int cls = it.n_rows > 0 ? sp_band_class6(bw) : SP_N_CLASSES;  // row-less instances are not run
+    const int cls = it.n_rows > 0 ? sp_band_class(bw) : SP_N_CLASSES;  // row-less instances are not run
     return cls * SP_SORT_LBINS + (SP_SORT_LBINS - 1 - lq);
 }
 __global__ void k_sort_hist(const SpItem *items, int n, int32_t *bins) {
@@ -316,45 +317,58 @@ __global__ void __launch_bounds__(32) k_hmm(const SpConst *__restrict__ Cp, cons
 }
 
 
-// Main K4 kernel (band half-width <= SP_H2_MAXBW): one warp per CTA, one HMM instance per lane,
-// band in dynamic shared memory: ncell x 32 double2 (M,I) followed by ncell x 32 double (D),
-// lane-interleaved; see sp_hmm2.cuh.
-__global__ void __launch_bounds__(32) k_hmm2(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
-                                             const int32_t *__restrict__ order, int first, int count, int ncell,
-                                             const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qbytes,
-                                             const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,
-                                             double *__restrict__ s_pool, double *__restrict__ fsave, int64_t fs_stride,
-                                             SpRow *rows) {
+// Main K4 kernel (band half-width <= SP_H2_MAXBW): persistent CTAs (one per SM, as many warps as
+// band slabs fit the SM's shared memory), one HMM instance per lane.  Warps pull sets of 32
+// instances from a global counter in (band class, length)-sorted order, i.e. longest first, so the
+// SMs drain together.  Per-warp slab in dynamic shared memory: ncell x 32 double2 (M,I) followed
+// by ncell x 32 double (D), lane-interleaved; see sp_hmm2.cuh.
+template <int NW>
+__global__ void __launch_bounds__(256) k_hmm2(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
+                                              const int32_t *__restrict__ order, int first, int count, int ncell,
+                                              const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qbytes,
+                                              const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,
+                                              double *__restrict__ s_pool, double *__restrict__ fsave, int64_t fs_stride,
+                                              SpRow *rows, int *work_counter) {
     extern __shared__ double2 smem2[];
-    const int lane = threadIdx.x;
-    const int slot = blockIdx.x * 32 + lane;
-    if (slot >= count) return;
-    const SpItem it = items[order ? order[first + slot] : first + slot];
-    double2 *mi = smem2 + lane;
-    double *d = reinterpret_cast<double *>(smem2 + ncell * 32) + lane;
-    for (int c = 0; c < ncell; c++) {
-        mi[c * 32] = make_double2(0., 0.);
-        d[c * 32] = 0.;
+    const int lane = threadIdx.x & 31;
+    double2 *slab = smem2 + (size_t) (threadIdx.x >> 5) * ncell * 48;  // ncell*32*(16+8) bytes per warp
+    double2 *mi = slab + lane;
+    double *d = reinterpret_cast<double *>(slab + ncell * 32) + lane;
+    const int nwork = (count + 31) >> 5;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nwork) break;
+        const int slot = w * 32 + lane;
+        if (slot < count) {
+            const SpItem it = items[order ? order[first + slot] : first + slot];
+            for (int c = 0; c < ncell; c++) {
+                mi[c * 32] = make_double2(0., 0.);
+                d[c * 32] = 0.;
+            }
+            SpBand2<32> B;
+            B.mi = mi + 32;  // cell -1 is the permanent zero cell
+            B.d = d + 32;
+            SpHmmIn in;
+            in.ref = ref + it.ref_off;
+            if (it.query_off >= 0) {
+                in.qbytes = qbytes;
+                in.qseq4 = nullptr;
+                in.q0 = it.query_off;
+            } else {
+                in.qbytes = nullptr;
+                in.qseq4 = seq_pool + seq_off[it.aln];
+                in.q0 = it.q_sqs;
+            }
+            in.l_ref = it.l_ref;
+            in.l_query = it.l_query;
+            in.par_bw = it.par_bw;
+            sp_hmm2_instance<32, NW>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
+                                 rows + it.row0, it.n_rows);
+        }
+        __syncwarp();
     }
-    SpBand2<32> B;
-    B.mi = mi + 32;  // cell -1 is the permanent zero cell
-    B.d = d + 32;
-    SpHmmIn in;
-    in.ref = ref + it.ref_off;
-    if (it.query_off >= 0) {
-        in.qbytes = qbytes;
-        in.qseq4 = nullptr;
-        in.q0 = it.query_off;
-    } else {
-        in.qbytes = nullptr;
-        in.qseq4 = seq_pool + seq_off[it.aln];
-        in.q0 = it.q_sqs;
-    }
-    in.l_ref = it.l_ref;
-    in.l_query = it.l_query;
-    in.par_bw = it.par_bw;
-    sp_hmm2_instance<32>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
-                         rows + it.row0, it.n_rows);
 }
 
 __global__ void __launch_bounds__(64) k_score(SpBatchPtrs B, const SpConst *__restrict__ Cp, const SpRow *rows,

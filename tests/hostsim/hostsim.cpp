@@ -121,7 +121,12 @@ int hs_hmm2(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *qu
     in.l_ref = l_ref; in.l_query = l_query; in.par_bw = par_bw;
     SpBand2<1> B;
     B.mi = mi.data() + 1; B.d = d.data() + 1;
-    sp_hmm2_instance<1>(C, in, B, rinv.data(), fsave.data(), 2 * (2 * bw + 1), rows.data(), n_rows);
+    const int64_t fss = 2 * (2 * bw + 1);
+    switch (sp_h2_words(sp_class_bw(sp_band_class(bw)))) {  // same instantiation as launch_hmm() picks
+        case 1: sp_hmm2_instance<1, 1>(C, in, B, rinv.data(), fsave.data(), fss, rows.data(), n_rows); break;
+        case 2: sp_hmm2_instance<1, 2>(C, in, B, rinv.data(), fsave.data(), fss, rows.data(), n_rows); break;
+        default: sp_hmm2_instance<1, 3>(C, in, B, rinv.data(), fsave.data(), fss, rows.data(), n_rows); break;
+    }
     for (int i = 0; i < n_rows; i++) {
         state[i] = rows[i].state;
         q[i] = (uint8_t) rows[i].q;
@@ -290,7 +295,12 @@ int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes,
             for (auto &v : mi) v.x = v.y = 0.0;
             SpBand2<1> B2;
             B2.mi = mi.data() + 1; B2.d = dd.data() + 1;
-            sp_hmm2_instance<1>(C, in, B2, s.data(), fsave.data(), 2 * (2 * bw + 1), rows.data() + I.row0, I.n_rows);
+            const int64_t fss = 2 * (2 * bw + 1);
+            switch (sp_h2_words(sp_class_bw(sp_band_class(bw)))) {
+                case 1: sp_hmm2_instance<1, 1>(C, in, B2, s.data(), fsave.data(), fss, rows.data() + I.row0, I.n_rows); break;
+                case 2: sp_hmm2_instance<1, 2>(C, in, B2, s.data(), fsave.data(), fss, rows.data() + I.row0, I.n_rows); break;
+                default: sp_hmm2_instance<1, 3>(C, in, B2, s.data(), fsave.data(), fss, rows.data() + I.row0, I.n_rows); break;
+            }
         } else {
             SpBand<1> B;
             B.row = band.data(); B.code = code.data(); B.W = W;
