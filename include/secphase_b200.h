@@ -101,8 +101,18 @@ typedef struct sp_result {
     int32_t gpu_launches;      /* kernels launched for this batch */
 } sp_result;
 
-/* Asynchronous: packs the groups into the slot's pinned staging buffer, then enqueues
- * H2D copy -> kernels -> D2H copy on the slot's stream.  slot in [0, SP_N_SLOTS). */
+/* Page-locked host memory for the pools of an sp_flat_batch (cigar_pool, tag_pool, seq_pool,
+ * qual_pool).  The reference hands each worker a pointer to records the reader thread already
+ * holds in memory (secphase.c:303, 338); the equivalent here is that the BAM reader decodes
+ * straight into these buffers, from which sp_submit copies to the device without an intermediate
+ * host copy.  Pools in ordinary (pageable) memory are accepted too and are staged first.
+ * The caller must keep a submitted batch's pools unchanged until sp_wait returns. */
+void *sp_host_alloc(size_t bytes); /* NULL on error */
+void sp_host_free(void *p);
+
+/* Asynchronous: stages the per-alignment metadata (and any pageable pool) into the slot's pinned
+ * buffer, then enqueues H2D copies -> kernels -> D2H copy on the slot's stream.
+ * slot in [0, SP_N_SLOTS). */
 int sp_submit(sp_ctx *ctx, const sp_flat_batch *batch, int slot);
 /* Blocks until the slot's batch is complete, replays the tie-break RNG for its groups and fills
  * *out; the pointers stay valid until the next sp_submit on the same slot. */

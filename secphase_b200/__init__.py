@@ -5,6 +5,8 @@ CPU implementation in this package: importing works anywhere (so that the build 
 on a GPU-less box), but every call that computes raises SecphaseError when the CUDA library or a
 CUDA device is missing.
 """
-from .api import (LIB_PATH, Secphase, SecphaseError, SpParams, load_library, params_for)  # noqa: F401
+from .api import (LIB_PATH, PinnedArray, Secphase, SecphaseError, SpParams, load_library, params_for,  # noqa: F401
+                  pin_batch)
 
-__all__ = ["Secphase", "SecphaseError", "SpParams", "params_for", "load_library", "LIB_PATH"]
+__all__ = ["Secphase", "SecphaseError", "SpParams", "params_for", "load_library", "LIB_PATH", "pin_batch",
+           "PinnedArray"]

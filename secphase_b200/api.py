@@ -94,6 +94,9 @@ def load_library(path=None):
     L.sp_hmm_batch.restype = C.c_int
     L.sp_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.sp_fp64_peak.restype = C.c_int
+    L.sp_host_alloc.argtypes = [C.c_size_t]
+    L.sp_host_alloc.restype = C.c_void_p
+    L.sp_host_free.argtypes = [C.c_void_p]
     L.sp_rng_seed.argtypes = [C.c_void_p, C.c_uint]
     L.sp_rng_next.argtypes = [C.c_void_p]
     L.sp_rng_next.restype = C.c_int
@@ -104,8 +107,45 @@ def load_library(path=None):
 EXPORTED_SYMBOLS = [
     "sp_params_default", "sp_params_preset", "sp_create", "sp_destroy", "sp_last_error", "sp_version",
     "sp_set_reference_ascii", "sp_set_reference_codes", "sp_submit", "sp_wait", "sp_upload", "sp_run_resident",
-    "sp_debug_table", "sp_hmm_batch", "sp_fp64_peak", "sp_rng_seed", "sp_rng_next",
+    "sp_debug_table", "sp_hmm_batch", "sp_fp64_peak", "sp_rng_seed", "sp_rng_next", "sp_host_alloc", "sp_host_free",
 ]
+
+
+class PinnedArray:
+    """numpy view over page-locked memory from sp_host_alloc (freed when the object dies)."""
+
+    def __init__(self, like):
+        L = load_library()
+        like = np.ascontiguousarray(like)
+        self._L = L
+        self.nbytes = max(int(like.nbytes), 1)
+        self.ptr = L.sp_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise SecphaseError(L.sp_last_error().decode())
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=like.dtype, count=like.size)
+        self.array[...] = like.ravel()
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._L.sp_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pin_batch(batch):
+    """Copy of a FlatBatch whose four pools live in page-locked memory (what a reader thread that
+    decodes straight into sp_host_alloc'ed buffers would hand to sp_submit)."""
+    import copy
+    out = copy.copy(batch)
+    out._pins = []
+    for name in ("cigar_pool", "tag_pool", "seq_pool", "qual_pool"):
+        pa = PinnedArray(getattr(batch, name))
+        out._pins.append(pa)
+        setattr(out, name, pa.array)
+    return out
 
 
 def params_for(preset=None, **overrides):

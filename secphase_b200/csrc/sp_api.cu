@@ -91,9 +91,14 @@ struct Slot {
     cudaStream_t aux[SP_N_AUX] = {};  // the HMM class launches fork onto these and join back
     cudaEvent_t ev_fork = nullptr, ev_join[SP_N_AUX] = {};
     cudaEvent_t ev[EV_N] = {};
-    PinBuf h_in;    // staged batch (one H2D copy)
+    PinBuf h_in;    // staged batch: metadata always, pools only when the caller's are pageable
     DevBuf d_in;
-    size_t in_bytes = 0;
+    size_t in_bytes = 0, meta_bytes = 0, tag_pad_off = 0;
+    struct Copy {
+        const void *src;
+        size_t off, bytes;
+    } copies[4];
+    int n_copies = 0;
     SpPlan plan;
     bool safe_caps = false;
     // device work tables
@@ -254,6 +259,18 @@ void sp_destroy(sp_ctx *c) {
     delete c;
 }
 
+void *sp_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        set_err("sp_host_alloc(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void sp_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 void sp_rng_seed(sp_ctx *c, unsigned seed) { c->rng.seed(seed); }
 int sp_rng_next(sp_ctx *c) { return c->rng.next(); }
 
@@ -317,6 +334,15 @@ struct InLayout {
     size_t total;
 };
 
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 static InLayout make_layout(const sp_flat_batch *b, const SpPlan &pl) {
     InLayout L;
     size_t o = 0;
@@ -370,9 +396,26 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
     put(L.ops_off, pl.ops_off.data()); put(L.imk_off, pl.imk_off.data());
     put(L.gpos_off, pl.gpos_off.data()); put(L.gent_off, pl.gent_off.data());
     put(L.gblk_off, pl.gblk_off.data()); put(L.giv_off, pl.giv_off.data());
-    put(L.cigar_pool, b->cigar_pool); put(L.tag_pool, b->tag_pool); put(L.seq_pool, b->seq_pool);
-    put(L.qual_pool, b->qual_pool);
-    memset(h + L.tag_pool.off + L.tag_pool.bytes, 0, 16);
+    // The four pools are the bulk of a batch.  A pool the caller keeps in page-locked memory
+    // (sp_host_alloc, or any cudaHostAlloc/cudaHostRegister'ed range) is copied to the device
+    // straight from where it lies; a pageable pool is first staged into the slot's pinned buffer.
+    S.n_copies = 0;
+    auto pool = [&](const Section &sec, const void *src) {
+        if (sec.bytes == 0) return;
+        Slot::Copy &cp = S.copies[S.n_copies++];
+        cp.off = sec.off;
+        cp.bytes = sec.bytes;
+        if (is_pinned(src)) {
+            cp.src = src;
+        } else {
+            memcpy(h + sec.off, src, sec.bytes);
+            cp.src = h + sec.off;
+        }
+    };
+    S.meta_bytes = L.cigar_pool.off;  // everything before the pools is small per-alignment metadata
+    pool(L.cigar_pool, b->cigar_pool); pool(L.tag_pool, b->tag_pool); pool(L.seq_pool, b->seq_pool);
+    pool(L.qual_pool, b->qual_pool);
+    S.tag_pad_off = L.tag_pool.off + L.tag_pool.bytes;
     S.in_bytes = L.total;
 
     // device work tables
@@ -558,6 +601,16 @@ static int run_pipeline(sp_ctx *c, Slot &S) {
     return SP_OK;
 }
 
+static int enqueue_h2d(Slot &S) {
+    cudaStream_t st = S.stream;
+    uint8_t *d = S.d_in.as<uint8_t>();
+    CK(cudaMemcpyAsync(d, S.h_in.p, S.meta_bytes, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < S.n_copies; k++)
+        CK(cudaMemcpyAsync(d + S.copies[k].off, S.copies[k].src, S.copies[k].bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d + S.tag_pad_off, 0, 16, st));  // SpByteReader may read one aligned word past the tags
+    return SP_OK;
+}
+
 static int enqueue_results(Slot &S) {
     cudaStream_t st = S.stream;
     const size_t G = (size_t) S.P.G, A = (size_t) S.P.A;
@@ -587,7 +640,7 @@ int sp_submit(sp_ctx *c, const sp_flat_batch *b, int slot) {
     int rc = stage_batch(c, S, b);
     if (rc) return rc;
     CK(cudaEventRecord(S.ev[EV_START], S.stream));
-    CK(cudaMemcpyAsync(S.d_in.p, S.h_in.p, S.in_bytes, cudaMemcpyHostToDevice, S.stream));
+    if ((rc = enqueue_h2d(S))) return rc;
     CK(cudaEventRecord(S.ev[EV_H2D], S.stream));
     S.h2d_bytes = (int64_t) S.in_bytes;
     rc = run_pipeline(c, S);
@@ -607,7 +660,7 @@ int sp_upload(sp_ctx *c, const sp_flat_batch *b, int slot) {
     S.safe_caps = false;
     int rc = stage_batch(c, S, b);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(S.d_in.p, S.h_in.p, S.in_bytes, cudaMemcpyHostToDevice, S.stream));
+    if ((rc = enqueue_h2d(S))) return rc;
     CK(cudaStreamSynchronize(S.stream));
     S.h2d_bytes = 0;
     S.state = 1;

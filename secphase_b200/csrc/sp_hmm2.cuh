@@ -103,6 +103,16 @@ struct SpBand2 {
 
 SP_HD int sp_h2_cells(int bw) { return 2 * bw + 3; }  // cells -1 .. 2bw+1
 
+// Query base i0 in two steps, so that the load can be issued a whole row before the decode needs it.
+SP_HD uint32_t sp_query_raw(const SpHmmIn &in, int i0) {
+    return in.qbytes ? in.qbytes[in.q0 + i0] : in.qseq4[(in.q0 + i0) >> 1];
+}
+SP_HD int sp_query_decode(const SpHmmIn &in, int i0, uint32_t raw) {
+    if (in.qbytes) return (int) raw;
+    const int nib = (raw >> ((~(in.q0 + i0) & 1) << 2)) & 0xf;  // bam_seqi
+    return nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : 4;  // seq_nt16_int
+}
+
 // rinv[i], i = 1..l_query : 1/s[i].   fsave + r*fs_stride : scaled forward (M,I) of marker row r, [o*2+{0,1}].
 template <int STRIDE, int NW>
 SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<STRIDE> B, double *rinv, double *fsave,
@@ -167,16 +177,16 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
     double r = 1.;
     int beg_prev = 1, end_prev = n_prev;
     int t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
-    int qc_next = Lq >= 2 ? sp_query_code(in, 1) : 0;
+    uint32_t qraw_next = Lq >= 2 ? sp_query_raw(in, 1) : 0;
     int rc_next = 2 + bw <= Lr ? in.ref[1 + bw] : 0;  // the column entering at row 2, if any
     for (int i = 2; i <= Lq; i++) {
         const int beg = i - bw > 1 ? i - bw : 1;
         const int end = i + bw < Lr ? i + bw : Lr;
         const int n = end - beg + 1;
         const int sh = beg - beg_prev;
-        const int qc = qc_next;
+        const int qc = sp_query_decode(in, i - 1, qraw_next);
         const int rc_in = rc_next;
-        if (i < Lq) qc_next = sp_query_code(in, i);
+        if (i < Lq) qraw_next = sp_query_raw(in, i);
         if (i + 1 + bw <= Lr) rc_next = in.ref[i + bw];
         if (sh) { p0.shr1(); p1.shr1(); p2.shr1(); }
         if (end > end_prev) {  // one column enters the band on the right
@@ -331,7 +341,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
     p0.shr1(); p1.shr1(); p2.shr1();
     int beg_next = beg_prev, end_next = end_prev;  // band of row i+1
     t_next = rows[nr].t;
-    qc_next = Lq >= 2 ? sp_query_code(in, Lq - 1) : 0;
+    qraw_next = Lq >= 2 ? sp_query_raw(in, Lq - 1) : 0;
     {
         const int b = Lq - 1 - bw > 1 ? Lq - 1 - bw : 1;
         rc_next = (b != beg_prev && b < Lr) ? in.ref[b] : 0;
@@ -343,11 +353,11 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         const int end = i + bw < Lr ? i + bw : Lr;
         const int n = end - beg + 1;
         const int sh = beg_next - beg;
-        const int qc = qc_next;  // query[i] (0-based) == base of row i+1
+        const int qc = sp_query_decode(in, i, qraw_next);  // query[i] (0-based) == base of row i+1
         const int rc_in = rc_next;
         const double y = rinv_i;
         if (i > i_stop) {
-            qc_next = sp_query_code(in, i - 1);
+            qraw_next = sp_query_raw(in, i - 1);
             const int b = i - 1 - bw > 1 ? i - 1 - bw : 1;
             rc_next = (b != beg && b < Lr) ? in.ref[b] : 0;  // (the bit of column Lr+1 is never consumed)
             rinv_i = rinv[i - 1];
