@@ -151,7 +151,7 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     synth = make_synth(args)
     # bounded sample per step so that the whole run stays within a few minutes
-    per_step = args.cpu_sample or min(args.groups, 24 * threads)
+    per_step = args.cpu_sample or min(args.groups, 128 * threads)
     n_steps = args.warmup + args.steps
     batches = [synth.generate(i * per_step, per_step) for i in range(min(n_steps, 3))]
     times, groups, cells = [], 0, 0
@@ -339,7 +339,7 @@ def main():
     }
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         threads = os.cpu_count() or 1
-        n_cpu = args.cpu_sample or min(args.groups, 16 * threads)
+        n_cpu = args.cpu_sample or min(args.groups, 512 * threads)  # ~5-10 s on all host cores
         sample = batches[0].group_slice(0, n_cpu)
         g, c, dt, kind = cpu_reference_run(synth, [sample], "hifi", threads)
         line["cpu_baseline"] = {"value": g / dt, "unit": "read-groups/s", "cores": threads, "kind": kind,

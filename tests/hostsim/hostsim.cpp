@@ -135,6 +135,34 @@ int hs_hmm2(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *qu
     return 0;
 }
 
+// Diagnostic: refined-op / initial-marker counts of every alignment against the planned capacities.
+int hs_walk_stats(const sp_flat_batch *b, const sp_params *p, int32_t *out /* [A][5]: n_ops, cap, n_imk, cap, err */) {
+    SpConst C;
+    sp_fill_const(*p, C);
+    SpPlan pl;
+    int rc = sp_make_plan(b, p->indel_threshold, false, pl);
+    if (rc != SP_OK) return rc;
+    const int64_t tag_bytes = b->tag_off[pl.A];
+    std::vector<uint8_t> tagbuf((size_t) tag_bytes + 32, 0);
+    uint8_t *tag_pool = tagbuf.data();
+    while (((uintptr_t) tag_pool) & 15) tag_pool++;
+    memcpy(tag_pool, b->tag_pool, (size_t) tag_bytes);
+    for (int a = 0; a < pl.A; a++) {
+        const int ocap = (int) (pl.ops_off[a + 1] - pl.ops_off[a] - 1), mcap = (int) (pl.imk_off[a + 1] - pl.imk_off[a]);
+        std::vector<SpOp> ops((size_t) ocap + 1);
+        std::vector<SpInitMarker> imk((size_t) mcap + 1);
+        std::vector<SpBlock> cb((size_t) pl.cb_cap[a] + 1);
+        SpAlnInfo info;
+        sp_walk_alignment(C.indel_threshold, C.min_q, b->flag[a], b->pos[a], b->l_qseq[a], b->n_cigar[a],
+                          b->cigar_pool + b->cigar_off[a], tag_pool, b->tag_off[a], b->tag_off[a + 1],
+                          b->tag_kind ? b->tag_kind[a] : 0, b->qual_pool + b->qual_off[a], ops.data(), ocap, imk.data(),
+                          mcap, cb.data(), pl.cb_cap[a], &info);
+        out[a * 5 + 0] = info.n_ops; out[a * 5 + 1] = ocap; out[a * 5 + 2] = info.n_imk; out[a * 5 + 3] = mcap;
+        out[a * 5 + 4] = info.err;
+    }
+    return 0;
+}
+
 // Whole marker path for a batch; ref_codes: concatenated contigs (codes 0..4), contig_off[n+1].
 int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
            int n_contigs, int safe_caps, unsigned rng_seed, HsOut *out) {

@@ -620,7 +620,10 @@ static void emit_alignment(synth_batch *b, const synth *s, int tid, int is_secon
         int prev_del = 0;
         for (int64_t i = c0; i < c1; i++) {
             char t = cols->p[i].type;
-            if (t == 'I') continue;
+            if (t == 'I') {  /* an insertion splits a deletion run: samtools calmd writes "^A0^C" */
+                prev_del = 0;
+                continue;
+            }
             if (t == '=') {
                 run++;
                 prev_del = 0;
