@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsecphase_b200.so")
+LIB_PATH = os.environ.get("SECPHASE_B200_LIB") or os.path.join(_HERE, "lib", "libsecphase_b200.so")
 
 GROUP_W, MARKER_W, BLOCK_W, HMM_W = 10, 6, 6, 8
 N_SLOTS = 3

@@ -28,6 +28,17 @@ def deps():
     return d
 
 
+def build_variant(name, extra_flags):
+    """Tuning aid: libsecphase_b200 with extra nvcc flags (e.g. -DSP_H2_NCR=12) under lib/variants/;
+    select it at run time with SECPHASE_B200_LIB=<path>."""
+    vdir = os.path.join(LIBDIR, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, f"lib_{name}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + list(extra_flags) + ["-o", out] + sources())
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     newest = max(os.path.getmtime(p) for p in deps())

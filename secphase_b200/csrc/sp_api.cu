@@ -211,9 +211,12 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
         return nullptr;
     }
     if (cudaFuncSetAttribute(k_hmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
+        cudaFuncSetAttribute(k_hmm2<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<1, 41>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<1, 43>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<1, 45>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
         set_err("sp_create: cudaFuncSetAttribute(k_hmm) failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
         return nullptr;
@@ -479,18 +482,18 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
 // whose band falls back to global memory when it outgrows shared memory.  Every class is an
 // independent launch on its own auxiliary stream, widest (= fewest, slowest instances) first, so
 // that a handful of wide instances overlaps with the bulk instead of trailing it.
-template <int NW>
+template <int NW, int NC>
 static void launch_hmm2(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first, int cnt, const uint8_t *ref,
                         const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride) {
     const int nblk = (cnt + 31) / 32;
     const int ncell = sp_h2_cells(sp_class_bw(cls));
     const size_t slab = (size_t) ncell * 32 * 24;
     int wpc = (int) (c->max_smem / slab);  // warps per CTA = band slabs per SM
-    if (wpc > 8) wpc = 8;
+    if (wpc > 7) wpc = 7;  // k_hmm2 is compiled for at most 224 threads per CTA
     if (wpc > nblk) wpc = nblk;
     int grid = (nblk + wpc - 1) / wpc;
     if (grid > c->sm_count) grid = c->sm_count;
-    k_hmm2<NW><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(),
+    k_hmm2<NW, NC><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(),
                                                    first, cnt, ncell, ref, qbytes, seq_pool, seq_off,
                                                    S.s_pool.as<double>(), S.fsave.as<double>(), fs_stride,
                                                    S.rows.as<SpRow>(), S.work_counter.as<int>() + cls);
@@ -515,9 +518,17 @@ static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_
         const int bwc = sp_class_bw(cls);
         if (bwc != 0) {
             const int nw = sp_h2_words(bwc);
-            if (nw == 1) launch_hmm2<1>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride);
-            else if (nw == 2) launch_hmm2<2>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride);
-            else launch_hmm2<3>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride);
+#define SP_LAUNCH(NW, NC) launch_hmm2<NW, NC>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride)
+            switch (sp_class_unrolled_cells(cls)) {
+                case 41: SP_LAUNCH(1, 41); break;
+                case 43: SP_LAUNCH(1, 43); break;
+                case 45: SP_LAUNCH(1, 45); break;
+                default:
+                    if (nw == 1) SP_LAUNCH(1, 0);
+                    else if (nw == 2) SP_LAUNCH(2, 0);
+                    else SP_LAUNCH(3, 0);
+            }
+#undef SP_LAUNCH
         } else {
             const int nblk = (cnt + 31) / 32;
             int W = 2 * max_bw + 2;

@@ -29,6 +29,16 @@
 #include "sp_hmm.cuh"
 
 #define SP_H2_U 4
+// Unrolled row bodies: number of low band cells whose forward D / backward bI live in registers
+// (the remaining cells keep them in shared memory).  Bounded by the 255-register file: a single
+// spill is ruinous here because local memory competes for the ~28 KB of L1 left beside 227 KB of
+// shared memory.
+#ifndef SP_H2_NCRF
+#define SP_H2_NCRF 64  // forward: D of cells < NCRF in registers (clamped to NC)
+#endif
+#ifndef SP_H2_NCRB
+#define SP_H2_NCRB -1  // backward: bI of cells < NCRB in registers; -1 = no unrolled backward body at all
+#endif
 #define SP_H2_MAXBW 94  // 2*bw+1 <= 189 cells: the per-row emission masks are NW <= 3 64-bit words
 SP_HD int sp_h2_words(int bw) { return (2 * bw + 1 + 63) >> 6; }
 
@@ -86,6 +96,24 @@ SP_HD void sp_h2_row_masks(const SpBits<NW> &p0, const SpBits<NW> &p1, const SpB
     }
 }
 
+// Warp-uniform decisions of the unrolled fast path (every lane of a full warp is inside
+// sp_hmm2_instance together); the host simulation runs one lane at a time.
+#if defined(__CUDA_ARCH__)
+#define SP_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#define SP_WARP_ALL(p) __all_sync(0xffffffffu, (p))
+#define SP_WARP_MIN(x) __reduce_min_sync(0xffffffffu, (x))
+#define SP_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
+// scheduling fence inside the fully unrolled row bodies: stops ptxas hoisting shared-memory loads
+// of far-away cells (it otherwise runs out of the 255 registers and spills)
+#define SP_SCHED_FENCE() asm volatile("" ::: "memory")
+#else
+#define SP_WARP_ANY(p) (p)
+#define SP_WARP_ALL(p) (p)
+#define SP_WARP_MIN(x) (x)
+#define SP_WARP_MAX(x) (x)
+#define SP_SCHED_FENCE() ((void) 0)
+#endif
+
 #if defined(__CUDACC__)
 typedef double2 SpD2;
 #else
@@ -114,12 +142,34 @@ SP_HD int sp_query_decode(const SpHmmIn &in, int i0, uint32_t raw) {
 }
 
 // rinv[i], i = 1..l_query : 1/s[i].   fsave + r*fs_stride : scaled forward (M,I) of marker row r, [o*2+{0,1}].
-template <int STRIDE, int NW>
+//
+// NC > 0 selects the fully unrolled row bodies for bands of exactly NC = 2*bw+1 cells: for the rows
+// where every lane of the warp has a full, sliding band (bw+2 <= i <= Lr-bw) the D plane (forward)
+// lives in registers and every cell index is a compile-time constant, which removes a third of
+// the shared-memory traffic and all per-chunk address / mask arithmetic.  full_warp says that all
+// 32 lanes are inside this function (the fast path takes warp-uniform decisions by vote).
+template <int STRIDE, int NW, int NC, int NCRF_ = SP_H2_NCRF, int NCRB_ = SP_H2_NCRB>
 SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<STRIDE> B, double *rinv, double *fsave,
-                            int64_t fs_stride, SpRow *rows, int n_rows) {
+                            int64_t fs_stride, SpRow *rows, int n_rows, bool full_warp) {
     constexpr int U = SP_H2_U;
     const int Lr = in.l_ref, Lq = in.l_query;
     const int bw = sp_hmm_bw(Lr, Lq, in.par_bw);
+    // rows [fi0, fi1] run the unrolled forward body (empty range when NC == 0 or the warp is mixed)
+    int fi0 = 1, fi1 = 0;
+    bool unrolled_ok = false;
+    if constexpr (NC > 0) {
+        unrolled_ok = full_warp && SP_WARP_ALL(2 * bw + 1 == NC);
+        if (unrolled_ok) {
+            fi0 = bw + 2;
+            fi1 = SP_WARP_MIN(Lq < Lr - bw ? Lq : Lr - bw);
+        }
+    }
+    constexpr int NCR = NCRF_ < NC ? NCRF_ : NC;               // forward cells with D in registers
+    constexpr int NCB = NCRB_ < NC ? (NCRB_ < 0 ? 0 : NCRB_) : NC;  // backward cells with bI in registers
+    constexpr bool BWD_UNROLLED = NC > 0 && NCRB_ >= 0;
+    double Dr[(NCR > NCB ? NCR : NCB) > 0 ? (NCR > NCB ? NCR : NCB) : 1];  // see the unrolled bodies
+    bool d_regs = false;
+    (void) Dr; (void) d_regs; (void) fi0; (void) fi1; (void) unrolled_ok;
     // transition matrix; float-typed sub-expressions were folded on the host
     const double sM = SP_DDIV(1., (double) (2 * Lq + 2));
     const double sI = sM;
@@ -199,6 +249,49 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         // rows whose band holds an N (rare) take the one-cell-at-a-time code, which knows about nn
         const bool has_n = nn.any_below(n);
 
+        double sum = 0.;
+        bool fast = false;
+        if constexpr (NC > 0) {
+            fast = i >= fi0 && i <= fi1 && !SP_WARP_ANY(has_n);  // warp-uniform: fi0, fi1 are
+            if (fast != d_regs) {                                 // move D between its plane and registers
+#pragma unroll
+                for (int o = 0; o < NCR; o++) {
+                    if (fast) Dr[o] = B.d[o * STRIDE];
+                    else B.d[o * STRIDE] = Dr[o];
+                }
+                d_regs = fast;
+            }
+        }
+        if (NC > 0 && fast) {
+            if constexpr (NC > 0) {
+                // full sliding band: n == NC, sh == 1; M[i,o] reads old cell o, I[i,o] old cell o+1
+                SpD2 a = B.mi[0];
+                double pM = SP_DMUL(a.x, r), pI = SP_DMUL(a.y, r), pD = SP_DMUL(NCR > 0 ? Dr[0] : B.d[0], r);
+                double Mlast = 0., cD = 0.;
+#pragma unroll
+                for (int o = 0; o < NC; o++) {
+                    double qM = 0., qI = 0., qD = 0.;
+                    SpD2 v;
+                    if (o + 1 < NC) {
+                        a = B.mi[(o + 1 < NC ? o + 1 : 0) * STRIDE];
+                        qM = SP_DMUL(a.x, r); qI = SP_DMUL(a.y, r);
+                        qD = SP_DMUL(o + 1 < NCR ? Dr[o + 1 < NCR ? o + 1 : 0] : B.d[(o + 1) * STRIDE], r);
+                        v.y = SP_DADD(SP_DMUL(eim1, qM), SP_DMUL(eim4, qI));
+                    } else {
+                        v.y = 0.;  // the column that just entered: row i-1 holds zeros there
+                    }
+                    const double e = ((mm.w[o >> 6] >> (o & 63)) & 1) ? emA : emB;
+                    v.x = SP_DMUL(e, SP_DADD(SP_DADD(SP_DMUL(m0, pM), SP_DMUL(m3, pI)), SP_DMUL(m6, pD)));
+                    cD = SP_DADD(SP_DMUL(m2, Mlast), SP_DMUL(m8, cD));
+                    sum = SP_DADD(sum, SP_DADD(SP_DADD(v.x, v.y), cD));
+                    B.mi[o * STRIDE] = v;
+                    if (o < NCR) Dr[o < NCR ? o : 0] = cD;
+                    else B.d[o * STRIDE] = cD;
+                    Mlast = v.x;
+                    pM = qM; pI = qI; pD = qD;
+                }
+            }
+        } else {
         // old row (i-1): M[i,o] reads old cell o-1+sh, I[i,o] reads old cell o+sh
         const SpD2 *omi = B.mi + sh * STRIDE;
         const double *od = B.d + sh * STRIDE;
@@ -207,7 +300,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
             const SpD2 a = omi[-STRIDE];
             pM = SP_DMUL(a.x, r); pI = SP_DMUL(a.y, r); pD = SP_DMUL(od[-STRIDE], r);
         }
-        double Mlast = 0., cD = 0., sum = 0.;
+        double Mlast = 0., cD = 0.;
 
         // parallel part of U cells starting at o0: everything that does not depend on this row's D chain
         auto fwdP = [&](int o0, double (&t)[U], double (&u)[U]) {
@@ -276,6 +369,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
             Mlast = v.x;
             pM = qM; pI = qI; pD = qD;
         }
+        }  // generic row body
         const double ri = SP_DDIV(1., sum);
         rinv[i] = ri;
         s_last = sum;
@@ -300,11 +394,10 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         const SpD2 a = B.mi[o * STRIDE];
         sLq1 = SP_DADD(sLq1, SP_DADD(SP_DMUL(SP_DMUL(a.x, r), sM), SP_DMUL(SP_DMUL(a.y, r), sI)));
     }
-    if (n_rows == 0) return;
-
     // ------------------------------------------------------------------ backward (+ MAP at marker rows)
-    const int i_stop = rows[0].t + 1;  // nothing below the lowest marker row is consumed
-    {  // row Lq: constant inside the band, already in its final scale
+    // (no early return below: the lanes of a full warp vote together further down)
+    int i_stop = n_rows > 0 ? rows[0].t + 1 : Lq;  // nothing below the lowest marker row is consumed
+    if (n_rows > 0) {  // row Lq: constant inside the band, already in its final scale
         SpD2 v;
         v.x = SP_DDIV(SP_DDIV(sM, s_last), sLq1);
         v.y = SP_DDIV(SP_DDIV(sI, s_last), sLq1);
@@ -332,15 +425,15 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         rows[ri].q = sp_q_from_t(C, SP_DADD(1., -mx));
     };
     nr = n_rows - 1;
-    if (rows[nr].t + 1 == Lq) {  // stand-alone API only (pipeline rows satisfy t <= Lq-12)
+    if (nr >= 0 && rows[nr].t + 1 == Lq) {  // stand-alone API only (pipeline rows satisfy t <= Lq-12)
         map_row(nr, beg_prev, n_prev, 1., false);
         nr--;
-        if (nr < 0) return;
     }
+    if (nr < 0) i_stop = Lq;  // nothing (left) to do for this lane: no live step below
     // planes re-aligned for the backward sweep: bit o <-> ref[beg+o] (the base of column beg+o+1)
     p0.shr1(); p1.shr1(); p2.shr1();
     int beg_next = beg_prev, end_next = end_prev;  // band of row i+1
-    t_next = rows[nr].t;
+    t_next = nr >= 0 ? rows[nr].t : -2;
     qraw_next = Lq >= 2 ? sp_query_raw(in, Lq - 1) : 0;
     {
         const int b = Lq - 1 - bw > 1 ? Lq - 1 - bw : 1;
@@ -348,22 +441,40 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
     }
     double rinv_i = Lq >= 2 ? rinv[Lq - 1] : 1.;  // 1/s[i], fetched one row before it scales row i
     double r1 = 1.;                               // row Lq is stored in its final scale
-    for (int i = Lq - 1; i >= i_stop; i--) {
+    // The sweep is counted in steps j (row i = Lq-1-j) so that a full warp stays in lock step even
+    // though its lanes start and stop at different rows: a lane that has passed its lowest marker
+    // row ("dead") keeps executing the unrolled body on its own slab -- which costs nothing, the
+    // warp is busy anyway -- so that the warp-uniform choice of the unrolled body does not end when
+    // the first lane finishes.
+    int jmax = Lq - 1 - i_stop;
+    if constexpr (BWD_UNROLLED) {
+        if (unrolled_ok) jmax = SP_WARP_MAX(jmax);
+    }
+#define Ir Dr  // backward: the same registers hold bI of the last written row while in the unrolled body
+    bool i_regs = false;
+    (void) i_regs;
+    for (int j = 0; j <= jmax; j++) {
+        const int i = Lq - 1 - j;
+        const bool live = i >= i_stop;
         const int beg = i - bw > 1 ? i - bw : 1;
         const int end = i + bw < Lr ? i + bw : Lr;
         const int n = end - beg + 1;
         const int sh = beg_next - beg;
-        const int qc = sp_query_decode(in, i, qraw_next);  // query[i] (0-based) == base of row i+1
-        const int rc_in = rc_next;
-        const double y = rinv_i;
-        if (i > i_stop) {
-            qraw_next = sp_query_raw(in, i - 1);
-            const int b = i - 1 - bw > 1 ? i - 1 - bw : 1;
-            rc_next = (b != beg && b < Lr) ? in.ref[b] : 0;  // (the bit of column Lr+1 is never consumed)
-            rinv_i = rinv[i - 1];
+        int qc = 0, rc_in = 0;
+        double y = 0.;
+        if (live) {
+            qc = sp_query_decode(in, i, qraw_next);  // query[i] (0-based) == base of row i+1
+            rc_in = rc_next;
+            y = rinv_i;
+            if (i > i_stop) {
+                qraw_next = sp_query_raw(in, i - 1);
+                const int b = i - 1 - bw > 1 ? i - 1 - bw : 1;
+                rc_next = (b != beg && b < Lr) ? in.ref[b] : 0;  // (the bit of column Lr+1 is never consumed)
+                rinv_i = rinv[i - 1];
+            }
         }
         const double m6e = i > 1 ? m6 : 0., m8e = i > 1 ? m8 : 0.;
-        if (sh) {  // one column enters the band on the left
+        if (live && sh) {  // one column enters the band on the left
             p0.shl1_in((uint64_t) (rc_in & 1));
             p1.shl1_in((uint64_t) ((rc_in >> 1) & 1));
             p2.shl1_in((uint64_t) ((rc_in >> 2) & 1));
@@ -371,6 +482,78 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         SpBits<NW> mm, nn;
         sp_h2_row_masks(p0, p1, p2, qc, mm, nn);
         const bool has_n = nn.any_below(n);
+        bool fast = false;
+        if constexpr (BWD_UNROLLED) {
+            if (unrolled_ok) {
+                // full sliding band with an in-range top cell: i >= bw+1 and i+bw < Lr
+                fast = SP_WARP_ALL(!live || (i >= bw + 1 && i + bw < Lr && !has_n));
+                if (fast != i_regs) {  // unrolled body, cells < NCB: bM in the dense 8-byte plane, bI in registers
+#pragma unroll
+                    for (int o = 0; o < NCB; o++) {
+                        if (fast) {
+                            const SpD2 a = B.mi[o * STRIDE];
+                            B.d[o * STRIDE] = a.x;
+                            Ir[o] = a.y;
+                        } else {
+                            SpD2 a;
+                            a.x = B.d[o * STRIDE];
+                            a.y = Ir[o];
+                            B.mi[o * STRIDE] = a;
+                        }
+                    }
+                    i_regs = fast;
+                }
+            }
+        }
+        if (BWD_UNROLLED && fast) {
+            if constexpr (BWD_UNROLLED) {
+                // cell o needs bM of old cell o and bI of old cell o-1.  Cells >= NCB keep (bM,bI) as one
+                // double2: the word of cell o-1 is loaded at step o (its bI is needed now, its bM at the
+                // next step); cells < NCB read bM from the dense plane and bI from registers.
+                double cD = 0.;
+                double nMraw = NC - 1 >= NCB ? B.mi[(NC - 1) * STRIDE].x : 0.;  // bM of old cell o, cells >= NCB
+#pragma unroll
+                for (int o = NC - 1; o >= 0; o--) {
+                    double bm_old, bi_old = 0.;
+                    if (o >= NCB) {
+                        bm_old = nMraw;
+                        if (o - 1 >= NCB) {
+                            const SpD2 a = B.mi[(o > 0 ? o - 1 : 0) * STRIDE];
+                            bi_old = a.y;
+                            nMraw = a.x;
+                        } else if (o > 0) {
+                            bi_old = Ir[o - 1 >= 0 && o - 1 < NCB ? o - 1 : 0];
+                        }
+                    } else {
+                        bm_old = B.d[o * STRIDE];
+                        if (o > 0) bi_old = Ir[o > 0 && o - 1 < NCB ? o - 1 : 0];
+                    }
+                    const double nM = SP_DMUL(bm_old, r1);
+                    const double em = ((mm.w[o >> 6] >> (o & 63)) & 1) ? emA : emB;
+                    const double e = SP_DMUL(em, nM);
+                    double X, bIv;
+                    if (o > 0) {
+                        const double qI = SP_DMUL(bi_old, r1);
+                        X = SP_DADD(SP_DMUL(e, m0), SP_DMUL(eim1, qI));
+                        bIv = SP_DADD(SP_DMUL(e, m3), SP_DMUL(eim4, qI));
+                    } else {  // column beg is outside the band of row i+1: bI there is zero
+                        X = SP_DADD(SP_DMUL(e, m0), 0.);
+                        bIv = SP_DADD(SP_DMUL(e, m3), 0.);
+                    }
+                    const double bMv = SP_DADD(X, SP_DMUL(m2, cD));
+                    if (o >= NCB) {
+                        SpD2 v;
+                        v.x = bMv;
+                        v.y = bIv;
+                        B.mi[o * STRIDE] = v;
+                    } else {
+                        B.d[o * STRIDE] = bMv;
+                        Ir[o < NCB ? o : 0] = bIv;
+                    }
+                    cD = SP_DADD(SP_DMUL(e, m6e), SP_DMUL(m8e, cD));
+                }
+            }
+        } else if (live) {
         // old row (i+1): cell o needs bI of old cell o-sh and bM of old cell o+1-sh
         const SpD2 *omi = B.mi - sh * STRIDE;
         double nM = (end + 1 <= end_next) ? SP_DMUL(omi[n * STRIDE].x, r1) : 0.;  // scaled bM[i+1][end+1]
@@ -437,13 +620,28 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
                 bwdC((c + 1) * U, XA, IA, wA);
             }
         }
-        beg_next = beg;
-        end_next = end;
-        r1 = y;
-        if (t_next + 1 == i) {
-            map_row(nr, beg, n, y, true);
-            nr--;
-            t_next = nr >= 0 ? rows[nr].t : -2;
+        }  // generic row body
+        if (live) {
+            beg_next = beg;
+            end_next = end;
+            r1 = y;
+            if (t_next + 1 == i) {
+                if constexpr (BWD_UNROLLED) {
+                    if (i_regs) {  // map_row reads (bM,bI) from the double2 plane
+#pragma unroll
+                        for (int o = 0; o < NCB; o++) {
+                            SpD2 a;
+                            a.x = B.d[o * STRIDE];
+                            a.y = Ir[o];
+                            B.mi[o * STRIDE] = a;
+                        }
+                    }
+                }
+                map_row(nr, beg, n, y, true);
+                nr--;
+                t_next = nr >= 0 ? rows[nr].t : -2;
+            }
         }
     }
 }
+#undef Ir

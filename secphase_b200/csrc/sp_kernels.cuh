@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(32) k_hmm(const SpConst *__restrict__ Cp, cons
 // instances from a global counter in (band class, length)-sorted order, i.e. longest first, so the
 // SMs drain together.  Per-warp slab in dynamic shared memory: ncell x 32 double2 (M,I) followed
 // by ncell x 32 double (D), lane-interleaved; see sp_hmm2.cuh.
-template <int NW>
-__global__ void __launch_bounds__(256) k_hmm2(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
+template <int NW, int NC>
+__global__ void __launch_bounds__(224, 1) k_hmm2(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
                                               const int32_t *__restrict__ order, int first, int count, int ncell,
                                               const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qbytes,
                                               const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,
@@ -364,8 +364,8 @@ __global__ void __launch_bounds__(256) k_hmm2(const SpConst *__restrict__ Cp, co
             in.l_ref = it.l_ref;
             in.l_query = it.l_query;
             in.par_bw = it.par_bw;
-            sp_hmm2_instance<32, NW>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
-                                 rows + it.row0, it.n_rows);
+            sp_hmm2_instance<32, NW, NC>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride,
+                                         fs_stride, rows + it.row0, it.n_rows, w * 32 + 32 <= count);
         }
         __syncwarp();
     }

@@ -37,6 +37,25 @@ struct HsOut {
     int32_t err = 0;
 };
 
+// the instantiation launch_hmm() (sp_api.cu) picks for a band half-width; `unrolled` = what a full
+// warp of that class runs, otherwise what a partial last warp runs
+static void hs_hmm2_dispatch(const SpConst &C, const SpHmmIn &in, const SpBand2<1> &B, int bw, double *rinv,
+                             double *fsave, SpRow *rows, int n_rows, bool unrolled) {
+    const int64_t fss = 2 * (2 * bw + 1);
+    const int cls = sp_band_class(bw);
+    switch (sp_class_unrolled_cells(cls)) {
+        case 41: sp_hmm2_instance<1, 1, 41>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
+        case 43: sp_hmm2_instance<1, 1, 43>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
+        case 45: sp_hmm2_instance<1, 1, 45>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
+        default: break;
+    }
+    switch (sp_h2_words(sp_class_bw(cls))) {
+        case 1: sp_hmm2_instance<1, 1, 0>(C, in, B, rinv, fsave, fss, rows, n_rows, false); break;
+        case 2: sp_hmm2_instance<1, 2, 0>(C, in, B, rinv, fsave, fss, rows, n_rows, false); break;
+        default: sp_hmm2_instance<1, 3, 0>(C, in, B, rinv, fsave, fss, rows, n_rows, false); break;
+    }
+}
+
 extern "C" {
 
 HsOut *hs_out_create() { return new HsOut(); }
@@ -100,7 +119,7 @@ int hs_hmm(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *que
 
 // Same, through the shared-memory-band kernel body (sp_hmm2.cuh); bw must be <= SP_H2_MAXBW.
 int hs_hmm2(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *query, int l_query, int par_bw,
-            const int32_t *rows_t, int n_rows, int32_t *state, uint8_t *q, double *pmax) {
+            const int32_t *rows_t, int n_rows, int32_t *state, uint8_t *q, double *pmax, int unrolled) {
     SpConst C;
     sp_fill_const(*p, C);
     const int bw = sp_hmm_bw(l_ref, l_query, par_bw);
@@ -121,12 +140,7 @@ int hs_hmm2(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *qu
     in.l_ref = l_ref; in.l_query = l_query; in.par_bw = par_bw;
     SpBand2<1> B;
     B.mi = mi.data() + 1; B.d = d.data() + 1;
-    const int64_t fss = 2 * (2 * bw + 1);
-    switch (sp_h2_words(sp_class_bw(sp_band_class(bw)))) {  // same instantiation as launch_hmm() picks
-        case 1: sp_hmm2_instance<1, 1>(C, in, B, rinv.data(), fsave.data(), fss, rows.data(), n_rows); break;
-        case 2: sp_hmm2_instance<1, 2>(C, in, B, rinv.data(), fsave.data(), fss, rows.data(), n_rows); break;
-        default: sp_hmm2_instance<1, 3>(C, in, B, rinv.data(), fsave.data(), fss, rows.data(), n_rows); break;
-    }
+    hs_hmm2_dispatch(C, in, B, bw, rinv.data(), fsave.data(), rows.data(), n_rows, unrolled != 0);
     for (int i = 0; i < n_rows; i++) {
         state[i] = rows[i].state;
         q[i] = (uint8_t) rows[i].q;
@@ -323,12 +337,7 @@ int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes,
             for (auto &v : mi) v.x = v.y = 0.0;
             SpBand2<1> B2;
             B2.mi = mi.data() + 1; B2.d = dd.data() + 1;
-            const int64_t fss = 2 * (2 * bw + 1);
-            switch (sp_h2_words(sp_class_bw(sp_band_class(bw)))) {
-                case 1: sp_hmm2_instance<1, 1>(C, in, B2, s.data(), fsave.data(), fss, rows.data() + I.row0, I.n_rows); break;
-                case 2: sp_hmm2_instance<1, 2>(C, in, B2, s.data(), fsave.data(), fss, rows.data() + I.row0, I.n_rows); break;
-                default: sp_hmm2_instance<1, 3>(C, in, B2, s.data(), fsave.data(), fss, rows.data() + I.row0, I.n_rows); break;
-            }
+            hs_hmm2_dispatch(C, in, B2, bw, s.data(), fsave.data(), rows.data() + I.row0, I.n_rows, true);
         } else {
             SpBand<1> B;
             B.row = band.data(); B.code = code.data(); B.W = W;

@@ -61,7 +61,7 @@ def lib():
                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_hmm.restype = C.c_int
         L.hs_hmm2.argtypes = [C.POINTER(SpParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.hs_hmm2.restype = C.c_int
         L.hs_rng_create.argtypes = [C.c_uint]
         L.hs_rng_create.restype = C.c_void_p
@@ -113,8 +113,9 @@ def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1):
         L.hs_out_destroy(out)
 
 
-def hmm2(params, ref, query, par_bw, rows_t):
-    """The shared-memory-band kernel body (sp_hmm2.cuh) on the host; None if the band is too wide for it."""
+def hmm2(params, ref, query, par_bw, rows_t, unrolled=True):
+    """The shared-memory-band kernel body (sp_hmm2.cuh) on the host; None if the band is too wide for it.
+    unrolled: use the fully unrolled row bodies where the band class has them (a full warp's path)."""
     L = lib()
     ref = np.ascontiguousarray(ref, np.uint8)
     query = np.ascontiguousarray(query, np.uint8)
@@ -124,7 +125,7 @@ def hmm2(params, ref, query, par_bw, rows_t):
     q = np.zeros(n, np.uint8)
     pmax = np.zeros(n, np.float64)
     rc = L.hs_hmm2(C.byref(params), ref.ctypes.data, len(ref), query.ctypes.data, len(query), par_bw,
-                   rows_t.ctypes.data, n, state.ctypes.data, q.ctypes.data, pmax.ctypes.data)
+                   rows_t.ctypes.data, n, state.ctypes.data, q.ctypes.data, pmax.ctypes.data, 1 if unrolled else 0)
     if rc != 0:
         return None
     return dict(state=state, q=q, pmax=pmax)
