@@ -131,14 +131,27 @@ struct SpBand2 {
 
 SP_HD int sp_h2_cells(int bw) { return 2 * bw + 3; }  // cells -1 .. 2bw+1
 
+// One byte from global memory into a 32-bit register with nothing hanging off the load (the
+// compiler otherwise appends a zero-extension right behind it, which makes a load issued a whole
+// row ahead of its use stall at once).
+SP_HD uint32_t sp_ldg_u8(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+    uint32_t v;
+    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
 // Query base i0 in two steps, so that the load can be issued a whole row before the decode needs it.
 SP_HD uint32_t sp_query_raw(const SpHmmIn &in, int i0) {
-    return in.qbytes ? in.qbytes[in.q0 + i0] : in.qseq4[(in.q0 + i0) >> 1];
+    return sp_ldg_u8(in.qbytes ? in.qbytes + in.q0 + i0 : in.qseq4 + ((in.q0 + i0) >> 1));
 }
 SP_HD int sp_query_decode(const SpHmmIn &in, int i0, uint32_t raw) {
     if (in.qbytes) return (int) raw;
-    const int nib = (raw >> ((~(in.q0 + i0) & 1) << 2)) & 0xf;  // bam_seqi
-    return nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : 4;  // seq_nt16_int
+    const uint32_t nib = (raw >> ((~(in.q0 + i0) & 1) << 2)) & 0xf;  // bam_seqi
+    // seq_nt16_int = {4,0,1,4,2,4,4,4,3,4,4,4,4,4,4,4}, one hex digit per nibble value
+    return (int) ((0x4444444344424104ull >> (nib << 2)) & 0xf);
 }
 
 // rinv[i], i = 1..l_query : 1/s[i].   fsave + r*fs_stride : scaled forward (M,I) of marker row r, [o*2+{0,1}].
@@ -228,16 +241,16 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
     int beg_prev = 1, end_prev = n_prev;
     int t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
     uint32_t qraw_next = Lq >= 2 ? sp_query_raw(in, 1) : 0;
-    int rc_next = 2 + bw <= Lr ? in.ref[1 + bw] : 0;  // the column entering at row 2, if any
+    uint32_t rc_next = 2 + bw <= Lr ? sp_ldg_u8(in.ref + 1 + bw) : 0;  // the column entering at row 2, if any
     for (int i = 2; i <= Lq; i++) {
         const int beg = i - bw > 1 ? i - bw : 1;
         const int end = i + bw < Lr ? i + bw : Lr;
         const int n = end - beg + 1;
         const int sh = beg - beg_prev;
         const int qc = sp_query_decode(in, i - 1, qraw_next);
-        const int rc_in = rc_next;
+        const uint32_t rc_in = rc_next;
         if (i < Lq) qraw_next = sp_query_raw(in, i);
-        if (i + 1 + bw <= Lr) rc_next = in.ref[i + bw];
+        if (i + 1 + bw <= Lr) rc_next = sp_ldg_u8(in.ref + i + bw);
         if (sh) { p0.shr1(); p1.shr1(); p2.shr1(); }
         if (end > end_prev) {  // one column enters the band on the right
             p0.or_bit(n - 1, (uint64_t) (rc_in & 1));
@@ -437,7 +450,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
     qraw_next = Lq >= 2 ? sp_query_raw(in, Lq - 1) : 0;
     {
         const int b = Lq - 1 - bw > 1 ? Lq - 1 - bw : 1;
-        rc_next = (b != beg_prev && b < Lr) ? in.ref[b] : 0;
+        rc_next = (b != beg_prev && b < Lr) ? sp_ldg_u8(in.ref + b) : 0;
     }
     double rinv_i = Lq >= 2 ? rinv[Lq - 1] : 1.;  // 1/s[i], fetched one row before it scales row i
     double r1 = 1.;                               // row Lq is stored in its final scale
@@ -460,7 +473,8 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         const int end = i + bw < Lr ? i + bw : Lr;
         const int n = end - beg + 1;
         const int sh = beg_next - beg;
-        int qc = 0, rc_in = 0;
+        int qc = 0;
+        uint32_t rc_in = 0;
         double y = 0.;
         if (live) {
             qc = sp_query_decode(in, i, qraw_next);  // query[i] (0-based) == base of row i+1
@@ -469,7 +483,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
             if (i > i_stop) {
                 qraw_next = sp_query_raw(in, i - 1);
                 const int b = i - 1 - bw > 1 ? i - 1 - bw : 1;
-                rc_next = (b != beg && b < Lr) ? in.ref[b] : 0;  // (the bit of column Lr+1 is never consumed)
+                rc_next = (b != beg && b < Lr) ? sp_ldg_u8(in.ref + b) : 0;  // (the bit of column Lr+1 is never consumed)
                 rinv_i = rinv[i - 1];
             }
         }
