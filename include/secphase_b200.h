@@ -117,6 +117,11 @@ int sp_submit(sp_ctx *ctx, const sp_flat_batch *batch, int slot);
 /* Blocks until the slot's batch is complete, replays the tie-break RNG for its groups and fills
  * *out; the pointers stay valid until the next sp_submit on the same slot. */
 int sp_wait(sp_ctx *ctx, int slot, sp_result *out);
+/* Non-blocking: 1 if the slot's batch has finished on the device (sp_wait will not block on
+ * the GPU), 0 if it is still running, negative on error.  Lets one host thread keep feeding a
+ * device while it retires finished batches (the reference's tpool_wait has no such need: its
+ * workers write their own output, secphase.c:194-216). */
+int sp_poll(sp_ctx *ctx, int slot);
 
 /* --- device-resident variant used to time the kernels alone (bench `value`): the batch is
  * uploaded once with sp_upload, sp_run_resident enqueues kernels only. */

@@ -50,6 +50,11 @@ const char *sph_bam_target_name(const sph_bam *r, int32_t tid); /* sam_hdr_tid2n
 int64_t sph_bam_target_len(const sph_bam *r, int32_t tid);
 const char *sph_bam_header_text(const sph_bam *r, int64_t *len);
 
+/* Sequence length available per BAM tid (0 = contig absent from the FASTA).  Groups with an
+ * alignment that leaves [0, len) -- where the reference's fai_fetch would fail its assert
+ * (ptMarker.c:741-742) -- are skipped and counted by sph_bam_skipped_groups. */
+int sph_bam_set_contig_limits(sph_bam *r, const int64_t *len_by_tid);
+
 /* A reusable host batch whose four pools (cigar/tag/seq/qual) live in memory obtained from
  * `alloc` -- pass sp_host_alloc / sp_host_free (include/secphase_b200.h) to get page-locked
  * pools that sp_submit copies to the device without staging; NULL,NULL = malloc/free. */
@@ -72,6 +77,15 @@ void sph_bam_counts(const sph_bam *r, int64_t *parsed_alignments, int64_t *parse
  * @SQ header built from the names/lengths.  Every alignment carries its cs:Z or MD:Z tag. */
 int sph_bam_write(const char *path, int32_t n_targets, const char *const *names, const int64_t *lens,
                   const sp_flat_batch *b, int level, int threads);
+/* the same, incrementally (files larger than one batch) */
+typedef struct sph_bamw sph_bamw;
+sph_bamw *sph_bamw_open(const char *path, int32_t n_targets, const char *const *names, const int64_t *lens,
+                        int level, int threads);
+int sph_bamw_add(sph_bamw *w, const sp_flat_batch *b);
+int sph_bamw_close(sph_bamw *w); /* also frees w */
+/* groups skipped because the marker path is undefined for them in the reference (CIGAR N/P ops,
+ * SEQ/QUAL absent or inconsistent with the CIGAR) */
+int64_t sph_bam_skipped_groups(const sph_bam *r);
 
 /* ------------------------------------------------------------------ FASTA */
 typedef struct sph_fasta sph_fasta;

@@ -76,6 +76,12 @@ def _load(kind):
         f = getattr(L, "oracle_out_" + name)
         f.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         f.restype = C.POINTER(rt)
+    if kind == "reference":
+        L.oracle_out_enable_outputs.argtypes = [C.c_void_p]
+        L.oracle_out_save.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.oracle_out_save.restype = C.c_int
+        L.oracle_merge_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
+        L.oracle_merge_blocks.restype = C.c_int64
     L.oracle_out_markers.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
     L.oracle_out_markers.restype = C.POINTER(C.c_int32)
     L.oracle_out_marker_off.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
@@ -118,8 +124,22 @@ def preset_params(preset="hifi", **over):
     return OracleParams(**p)
 
 
-def run(batch, params, refseq, kind=None, keep_hmm=False, seed=1):
-    """Run every read group of `batch` (tools.flatbatch.FlatBatch) through the CPU checker."""
+def merge_blocks(rows, mode):
+    """The reference's own ptBlock_merge_blocks (mode 0) / ptBlock_merge_blocks_v2 (mode 1) on rows of
+    (start, end, count); count < 0 = no count data.  Needs kind="reference" (oracle/_ref)."""
+    L = _load("reference")
+    rows = np.ascontiguousarray(rows, np.int32).reshape(-1, 3)
+    cap = 4 * len(rows) + 8
+    out = np.zeros((cap, 3), np.int32)
+    k = L.oracle_merge_blocks(rows.ctypes.data, len(rows), mode, out.ctypes.data, cap)
+    assert k <= cap
+    return out[:k]
+
+
+def run(batch, params, refseq, kind=None, keep_hmm=False, seed=1, outputs=None):
+    """Run every read group of `batch` (tools.flatbatch.FlatBatch; or a list of them, processed in
+    order with one rand() stream) through the CPU checker.  outputs=(dir, prefix) additionally
+    writes out.log and the two marker BED files the way secphase.c does (reference kind only)."""
     if kind is None:
         kind = available_kinds()[0]
     L = _load(kind)
@@ -127,12 +147,25 @@ def run(batch, params, refseq, kind=None, keep_hmm=False, seed=1):
     try:
         if seed is not None:
             L.oracle_srand(seed)
-        cb = batch.as_c()
-        rc = L.oracle_run(C.byref(cb), C.byref(params), C.byref(refseq), out)
-        if rc != 0:
-            raise RuntimeError(f"oracle_run failed: {rc}")
+        if outputs is not None:
+            if kind != "reference":
+                raise ValueError("text outputs need the reference kind")
+            L.oracle_out_enable_outputs(out)
+        for b1 in (batch if isinstance(batch, (list, tuple)) else [batch]):
+            cb = b1.as_c()
+            rc = L.oracle_run(C.byref(cb), C.byref(params), C.byref(refseq), out)
+            if rc != 0:
+                raise RuntimeError(f"oracle_run failed: {rc}")
         n = C.c_int64()
         res = {"kind": kind}
+        if outputs is not None:
+            tot = (C.c_int32 * 4)()
+            nm = C.c_int32()
+            rc = L.oracle_out_save(out, os.fsencode(outputs[0]), outputs[1].encode(), tot, C.byref(nm))
+            if rc != 0:
+                raise RuntimeError(f"oracle_out_save failed: {rc}")
+            res["totals"] = list(tot)
+            res["reads_modified_by_marker"] = nm.value
         res["groups"] = _take(L.oracle_out_groups(out, C.byref(n)), n.value, GROUP_W, np.int32)
         res["scores"] = _take(L.oracle_out_scores(out, C.byref(n)), n.value, 1, np.float64)
         res["extents"] = _take(L.oracle_out_extents(out, C.byref(n)), n.value, 4, np.int32)

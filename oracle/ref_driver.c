@@ -9,6 +9,7 @@
  * Quirk handling ("Quirks"): Q1 conf_blocks_length is read uninitialised
  * by the reference when the x0.8 loop never runs (secphase.c:107,170); it is defined here as 1.
  */
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -37,6 +38,13 @@ static void *vec_push(vec *v, int64_t cnt) {
 
 struct oracle_out {
     int keep_hmm;
+    /* optional text-output sink (oracle_out_enable_outputs): what secphase.c:194-216 does when the
+     * selected alignment is a secondary, using the reference's own block functions */
+    int sink;
+    vec log;                 /* bytes of <prefix>.out.log */
+    stHash *mod_blocks;      /* modified_blocks_by_marker_per_contig */
+    stHash *marker_blocks;   /* marker_blocks_all_haps_per_contig */
+    int reads_modified_by_marker;
     vec groups, scores, extents, markers[3], marker_off[3], blocks, block_off, hmm, hmm_state, hmm_q;
     int32_t cur_aln_global; /* for the HMM trace */
 };
@@ -59,8 +67,89 @@ oracle_out *oracle_out_create(int keep_hmm_arrays) {
     return o;
 }
 
+void oracle_out_enable_outputs(oracle_out *o) {
+    if (o->sink) return;
+    o->sink = 1;
+    vec_init(&o->log, 1);
+    o->mod_blocks = stHash_construct3(stHash_stringKey, stHash_stringEqualKey, NULL, (void (*)(void *)) stList_destruct);
+    o->marker_blocks = stHash_construct3(stHash_stringKey, stHash_stringEqualKey, NULL, (void (*)(void *)) stList_destruct);
+}
+
+static void log_printf(oracle_out *o, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    int n = vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    memcpy(vec_push(&o->log, n), buf, (size_t) n);
+}
+
+/* merge_and_save_blocks, secphase.c:59-72, with the reference's own ptBlock functions */
+static int save_blocks(stHash *blocks, const char *bed_path, int print_count, int *total_len, int *total_n) {
+    ptBlock_sort_stHash_by_rfs(blocks);
+    stHash *merged = ptBlock_merge_blocks_per_contig_by_rf_v2(blocks);
+    *total_len = ptBlock_get_total_length_by_rf(merged);
+    *total_n = ptBlock_get_total_number(merged);
+    ptBlock_save_in_bed(merged, (char *) bed_path, print_count != 0);
+    stHash_destruct(merged);
+    return 0;
+}
+
+/* Writes <dir>/<prefix>.out.log, .modified_read_blocks.markers.bed and .marker_blocks.bed the way
+ * secphase.c:681-732 does; totals[4] = length/number of the two merged tables. */
+int oracle_out_save(oracle_out *o, const char *dir, const char *prefix, int32_t *totals, int32_t *n_modified) {
+    if (!o->sink) return -1;
+    char path[2048];
+    snprintf(path, sizeof(path), "%s/%s.out.log", dir, prefix);
+    FILE *fp = fopen(path, "w");
+    if (!fp) return -2;
+    if (o->log.n) fwrite(o->log.p, 1, (size_t) o->log.n, fp);
+    fclose(fp);
+    int tl, tn;
+    snprintf(path, sizeof(path), "%s/%s.modified_read_blocks.markers.bed", dir, prefix);
+    save_blocks(o->mod_blocks, path, 1, &tl, &tn);
+    if (totals) { totals[0] = tl; totals[1] = tn; }
+    snprintf(path, sizeof(path), "%s/%s.marker_blocks.bed", dir, prefix);
+    save_blocks(o->marker_blocks, path, 0, &tl, &tn);
+    if (totals) { totals[2] = tl; totals[3] = tn; }
+    if (n_modified) *n_modified = o->reads_modified_by_marker;
+    return 0;
+}
+
+/* The reference's block merges on caller-supplied intervals (rows of start, end, count):
+ * mode 0 = ptBlock_merge_blocks (union), 1 = ptBlock_merge_blocks_v2; count < 0 = no count data.
+ * Returns the number of merged rows (written to out3 up to max_rows). */
+int64_t oracle_merge_blocks(const int32_t *rows3, int64_t n, int mode, int32_t *out3, int64_t max_rows) {
+    stHash *h = stHash_construct3(stHash_stringKey, stHash_stringEqualKey, NULL, (void (*)(void *)) stList_destruct);
+    stList *l = stList_construct3(0, ptBlock_destruct);
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t *r = rows3 + 3 * i;
+        stList_append(l, r[2] < 0 ? ptBlock_construct(r[0], r[1], -1, -1, -1, -1)
+                                  : ptBlock_construct_with_count(r[0], r[1], -1, -1, -1, -1, r[2]));
+    }
+    stHash_insert(h, copyString("ctg"), l);
+    ptBlock_sort_stHash_by_rfs(h);
+    stHash *m = mode == 0 ? ptBlock_merge_blocks_per_contig_by_rf(h) : ptBlock_merge_blocks_per_contig_by_rf_v2(h);
+    stList *ml = (stList *) stHash_search(m, "ctg");
+    int64_t k = stList_length(ml);
+    for (int64_t i = 0; i < k && i < max_rows; i++) {
+        ptBlock *b = (ptBlock *) stList_get(ml, i);
+        out3[3 * i] = b->rfs;
+        out3[3 * i + 1] = b->rfe;
+        out3[3 * i + 2] = b->data ? ptBlock_get_count(b) : -1;
+    }
+    stHash_destruct(m);
+    stHash_destruct(h);
+    return k;
+}
+
 void oracle_out_destroy(oracle_out *o) {
     if (!o) return;
+    if (o->sink) {
+        free(o->log.p);
+        stHash_destruct(o->mod_blocks);
+        stHash_destruct(o->marker_blocks);
+    }
     free(o->groups.p); free(o->scores.p); free(o->extents.p);
     for (int s = 0; s < 3; s++) { free(o->markers[s].p); free(o->marker_off[s].p); }
     free(o->blocks.p); free(o->block_off.p); free(o->hmm.p); free(o->hmm_state.p); free(o->hmm_q.p);
@@ -267,6 +356,25 @@ int oracle_run(const sp_flat_batch *b, const oracle_params *p, const oracle_refs
                          : -1;
         grow[0] = best;
         grow[1] = n > 0 ? get_primary_index(alns, n) : -1;
+        if (out->sink && best >= 0 && (alns[best]->record->core.flag & BAM_FSECONDARY)) {
+            /* secphase.c:194-216; print_alignment_scores (secphase.c:32-57), SCORE_TYPE_MARKER */
+            log_printf(out, "#MARKER SCORE\n");
+            log_printf(out, "$\t%s\n", bam_get_qname(alns[0]->record));
+            for (int i = 0; i < n; i++) {
+                if ((alns[i]->record->core.flag & BAM_FSECONDARY) == 0) log_printf(out, "*\t");
+                else if (i == best) log_printf(out, "@\t");
+                else log_printf(out, "!\t");
+                log_printf(out, "%.2f\t%s\t%ld\t%d\n", alns[i]->score, alns[i]->contig,
+                           (long) alns[i]->record->core.pos, alns[i]->rfe);
+            }
+            log_printf(out, "\n");
+            int primary_idx = get_primary_index(alns, n);
+            ptBlock_add_alignment(out->mod_blocks, alns[primary_idx], true);
+            ptBlock_add_alignment(out->mod_blocks, alns[best], true);
+            ptMarker_add_marker_blocks_by_contig(out->marker_blocks, alns[primary_idx]->contig, primary_idx, markers);
+            ptMarker_add_marker_blocks_by_contig(out->marker_blocks, alns[best]->contig, best, markers);
+            out->reads_modified_by_marker += 1;
+        }
         for (int i = 0; i < n; i++) {
             *(double *) vec_push(&out->scores, 1) = alns[i]->score;
             int32_t *e = (int32_t *) vec_push(&out->extents, 4);

@@ -43,6 +43,16 @@ void oracle_out_destroy(oracle_out *o);
 int oracle_run(const sp_flat_batch *b, const oracle_params *p, const oracle_refseq *ref, oracle_out *out);
 void oracle_srand(unsigned seed);
 
+/* Text outputs (reference kind only): after oracle_out_enable_outputs, oracle_run also does what
+ * secphase.c:194-216 does for every group whose selected alignment is a secondary, with the
+ * reference's own ptBlock/ptMarker block functions; oracle_out_save then writes <prefix>.out.log,
+ * .modified_read_blocks.markers.bed and .marker_blocks.bed as secphase.c:681-732 does. */
+void oracle_out_enable_outputs(oracle_out *o);
+int oracle_out_save(oracle_out *o, const char *dir, const char *prefix, int32_t *totals4, int32_t *n_modified);
+/* the reference's ptBlock_merge_blocks (mode 0) / ptBlock_merge_blocks_v2 (mode 1) on rows of
+ * (start, end, count); count < 0 = block without count data */
+int64_t oracle_merge_blocks(const int32_t *rows3, int64_t n, int mode, int32_t *out3, int64_t max_rows);
+
 /* flat result tables; *n receives the number of ROWS */
 const int32_t *oracle_out_groups(const oracle_out *o, int64_t *n);                 /* [n][ORACLE_GROUP_W] */
 const double *oracle_out_scores(const oracle_out *o, int64_t *n);                  /* [n_alns] */

@@ -106,7 +106,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = [
     "sp_params_default", "sp_params_preset", "sp_create", "sp_destroy", "sp_last_error", "sp_version",
-    "sp_set_reference_ascii", "sp_set_reference_codes", "sp_submit", "sp_wait", "sp_upload", "sp_run_resident",
+    "sp_set_reference_ascii", "sp_set_reference_codes", "sp_submit", "sp_wait", "sp_poll", "sp_upload", "sp_run_resident",
     "sp_debug_table", "sp_hmm_batch", "sp_fp64_peak", "sp_rng_seed", "sp_rng_next", "sp_host_alloc", "sp_host_free",
 ]
 

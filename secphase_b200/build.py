@@ -57,5 +57,36 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(LIBDIR, "libsecphase_host.so")
+BINDIR = os.path.join(os.path.dirname(HERE), "bin")
+CLI = os.path.join(BINDIR, "secphase")
+HOST_SRCS = ["sph_common.cpp", "sph_bgzf.cpp", "sph_bam.cpp", "sph_fasta.cpp", "sph_output.cpp"]
+CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-pthread"]
+
+
+def _stale(target, srcs):
+    return not os.path.exists(target) or os.path.getmtime(target) < max(os.path.getmtime(p) for p in srcs)
+
+
+def build_host(force=False):
+    """libsecphase_host.so (BGZF/BAM/FASTA ingest, BED/out.log writers; g++ only, no CUDA) and the
+    `secphase` executable that links it together with libsecphase_b200.so."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(BINDIR, exist_ok=True)
+    cxx = os.environ.get("CXX", "g++")
+    inc = [os.path.join(os.path.dirname(HERE), "include", f) for f in ("secphase_host.h", "secphase_b200.h", "sp_flat_batch.h")]
+    hdrs = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + inc
+    srcs = [os.path.join(HOST, f) for f in HOST_SRCS]
+    if force or _stale(HOST_LIB, srcs + hdrs):
+        subprocess.check_call([cxx] + CXX_FLAGS + ["-shared", "-o", HOST_LIB] + srcs + ["-lz"])
+    main = os.path.join(HOST, "secphase_main.cpp")
+    if force or _stale(CLI, [main, HOST_LIB, LIB] + inc):
+        subprocess.check_call([cxx] + CXX_FLAGS + ["-o", CLI, main, "-L" + LIBDIR, "-lsecphase_host", "-lsecphase_b200",
+                                                  "-Wl,-rpath,$ORIGIN/../secphase_b200/lib"])
+    return HOST_LIB, CLI
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

@@ -264,7 +264,7 @@ void sp_destroy(sp_ctx *c) {
 
 void *sp_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
         set_err("sp_host_alloc(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
@@ -694,6 +694,24 @@ int sp_run_resident(sp_ctx *c, int slot) {
     if (rc) return rc;
     S.state = 2;
     return SP_OK;
+}
+
+int sp_poll(sp_ctx *c, int slot) {
+    if (!c || slot < 0 || slot >= SP_N_SLOTS) return SP_EINVAL;
+    Slot &S = c->slot[slot];
+    if (S.state != 2) {
+        set_err("slot %d has nothing in flight", slot);
+        return SP_ESTATE;
+    }
+    CK(cudaSetDevice(c->device));
+    cudaError_t e = cudaStreamQuery(S.stream);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) {
+        cudaGetLastError();
+        return 0;
+    }
+    set_err("cudaStreamQuery: %s", cudaGetErrorString(e));
+    return SP_ECUDA;
 }
 
 int sp_wait(sp_ctx *c, int slot, sp_result *out) {

@@ -59,8 +59,23 @@ private:
     std::string err_text_;
 };
 
-// Splits `data` into BGZF blocks of <= 0xff00 payload bytes, deflates them in parallel and
-// writes them (plus the 28-byte EOF marker) to `path`.
-int bgzf_write_file(const char *path, const uint8_t *data, size_t len, int level, WorkerPool *pool);
+// Buffers written bytes and emits them as BGZF blocks of <= 0xff00 payload bytes, deflated in
+// parallel on the pool; close() appends the 28-byte end-of-file marker.
+class BgzfWriter {
+public:
+    ~BgzfWriter();
+    int open(const char *path, int level, WorkerPool *pool);
+    int write(const void *data, size_t len);
+    int close();
+
+private:
+    static constexpr size_t FLUSH_BYTES = 64u << 20;
+    int flush(bool all);
+    FILE *fp_ = nullptr;
+    std::string path_;
+    int level_ = 1;
+    WorkerPool *pool_ = nullptr;
+    std::vector<uint8_t> pend_;
+};
 
 }  // namespace sph

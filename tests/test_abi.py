@@ -31,6 +31,22 @@ def test_library_exports_every_declared_symbol():
     assert set(secphase_b200.api.EXPORTED_SYMBOLS) == set(declared_functions())
 
 
+def test_host_library_exports_every_declared_symbol():
+    """include/secphase_host.h <-> libsecphase_host.so (BAM/FASTA ingest, BED/out.log writers)."""
+    from secphase_b200 import hostlib
+    from secphase_b200.build import build_host
+    build_host()
+    text = open(os.path.join(ROOT, "include", "secphase_host.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(sph_[a-z0-9_]+)\s*\(", text)))
+    assert {"sph_bam_open", "sph_bam_next_batch", "sph_fasta_load", "sph_blocks_merge_v2",
+            "sph_format_marker_record"} <= set(names)
+    lib = ctypes.CDLL(hostlib.LIB_PATH)
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/secphase_host.h but not exported"
+    assert os.access(hostlib.CLI_PATH, os.X_OK)
+
+
 def test_no_cpu_fallback_without_device():
     """On a GPU-less box creating a context must fail loudly (and on a GPU box this is skipped)."""
     import secphase_b200
