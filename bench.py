@@ -40,7 +40,7 @@ FLOP_PER_CELL = 41  # 19 forward + 18 backward + 4 MAP
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups", type=int, default=8192, help="read groups per step and per GPU")
@@ -75,7 +75,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -237,16 +237,22 @@ def main():
             stats.append(eng.wait(inflight.pop(0), copy=False))
         return stats
 
+    def device_span_ms(n):
+        """CUDA-event time from the mark to the end of the last batch on any slot used by n steps."""
+        return max(eng.elapsed_since_mark(s) for s in range(min(n, n_slots)))
+
     resident_steps(args.warmup)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
+    eng.mark()
     t0 = time.perf_counter()
     stats = resident_steps(args.steps)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    dev_s = device_span_ms(args.steps) * 1e-3
+    dev_wall_s = t1 - t0
     barrier()
-    dev_s = t1 - t0
 
     # ---- end-to-end arm (host buffers, H2D + D2H inside the timed region) ------------------
     def e2e_steps(n):
@@ -262,15 +268,19 @@ def main():
             out.append(eng.wait(inflight.pop(0), copy=True))
         return out
 
-    e2e_steps(min(args.warmup, 3))
+    e2e_steps(max(args.warmup, 3))
     barrier()
+    # the end-to-end arm is a host-visible quantity (pack + H2D + kernels + D2H + result tables in
+    # host memory), so it is timed on the host clock around the synchronised region; the device-side
+    # span of the same steps is reported next to it
+    eng.mark()
     t2 = time.perf_counter()
     estats = e2e_steps(args.steps)
     torch.cuda.synchronize()
     t3 = time.perf_counter()
+    e2e_dev_s = device_span_ms(args.steps) * 1e-3
     barrier()
     e2e_s = t3 - t2
-    clocks = sampler.stop()
 
     # ---- the dominant kernel alone: one batch in flight, nothing overlapped, so that the CUDA
     # events around the HMM launches (fork -> class kernels on aux streams -> join, recorded on the
@@ -281,14 +291,15 @@ def main():
         r = eng.wait(0, copy=False)
         if i >= 2:
             iso.append(r)
+    clocks = sampler.stop()
     # ---- roofline denominators, measured live ------------------------------------------------
     dfma_ops, _ = eng.fp64_peak(0)
     dadd_ops, _ = eng.fp64_peak(1)
 
     if world > 1:
-        t = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_s, e2e_s, dev_wall_s, e2e_dev_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, e2e_s = float(t[0]), float(t[1])
+        dev_s, e2e_s, dev_wall_s, e2e_dev_s = (float(x) for x in t)
 
     groups_total = args.groups * args.steps * world
     cells_step = float(np.mean([s["hmm_cells"] for s in stats]))
@@ -321,7 +332,11 @@ def main():
         "e2e": {"value": groups_total / e2e_s, "unit": "read-groups/s",
                 "h2d_bytes_per_step": int(np.mean([s["h2d_bytes"] for s in estats])),
                 "d2h_bytes_per_step": int(np.mean([s["d2h_bytes"] for s in estats])),
-                "ms_per_step": 1e3 * e2e_s / args.steps},
+                "ms_per_step": 1e3 * e2e_s / args.steps, "device_ms_per_step": 1e3 * e2e_dev_s / args.steps,
+                "timing": "host clock around the synchronised region (host packing and result tables are part of "
+                          "the call); device_ms_per_step = CUDA-event span of the same steps"},
+        "timing": "CUDA events: mark on an idle device -> end of the last batch on each slot stream, max over slots "
+                  "and ranks (host wall clock of the same region: %.3f ms/step)" % (1e3 * dev_wall_s / args.steps),
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "k_hmm2 (all band-class launches of one step, forked on aux streams)", "bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops,
@@ -339,11 +354,19 @@ def main():
     }
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         threads = os.cpu_count() or 1
-        n_cpu = args.cpu_sample or min(args.groups, 512 * threads)  # ~5-10 s on all host cores
-        sample = batches[0].group_slice(0, n_cpu)
-        g, c, dt, kind = cpu_reference_run(synth, [sample], "hifi", threads)
+        # bounded sample: whole batches of the same workload until ~12 s of CPU work are done
+        n_cpu = args.cpu_sample or min(args.groups, 1024 * threads)
+        g = c = 0
+        dt = 0.0
+        kind = "port"
+        i = 0
+        while dt < 12.0 and i < 8:
+            sample = batches[i % len(batches)].group_slice(0, n_cpu)
+            g1, c1, dt1, kind = cpu_reference_run(synth, [sample], "hifi", threads)
+            g, c, dt, i = g + g1, c + c1, dt + dt1, i + 1
         line["cpu_baseline"] = {"value": g / dt, "unit": "read-groups/s", "cores": threads, "kind": kind,
-                                "sample": f"first {n_cpu} read groups of step 0, thread pool over read groups",
+                                "sample": f"{i} x the first {n_cpu} read groups of a step ({g} groups, {dt:.1f} s), "
+                                          "thread pool over read groups",
                                 "gcups": c / dt / 1e9, "seconds": dt}
     if rank == 0:
         print(json.dumps(line))

@@ -123,6 +123,13 @@ int sp_wait(sp_ctx *ctx, int slot, sp_result *out);
  * workers write their own output, secphase.c:194-216). */
 int sp_poll(sp_ctx *ctx, int slot);
 
+/* Device-side stopwatch over several batches (bench.py): sp_mark records a CUDA event on slot 0's
+ * stream (call it when the device is idle); sp_elapsed_since_mark gives the CUDA-event time from
+ * that mark to the end of the last batch completed (sp_wait) on `slot`.  The span of a pipelined
+ * run is the maximum over the slots used. */
+int sp_mark(sp_ctx *ctx);
+int sp_elapsed_since_mark(sp_ctx *ctx, int slot, float *ms);
+
 /* --- device-resident variant used to time the kernels alone (bench `value`): the batch is
  * uploaded once with sp_upload, sp_run_resident enqueues kernels only. */
 int sp_upload(sp_ctx *ctx, const sp_flat_batch *batch, int slot);

@@ -106,7 +106,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = [
     "sp_params_default", "sp_params_preset", "sp_create", "sp_destroy", "sp_last_error", "sp_version",
-    "sp_set_reference_ascii", "sp_set_reference_codes", "sp_submit", "sp_wait", "sp_poll", "sp_upload", "sp_run_resident",
+    "sp_set_reference_ascii", "sp_set_reference_codes", "sp_submit", "sp_wait", "sp_poll", "sp_mark", "sp_elapsed_since_mark", "sp_upload", "sp_run_resident",
     "sp_debug_table", "sp_hmm_batch", "sp_fp64_peak", "sp_rng_seed", "sp_rng_next", "sp_host_alloc", "sp_host_free",
 ]
 
@@ -327,6 +327,23 @@ class Secphase:
                                       pmax.ctypes.data, C.byref(ms)))
         sp = lambda a: [a[int(row_off[j]):int(row_off[j + 1])] for j in range(n)]  # noqa: E731
         return sp(state), sp(q), sp(pmax), ms.value
+
+    def poll(self, slot=0):
+        """True once the slot's batch has finished on the device (wait() will not block on the GPU)."""
+        r = self._L.sp_poll(self._h, slot)
+        if r < 0:
+            self._ck(r)
+        return r == 1
+
+    def mark(self):
+        """Start of a device-side stopwatch (CUDA event on slot 0's stream); see elapsed_since_mark."""
+        self._ck(self._L.sp_mark(self._h))
+
+    def elapsed_since_mark(self, slot=0):
+        """CUDA-event milliseconds from mark() to the end of the last batch waited for on `slot`."""
+        ms = C.c_float()
+        self._ck(self._L.sp_elapsed_since_mark(self._h, slot, C.byref(ms)))
+        return ms.value
 
     def fp64_peak(self, mode=0):
         ops = C.c_double()

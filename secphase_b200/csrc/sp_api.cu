@@ -133,6 +133,7 @@ struct sp_ctx {
     bool debug_tables = false;
     int sm_count = 0;
     size_t max_smem = 0;
+    cudaEvent_t mark = nullptr;  // sp_mark / sp_elapsed_since_mark
 };
 
 // ------------------------------------------------------------------------------------------
@@ -693,6 +694,25 @@ int sp_run_resident(sp_ctx *c, int slot) {
     rc = enqueue_results(S);
     if (rc) return rc;
     S.state = 2;
+    return SP_OK;
+}
+
+int sp_mark(sp_ctx *c) {
+    if (!c) return SP_EINVAL;
+    CK(cudaSetDevice(c->device));
+    if (!c->mark) CK(cudaEventCreate(&c->mark));
+    CK(cudaEventRecord(c->mark, c->slot[0].stream));
+    return SP_OK;
+}
+
+int sp_elapsed_since_mark(sp_ctx *c, int slot, float *ms) {
+    if (!c || slot < 0 || slot >= SP_N_SLOTS || !ms) return SP_EINVAL;
+    if (!c->mark || c->slot[slot].state != 3) {
+        set_err("sp_elapsed_since_mark needs sp_mark and a completed sp_wait on slot %d", slot);
+        return SP_ESTATE;
+    }
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventElapsedTime(ms, c->mark, c->slot[slot].ev[EV_END]));
     return SP_OK;
 }
 

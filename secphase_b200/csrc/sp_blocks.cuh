@@ -109,18 +109,24 @@ SP_HD int sp_correct_conf_blocks(const SpGroupAlnView &G, int P, const int32_t *
         if (P > 0) {
             int start = sp_max(ai.rds_f, gpos[0] - margin);
             int end = sp_min(ai.rde_f, gpos[0] + margin);
-            const int64_t total = (int64_t) P * n;  // the marker list holds n entries per position
-            for (int64_t idx = 1; idx < total; idx++) {
-                const int p = gpos[idx / n];
+            // The marker list holds n entries per position (ptMarker.c:455-476 iterates all of them).
+            // After the first entry of a position `end` equals that position's own clipped end, so the
+            // other n-1 entries are no-ops whenever the clipped interval is non-degenerate (cs < ce);
+            // only degenerate ones (cs >= ce) are replayed entry by entry.
+            for (int pi = 0; pi < P; pi++) {
+                const int p = gpos[pi];
                 const int cs = sp_max(ai.rds_f, p - margin);
                 const int ce = sp_min(ai.rde_f, p + margin);
-                if (cs < end) {
-                    end = ce;
-                } else {
-                    if (nf < cap) { W.flank[nf].s = start; W.flank[nf].e = end; } else *err |= SP_GERR_BLOCK_CAP;
-                    nf++;
-                    start = cs;
-                    end = ce;
+                const int reps = (cs < ce) ? 1 : n;
+                for (int r = (pi == 0 ? 1 : 0); r < (pi == 0 ? sp_max(reps, 1) : reps); r++) {
+                    if (cs < end) {
+                        end = ce;
+                    } else {
+                        if (nf < cap) { W.flank[nf].s = start; W.flank[nf].e = end; } else *err |= SP_GERR_BLOCK_CAP;
+                        nf++;
+                        start = cs;
+                        end = ce;
+                    }
                 }
             }
             if (nf < cap) { W.flank[nf].s = start; W.flank[nf].e = end; } else *err |= SP_GERR_BLOCK_CAP;
@@ -149,6 +155,25 @@ SP_HD int sp_correct_conf_blocks(const SpGroupAlnView &G, int P, const int32_t *
         int rfs = 0, rfe = 0, sqs = 0, sqe = 0;  // the reference leaves these uninitialised
         if (rev) { b_s = -cur[j].e; b_e = -cur[j].s; } else { b_s = cur[j].s; b_e = cur[j].e; }
         for (int o = 0; o < n_ops; o++) {
+            // Ops that cannot touch the current block are jumped over with a binary search in the op
+            // table instead of being visited (the reference walks every op of the record in every
+            // round of the x0.8 loop, ptMarker.c:545-641).  In walking coordinates an op spans
+            // [w[o], w[o+1]-1]; with del_flag clear, an op matters only if it ends at or after b_s-1
+            // (it may contain b_s, or be a deletion sitting at b_s) and, once ops start past b_s,
+            // only if it reaches b_e (the emitting branch).  Everything skipped would at most have
+            // cleared del_flag, which is already clear.
+            if (!del_flag) {
+                const int w0 = rev ? -ops[o].rdx : ops[o].rdx;
+                const int target = (w0 > b_s) ? b_e + 1 : b_s;
+                int lo = o, hi = n_ops;  // first idx in [o, n_ops) with w[idx+1] >= target
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int w1 = rev ? -ops[mid + 1].rdx : ops[mid + 1].rdx;
+                    if (w1 >= target) hi = mid; else lo = mid + 1;
+                }
+                o = lo;
+                if (o >= n_ops) break;
+            }
             const SpOpView v = sp_op_view(ops, o, rev);
             int c_s, c_e;
             if (rev) { c_s = -v.rde_f; c_e = -v.rds_f; } else { c_s = v.rds_f; c_e = v.rde_f; }

@@ -21,6 +21,7 @@
 #include <sys/types.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cfloat>
 #include <chrono>
 #include <condition_variable>
@@ -436,13 +437,19 @@ int main(int argc, char *argv[]) {
     }
     fprintf(stderr, "[%s] Started parsing alignments\n", get_timestamp());
 
+    std::atomic<int64_t> ingest_us{0}, submit_us{0}, wait_us{0}, starved_us{0};
+    auto now_us = [] {
+        return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
     std::thread reader([&] {
         int64_t seq = 0;
         for (;;) {
             sph_batch *hb = nullptr;
             if (!free_q.pop(hb)) break;
             if (shared.is_failed()) break;
+            int64_t t0 = now_us();
             int32_t n = sph_bam_next_batch(bam, hb, batch_groups, batch_mb << 20);
+            ingest_us += now_us() - t0;
             if (n < 0) {
                 shared.fail(sph_last_error());
                 break;
@@ -469,7 +476,10 @@ int main(int argc, char *argv[]) {
                 InFlight f = inflight.front();
                 inflight.pop_front();
                 sp_result r;
-                if (sp_wait(cx, f.slot, &r) != SP_OK) {
+                int64_t t0 = now_us();
+                int wrc = sp_wait(cx, f.slot, &r);
+                wait_us += now_us() - t0;
+                if (wrc != SP_OK) {
                     shared.fail(std::string("GPU ") + std::to_string(d) + ": " + sp_last_error());
                     return false;
                 }
@@ -494,7 +504,9 @@ int main(int argc, char *argv[]) {
             for (;;) {
                 if (shared.is_failed()) break;
                 // with batches in flight never block on the reader: retire finished ones meanwhile
+                int64_t tq = now_us();
                 int st = inflight.empty() ? (work_q.pop(w) ? 1 : -1) : work_q.try_pop(w);
+                if (inflight.empty()) starved_us += now_us() - tq;
                 if (st < 0) break;  // closed and drained
                 if (st == 0) {
                     int done = sp_poll(cx, inflight.front().slot);
@@ -511,7 +523,10 @@ int main(int argc, char *argv[]) {
                     continue;
                 }
                 if ((int) inflight.size() == SP_N_SLOTS && !(ok = collect())) break;
-                if (sp_submit(cx, sph_batch_view(w.hb), next_slot) != SP_OK) {
+                int64_t t0 = now_us();
+                int src = sp_submit(cx, sph_batch_view(w.hb), next_slot);
+                submit_us += now_us() - t0;
+                if (src != SP_OK) {
                     shared.fail(std::string("GPU ") + std::to_string(d) + ": " + sp_last_error());
                     ok = false;
                     break;
@@ -639,10 +654,12 @@ int main(int argc, char *argv[]) {
         fprintf(stderr,
                 "[secphase_b200] {\"read_groups\": %lld, \"alignments\": %lld, \"parsed_alignments\": %lld, \"parsed_reads\": %lld, "
                 "\"hmm_instances\": %lld, \"hmm_cells\": %lld, \"gpus\": %d, \"host_threads\": %d, \"setup_s\": %.3f, "
-                "\"score_s\": %.3f, \"gpu_busy_ms\": %.1f, \"hmm_ms\": %.1f, \"gpu_launches\": %lld, \"total_s\": %.3f}\n",
+                "\"score_s\": %.3f, \"gpu_busy_ms\": %.1f, \"hmm_ms\": %.1f, \"gpu_launches\": %lld, \"ingest_s\": %.3f, "
+                "\"submit_s\": %.3f, \"wait_s\": %.3f, \"gpu_starved_s\": %.3f, \"total_s\": %.3f}\n",
                 (long long) total_groups, (long long) total_alns, (long long) pa, (long long) pr, (long long) hmm_instances,
                 (long long) hmm_cells, n_gpus, threads, secs(t_start, t_ready), secs(t_ready, t_scored), gpu_ms, hmm_ms,
-                (long long) launches, secs(t_start, std::chrono::steady_clock::now()));
+                (long long) launches, ingest_us.load() * 1e-6, submit_us.load() * 1e-6, wait_us.load() * 1e-6,
+                starved_us.load() * 1e-6, secs(t_start, std::chrono::steady_clock::now()));
     }
     for (sph_batch *hb : all_batches) sph_batch_destroy(hb);
     sph_blocks_destroy(modified_blocks_by_vars);

@@ -60,9 +60,12 @@ struct sph_batch {
     std::vector<char> qname_pool;
     sp_flat_batch view;
 
-    int reserve(Pool &pl, size_t need) {
+    // `scale` extrapolates from what is packed so far to the full batch (>= 1): page-locked
+    // allocations are slow and cudaFreeHost synchronises the device, so a pool is sized once for
+    // the whole batch instead of growing chunk by chunk
+    int reserve(Pool &pl, size_t need, double scale = 1.0) {
         if (need <= pl.cap) return SPH_OK;
-        size_t ncap = std::max(need + need / 4, (size_t) 1 << 20);
+        size_t ncap = std::max((size_t) ((double) need * scale * 1.15) + 4096, (size_t) 1 << 20);
         uint8_t *np = (uint8_t *) alloc(ncap);
         if (!np) {
             set_error("cannot allocate a %zu-byte host pool", ncap);
@@ -123,6 +126,8 @@ struct sph_bam {
     std::vector<AlnDesc> open;
     std::vector<GroupDesc> pending;
     int64_t pending_bytes = 0;
+    int64_t target_bytes = 0;  // limits of the batch being filled (pool pre-sizing)
+    int32_t target_groups = 0;
     bool have_held = false;
     GroupDesc held;
     std::atomic<int64_t> n_records{0}, parsed_reads{0};
@@ -187,8 +192,17 @@ int sph_bam::pack_pending(sph_batch *b) {
         b->grp_aln_off.push_back((int32_t) (a0 + k));
     }
     int rc;
-    if ((rc = b->reserve(b->cigar, oc + 16)) || (rc = b->reserve(b->tag, ot + 16)) ||
-        (rc = b->reserve(b->seq, os + 16)) || (rc = b->reserve(b->qual, oq + 16)))
+    // expected final size of this batch relative to what it holds after this pack
+    double scale = 1.0;
+    {
+        const double have_b = (double) (oc + ot + os + oq), have_g = (double) (b->grp_aln_off.size() - 1);
+        if (have_b > 0 && have_g > 0) {
+            double by_bytes = (double) target_bytes / have_b, by_groups = (double) target_groups / have_g;
+            scale = std::max(1.0, std::min(by_bytes, by_groups));
+        }
+    }
+    if ((rc = b->reserve(b->cigar, oc + 16, scale)) || (rc = b->reserve(b->tag, ot + 16, scale)) ||
+        (rc = b->reserve(b->seq, os + 16, scale)) || (rc = b->reserve(b->qual, oq + 16, scale)))
         return rc;
     uint8_t *pc = b->cigar.p, *pt = b->tag.p, *ps = b->seq.p, *pq = b->qual.p;
     pool.parallel_for((int64_t) n_new, [&](int64_t i) {
@@ -446,6 +460,8 @@ int32_t sph_bam_next_batch(sph_bam *r, sph_batch *b, int32_t max_groups, int64_t
     }
     if (r->err) return r->err;
     b->clear();
+    r->target_bytes = max_bytes;
+    r->target_groups = max_groups;
     int32_t n_groups = 0;
     int64_t n_bytes = 0;
     auto take = [&](const GroupDesc &g) {

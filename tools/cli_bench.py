@@ -71,6 +71,8 @@ def main():
             "groups_per_s_total": best["read_groups"] / best["total_s"],
             "gcups_scoring": best["hmm_cells"] / best["score_s"] / 1e9,
             "gpu_busy_ms": best["gpu_busy_ms"], "hmm_ms": best["hmm_ms"], "gpu_launches": best["gpu_launches"],
+            "ingest_s": best["ingest_s"], "submit_s": best["submit_s"], "wait_s": best["wait_s"],
+            "gpu_starved_s": best["gpu_starved_s"],
         }))
     finally:
         if not args.keep:
