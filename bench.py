@@ -31,6 +31,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# three slots x five streams per context: enough hardware queues that they do not alias (must be in
+# the environment before the first CUDA call of the process, which is torch's)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 
@@ -325,7 +328,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "groups_per_step_per_gpu": args.groups, "slots_in_flight": n_slots,
                    "l2": "per-step input (~%.0f MB) exceeds the 126 MB L2; no explicit flush" % (stats[0]["h2d_bytes"] / 1e6 if stats[0]["h2d_bytes"] else estats[0]["h2d_bytes"] / 1e6),
-                   "parallelism": f"read groups sharded by qname range over {world} GPU(s), no collective"},
+                   "parallelism": f"read groups sharded by qname range over {world} GPU(s), no collective",
+                   "sm_partition": dict(zip(("on", "int_sms", "hmm_sms"), eng.sm_partition()))},
         "gcups": gcups_job, "gcups_kernel": gcups_kernel,
         "hmm_instances_per_step": float(np.mean([s["hmm_instances"] for s in stats])),
         "band_cells_per_step": cells_step,

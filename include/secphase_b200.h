@@ -111,7 +111,10 @@ void *sp_host_alloc(size_t bytes); /* NULL on error */
 void sp_host_free(void *p);
 
 /* Asynchronous: stages the per-alignment metadata (and any pageable pool) into the slot's pinned
- * buffer, then enqueues H2D copies -> kernels -> D2H copy on the slot's stream.
+ * buffer, enqueues the H2D copies and the first kernels (walk, group) on the slot's stream and
+ * returns without waiting for the device.  The rest of the batch (HMM tables sized from the
+ * device-side totals, HMM kernels, scoring, D2H) is enqueued by the context's launcher thread as
+ * soon as those totals arrive, so the caller's thread is free to submit the next batch at once.
  * slot in [0, SP_N_SLOTS). */
 int sp_submit(sp_ctx *ctx, const sp_flat_batch *batch, int slot);
 /* Blocks until the slot's batch is complete, replays the tie-break RNG for its groups and fills
@@ -129,6 +132,12 @@ int sp_poll(sp_ctx *ctx, int slot);
  * run is the maximum over the slots used. */
 int sp_mark(sp_ctx *ctx);
 int sp_elapsed_since_mark(sp_ctx *ctx, int slot, float *ms);
+
+/* How the context split the GPU: the latency-bound integer stages of a batch run on *int_sms SMs of
+ * their own (a CUDA green context) while the FP64 HMM kernels of the batches ahead of it keep the
+ * other *hmm_sms.  Returns 1 when partitioned, 0 when not (both counts are then the whole GPU);
+ * SECPHASE_B200_INT_SMS=<n> in the environment of sp_create changes the request (0 = off). */
+int sp_sm_partition(sp_ctx *ctx, int32_t *int_sms, int32_t *hmm_sms);
 
 /* --- device-resident variant used to time the kernels alone (bench `value`): the batch is
  * uploaded once with sp_upload, sp_run_resident enqueues kernels only. */

@@ -97,6 +97,8 @@ def load_library(path=None):
     L.sp_host_alloc.argtypes = [C.c_size_t]
     L.sp_host_alloc.restype = C.c_void_p
     L.sp_host_free.argtypes = [C.c_void_p]
+    L.sp_sm_partition.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.sp_sm_partition.restype = C.c_int
     L.sp_rng_seed.argtypes = [C.c_void_p, C.c_uint]
     L.sp_rng_next.argtypes = [C.c_void_p]
     L.sp_rng_next.restype = C.c_int
@@ -106,7 +108,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = [
     "sp_params_default", "sp_params_preset", "sp_create", "sp_destroy", "sp_last_error", "sp_version",
-    "sp_set_reference_ascii", "sp_set_reference_codes", "sp_submit", "sp_wait", "sp_poll", "sp_mark", "sp_elapsed_since_mark", "sp_upload", "sp_run_resident",
+    "sp_set_reference_ascii", "sp_set_reference_codes", "sp_submit", "sp_wait", "sp_poll", "sp_sm_partition", "sp_mark", "sp_elapsed_since_mark", "sp_upload", "sp_run_resident",
     "sp_debug_table", "sp_hmm_batch", "sp_fp64_peak", "sp_rng_seed", "sp_rng_next", "sp_host_alloc", "sp_host_free",
 ]
 
@@ -334,6 +336,14 @@ class Secphase:
         if r < 0:
             self._ck(r)
         return r == 1
+
+    def sm_partition(self):
+        """(partitioned, int_sms, hmm_sms): SMs set aside for the integer stages / left to the HMM kernels."""
+        a, b = C.c_int32(), C.c_int32()
+        r = self._L.sp_sm_partition(self._h, C.byref(a), C.byref(b))
+        if r < 0:
+            self._ck(r)
+        return bool(r), a.value, b.value
 
     def mark(self):
         """Start of a device-side stopwatch (CUDA event on slot 0's stream); see elapsed_since_mark."""

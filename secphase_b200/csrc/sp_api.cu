@@ -2,13 +2,18 @@
 // that drives the kernels of sp_kernels.cuh.  Host side only plans, packs into pinned staging,
 // enqueues, and turns the device results into the reference's tables; there is no CPU
 // implementation of the hot path in this library.
+#include <cuda.h>  // types of the driver's green-context API only; entry points come from cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/secphase_b200.h"
@@ -109,6 +114,14 @@ struct Slot {
     SpBatchPtrs P;
     SpTotals tot;     // after the mid-pipeline read-back
     int state = 0;    // 0 idle, 1 uploaded, 2 in flight, 3 done
+    // Two-phase enqueue: the caller's thread enqueues phase A (H2D, walk, group, scan, totals read-back)
+    // and returns; the context's launcher thread waits for ev_a, sizes the HMM tables from the totals
+    // and enqueues phase B (emit, sort, HMM, score, result copies).  phase: 0 none, 1 A enqueued,
+    // 2 B enqueued (or failed: b_rc/b_err), guarded by sp_ctx::mu.
+    cudaEvent_t ev_a = nullptr;
+    int phase = 0;
+    int b_rc = 0;
+    std::string b_err;
     bool want_d2h = true;
     bool debug = false;
     int launches = 0;
@@ -134,7 +147,115 @@ struct sp_ctx {
     int sm_count = 0;
     size_t max_smem = 0;
     cudaEvent_t mark = nullptr;  // sp_mark / sp_elapsed_since_mark
+    // SM partition (green contexts): the latency-bound integer kernels of a batch (walk, group, scan,
+    // emit, sort, score) run on a few SMs of their own while the persistent FP64 HMM kernels of the
+    // batches ahead of it own the rest; without it a persistent HMM CTA per SM keeps the 1024-thread
+    // scan CTAs of the next batch waiting until the whole HMM kernel has drained.
+    bool partitioned = false;
+    CUgreenCtx g_int = nullptr, g_hmm = nullptr;
+    int int_sms = 0, hmm_sms = 0;
+    CUresult (*p_green_destroy)(CUgreenCtx) = nullptr;
+    // launcher thread (phase B of every slot, in submission order)
+    std::thread launcher;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<int> queue;
+    bool stop = false;
 };
+
+// ------------------------------------------------------------------------------------------
+// SM partition.  Everything is looked up at run time so that the library neither links libcuda nor
+// fails where green contexts are missing: any failure leaves the context un-partitioned.
+static void sp_log(const char *fmt, ...) {
+    if (!getenv("SECPHASE_B200_VERBOSE")) return;
+    va_list ap;
+    va_start(ap, fmt);
+    fputs("[secphase_b200:info] ", stderr);
+    vfprintf(stderr, fmt, ap);
+    fputc('\n', stderr);
+    va_end(ap);
+}
+
+template <class F> static bool drv(const char *name, F &fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+        cudaGetLastError();
+        return false;
+    }
+    fn = reinterpret_cast<F>(p);
+    return true;
+}
+
+static CUresult (*g_green_stream_create)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+
+static void partition_sms(sp_ctx *c, int want_int) {
+    c->partitioned = false;
+    c->hmm_sms = c->sm_count;
+    c->int_sms = c->sm_count;
+    if (want_int <= 0) return;
+    CUresult (*pDeviceGet)(CUdevice *, int) = nullptr;
+    CUresult (*pGetRes)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+    CUresult (*pSplit)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int) = nullptr;
+    CUresult (*pDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int) = nullptr;
+    CUresult (*pCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    if (!drv("cuDeviceGet", pDeviceGet) || !drv("cuDeviceGetDevResource", pGetRes) ||
+        !drv("cuDevSmResourceSplitByCount", pSplit) || !drv("cuDevResourceGenerateDesc", pDesc) ||
+        !drv("cuGreenCtxCreate", pCreate) || !drv("cuGreenCtxDestroy", c->p_green_destroy) ||
+        !drv("cuGreenCtxStreamCreate", g_green_stream_create)) {
+        sp_log("green-context entry points not available; SMs not partitioned");
+        return;
+    }
+    CUdevice dev;
+    CUdevResource all, small, rest;
+    memset(&all, 0, sizeof(all)); memset(&small, 0, sizeof(small)); memset(&rest, 0, sizeof(rest));
+    unsigned int nb = 1;
+    CUresult r;
+    if ((r = pDeviceGet(&dev, c->device)) != CUDA_SUCCESS || (r = pGetRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM)) != CUDA_SUCCESS) {
+        sp_log("cuDeviceGetDevResource failed (%d); SMs not partitioned", (int) r);
+        return;
+    }
+    r = pSplit(&small, &nb, &all, &rest, CU_DEV_SM_RESOURCE_SPLIT_IGNORE_SM_COSCHEDULING, (unsigned) want_int);
+    if (r != CUDA_SUCCESS || nb < 1 || small.sm.smCount == 0 || rest.sm.smCount == 0) {
+        sp_log("cuDevSmResourceSplitByCount(%d) failed (%d); SMs not partitioned", want_int, (int) r);
+        return;
+    }
+    CUdevResourceDesc d_int = nullptr, d_hmm = nullptr;
+    if ((r = pDesc(&d_int, &small, 1)) != CUDA_SUCCESS || (r = pDesc(&d_hmm, &rest, 1)) != CUDA_SUCCESS) {
+        sp_log("cuDevResourceGenerateDesc failed (%d); SMs not partitioned", (int) r);
+        return;
+    }
+    if ((r = pCreate(&c->g_int, d_int, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) {
+        sp_log("cuGreenCtxCreate failed (%d); SMs not partitioned", (int) r);
+        c->g_int = nullptr;
+        return;
+    }
+    if ((r = pCreate(&c->g_hmm, d_hmm, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) {
+        sp_log("cuGreenCtxCreate failed (%d); SMs not partitioned", (int) r);
+        c->p_green_destroy(c->g_int);
+        c->g_int = c->g_hmm = nullptr;
+        return;
+    }
+    c->partitioned = true;
+    c->int_sms = (int) small.sm.smCount;
+    c->hmm_sms = (int) rest.sm.smCount;
+    sp_log("SM partition: %d SMs for the integer stages, %d SMs for the HMM kernels", c->int_sms, c->hmm_sms);
+}
+
+// a non-blocking stream inside green context g (or an ordinary one when the device is not partitioned)
+static bool make_stream(sp_ctx *c, CUgreenCtx g, cudaStream_t *out) {
+    if (c->partitioned && g) {
+        CUstream s = nullptr;
+        if (g_green_stream_create(&s, g, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS) {
+            *out = reinterpret_cast<cudaStream_t>(s);
+            return true;
+        }
+        return false;
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking) == cudaSuccess;
+}
+
+static void launcher_main(sp_ctx *c);
 
 // ------------------------------------------------------------------------------------------
 extern "C" {
@@ -183,6 +304,10 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
         set_err("sp_create: params is NULL");
         return nullptr;
     }
+    // three slots x (1 + SP_N_AUX) streams: ask for enough hardware queues that streams of different
+    // slots do not alias (read by the driver when it creates the device context, i.e. only if nothing
+    // in the process has touched CUDA yet; bench.py and the CLI set it themselves at start-up)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -222,21 +347,46 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
         delete c;
         return nullptr;
     }
-    for (int s = 0; s < SP_N_SLOTS; s++) {
-        cudaStreamCreateWithFlags(&c->slot[s].stream, cudaStreamNonBlocking);
-        for (int k = 0; k < EV_N; k++) cudaEventCreate(&c->slot[s].ev[k]);
-        cudaEventCreateWithFlags(&c->slot[s].ev_fork, cudaEventDisableTiming);
-        for (int k = 0; k < SP_N_AUX; k++) {
-            cudaStreamCreateWithFlags(&c->slot[s].aux[k], cudaStreamNonBlocking);
-            cudaEventCreateWithFlags(&c->slot[s].ev_join[k], cudaEventDisableTiming);
+    // SECPHASE_B200_INT_SMS: SMs set aside for the integer stages (0 = no partition); the driver
+    // rounds the request up to its own granularity
+    {
+        const char *e = getenv("SECPHASE_B200_INT_SMS");
+        int want = e ? atoi(e) : 8;
+        if (want >= c->sm_count) want = 0;
+        partition_sms(c, want);
+    }
+    bool ok = true;
+    for (int s = 0; s < SP_N_SLOTS && ok; s++) {
+        Slot &S = c->slot[s];
+        ok = ok && make_stream(c, c->g_int, &S.stream);
+        for (int k = 0; k < EV_N; k++) ok = ok && cudaEventCreate(&S.ev[k]) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&S.ev_a, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
+        for (int k = 0; k < SP_N_AUX && ok; k++) {
+            ok = ok && make_stream(c, c->g_hmm, &S.aux[k]);
+            ok = ok && cudaEventCreateWithFlags(&S.ev_join[k], cudaEventDisableTiming) == cudaSuccess;
         }
     }
+    if (!ok) {
+        set_err("sp_create: could not create streams/events: %s", cudaGetErrorString(cudaGetLastError()));
+        sp_destroy(c);
+        return nullptr;
+    }
     c->rng.seed(1);
+    c->launcher = std::thread(launcher_main, c);
     return c;
 }
 
 void sp_destroy(sp_ctx *c) {
     if (!c) return;
+    if (c->launcher.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            c->stop = true;
+        }
+        c->cv_work.notify_all();
+        c->launcher.join();
+    }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (int s = 0; s < SP_N_SLOTS; s++) {
@@ -251,6 +401,7 @@ void sp_destroy(sp_ctx *c) {
         for (int k = 0; k < EV_N; k++)
             if (S.ev[k]) cudaEventDestroy(S.ev[k]);
         if (S.ev_fork) cudaEventDestroy(S.ev_fork);
+        if (S.ev_a) cudaEventDestroy(S.ev_a);
         for (int k = 0; k < SP_N_AUX; k++) {
             if (S.ev_join[k]) cudaEventDestroy(S.ev_join[k]);
             if (S.aux[k]) cudaStreamDestroy(S.aux[k]);
@@ -260,6 +411,11 @@ void sp_destroy(sp_ctx *c) {
     c->dC.release();
     c->ref.release();
     c->contig_off.release();
+    if (c->mark) cudaEventDestroy(c->mark);
+    if (c->partitioned && c->p_green_destroy) {
+        c->p_green_destroy(c->g_int);
+        c->p_green_destroy(c->g_hmm);
+    }
     delete c;
 }
 
@@ -493,7 +649,7 @@ static void launch_hmm2(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first,
     if (wpc > 7) wpc = 7;  // k_hmm2 is compiled for at most 224 threads per CTA
     if (wpc > nblk) wpc = nblk;
     int grid = (nblk + wpc - 1) / wpc;
-    if (grid > c->sm_count) grid = c->sm_count;
+    if (grid > c->hmm_sms) grid = c->hmm_sms;
     k_hmm2<NW, NC><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(),
                                                    first, cnt, ncell, ref, qbytes, seq_pool, seq_off,
                                                    S.s_pool.as<double>(), S.fsave.as<double>(), fs_stride,
@@ -554,8 +710,10 @@ static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_
     return SP_OK;
 }
 
-// enqueue kernels for the batch staged in S (device copy already enqueued or resident)
-static int run_pipeline(sp_ctx *c, Slot &S) {
+// Phase A, enqueued by the caller's thread for the batch staged in S (device copy already enqueued
+// or resident): walk, group, scans, and the one mid-pipeline read-back (instance / row / band totals,
+// which size the HMM tables and launches).  The launcher thread picks the slot up from there.
+static int run_phase_a(sp_ctx *c, Slot &S) {
     cudaStream_t st = S.stream;
     const SpBatchPtrs &P = S.P;
     const SpConst *dC = c->dC.as<SpConst>();
@@ -576,8 +734,17 @@ static int run_pipeline(sp_ctx *c, Slot &S) {
     CK(cudaEventRecord(S.ev[EV_GROUP], st));
     // the one mid-pipeline read-back: instance / row / band totals size the HMM launch
     CK(cudaMemcpyAsync(S.h_tot.p, S.totals.p, sizeof(SpTotals), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(S.ev_a, st));
     CK(cudaGetLastError());
+    return SP_OK;
+}
+
+// Phase B, enqueued by the launcher thread once ev_a has fired: emit, sort, HMM, score.
+static int run_phase_b(sp_ctx *c, Slot &S) {
+    cudaStream_t st = S.stream;
+    const SpBatchPtrs &P = S.P;
+    const SpConst *dC = c->dC.as<SpConst>();
+    CK(cudaEventSynchronize(S.ev_a));
     S.tot = *S.h_tot.as<SpTotals>();
     const SpTotals &T = S.tot;
     int rc;
@@ -611,6 +778,50 @@ static int run_pipeline(sp_ctx *c, Slot &S) {
     CK(cudaEventRecord(S.ev[EV_SCORE], st));
     CK(cudaGetLastError());
     return SP_OK;
+}
+
+static int enqueue_results(Slot &S);
+
+static void hand_to_launcher(sp_ctx *c, int slot) {
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->slot[slot].phase = 1;
+        c->slot[slot].b_rc = 0;
+        c->queue.push_back(slot);
+    }
+    c->cv_work.notify_one();
+}
+
+static void launcher_main(sp_ctx *c) {
+    cudaSetDevice(c->device);
+    for (;;) {
+        int s;
+        {
+            std::unique_lock<std::mutex> lk(c->mu);
+            c->cv_work.wait(lk, [&] { return c->stop || !c->queue.empty(); });
+            if (c->queue.empty()) return;  // stop requested and nothing left to launch
+            s = c->queue.front();
+            c->queue.pop_front();
+        }
+        Slot &S = c->slot[s];
+        int rc = run_phase_b(c, S);
+        if (rc == SP_OK) rc = enqueue_results(S);
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            S.b_rc = rc;
+            if (rc) S.b_err = g_err;  // this thread's message, re-raised by sp_wait in the caller's thread
+            S.phase = 2;
+        }
+        c->cv_done.notify_all();
+    }
+}
+
+// blocks until the launcher has enqueued (or failed to enqueue) phase B of the slot
+static int await_phase_b(sp_ctx *c, Slot &S) {
+    std::unique_lock<std::mutex> lk(c->mu);
+    c->cv_done.wait(lk, [&] { return S.phase == 2; });
+    if (S.b_rc) set_err("%s", S.b_err.c_str());
+    return S.b_rc;
 }
 
 static int enqueue_h2d(Slot &S) {
@@ -655,12 +866,11 @@ int sp_submit(sp_ctx *c, const sp_flat_batch *b, int slot) {
     if ((rc = enqueue_h2d(S))) return rc;
     CK(cudaEventRecord(S.ev[EV_H2D], S.stream));
     S.h2d_bytes = (int64_t) S.in_bytes;
-    rc = run_pipeline(c, S);
-    if (rc) return rc;
-    rc = enqueue_results(S);
+    rc = run_phase_a(c, S);
     if (rc) return rc;
     S.state = 2;
     S.want_d2h = true;
+    hand_to_launcher(c, slot);
     return SP_OK;
 }
 
@@ -689,11 +899,14 @@ int sp_run_resident(sp_ctx *c, int slot) {
     }
     CK(cudaEventRecord(S.ev[EV_START], S.stream));
     CK(cudaEventRecord(S.ev[EV_H2D], S.stream));
-    int rc = run_pipeline(c, S);
-    if (rc) return rc;
-    rc = enqueue_results(S);
+    if (S.state == 2) {
+        set_err("slot %d still in flight; call sp_wait first", slot);
+        return SP_ESTATE;
+    }
+    int rc = run_phase_a(c, S);
     if (rc) return rc;
     S.state = 2;
+    hand_to_launcher(c, slot);
     return SP_OK;
 }
 
@@ -716,12 +929,24 @@ int sp_elapsed_since_mark(sp_ctx *c, int slot, float *ms) {
     return SP_OK;
 }
 
+int sp_sm_partition(sp_ctx *c, int32_t *int_sms, int32_t *hmm_sms) {
+    if (!c) return SP_EINVAL;
+    if (int_sms) *int_sms = c->int_sms;
+    if (hmm_sms) *hmm_sms = c->hmm_sms;
+    return c->partitioned ? 1 : 0;
+}
+
 int sp_poll(sp_ctx *c, int slot) {
     if (!c || slot < 0 || slot >= SP_N_SLOTS) return SP_EINVAL;
     Slot &S = c->slot[slot];
     if (S.state != 2) {
         set_err("slot %d has nothing in flight", slot);
         return SP_ESTATE;
+    }
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (S.phase != 2) return 0;
+        if (S.b_rc) return 1;  // sp_wait reports the error
     }
     CK(cudaSetDevice(c->device));
     cudaError_t e = cudaStreamQuery(S.stream);
@@ -741,6 +966,11 @@ int sp_wait(sp_ctx *c, int slot, sp_result *out) {
     if (S.state != 2) {
         set_err("slot %d has nothing in flight", slot);
         return SP_ESTATE;
+    }
+    if (int brc = await_phase_b(c, S)) {
+        cudaStreamSynchronize(S.stream);
+        S.state = 3;
+        return brc;
     }
     CK(cudaStreamSynchronize(S.stream));
     SpTotals T = *S.h_tot.as<SpTotals>();
@@ -974,6 +1204,10 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
         }
     }
     Slot &S = c->slot[0];
+    if (S.state == 2) {
+        set_err("sp_hmm_batch uses slot 0, which still has a batch in flight");
+        return SP_ESTATE;
+    }
     cudaStream_t st = S.stream;
     DevBuf d_ref, d_q;
     int rc;

@@ -270,15 +270,16 @@ SP_HD int sp_hmm_bw(int l_ref, int l_query, int par_bw) {  // band half-width pr
     if (bw < d) bw = d;
     return bw;
 }
+// band cells of one instance: sum over rows i = 1..l_query of the columns max(1,i-bw)..min(l_ref,i+bw).
+// Closed form; every row is non-empty because bw >= |l_ref - l_query| (sp_hmm_bw).
 SP_HD int64_t sp_hmm_cells(int l_ref, int l_query, int bw) {
-    int64_t cells = 0;
-    // rows 1..l_query, columns max(1,i-bw)..min(l_ref,i+bw)
-    for (int i = 1; i <= l_query; i++) {
-        int beg = i - bw > 1 ? i - bw : 1;
-        int end = i + bw < l_ref ? i + bw : l_ref;
-        if (end >= beg) cells += end - beg + 1;
-    }
-    return cells;
+    const int64_t Lr = l_ref, Lq = l_query, w = bw;
+    int64_t k1 = Lr - w;  // rows i <= k1 end at i+bw, the others at l_ref
+    k1 = k1 < 0 ? 0 : (k1 > Lq ? Lq : k1);
+    const int64_t s_end = k1 * (k1 + 1) / 2 + k1 * w + (Lq - k1) * Lr;
+    const int64_t k2 = Lq < w + 1 ? Lq : w + 1;  // rows i <= k2 begin at column 1, the others at i-bw
+    const int64_t s_beg = k2 + (Lq * (Lq + 1) / 2 - k2 * (k2 + 1) / 2) - (Lq - k2) * w;
+    return s_end - s_beg + Lq;
 }
 
 struct SpEmitCounts {

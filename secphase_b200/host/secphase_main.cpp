@@ -245,6 +245,7 @@ void merge_and_save_blocks(sph_blocks *t, const char *info_str, const char *bed_
 }  // namespace
 
 int main(int argc, char *argv[]) {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);  // slots x streams per GPU context, see sp_create
     sp_params par;
     sp_params_default(&par);
     int min_var_margin = 50, min_gq = 10;
