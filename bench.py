@@ -34,6 +34,8 @@ if ROOT not in sys.path:
 # three slots x five streams per context: enough hardware queues that they do not alias (must be in
 # the environment before the first CUDA call of the process, which is torch's)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 

@@ -99,6 +99,11 @@ typedef struct sp_result {
     float ms_hmm;              /* CUDA-event time of the BAQ-HMM kernels only */
     float ms_stage[8];         /* h2d, walk, group (markers+blocks+count), emit+sort, hmm, score, d2h, 0 */
     int32_t gpu_launches;      /* kernels launched for this batch */
+    /* --writeBam mode only (sp_set_write_qual), else NULL / 0: the quality arrays of every record as
+     * calc_update_baq_all leaves them (ptMarker.c:786, 709-720, 797-806), laid out exactly like the
+     * batch's qual_pool / qual_off -- what sam_write1 emits at secphase.c:182-189. */
+    const uint8_t *baq_qual;
+    int64_t baq_qual_bytes;
 } sp_result;
 
 /* Page-locked host memory for the pools of an sp_flat_batch (cigar_pool, tag_pool, seq_pool,
@@ -125,6 +130,14 @@ int sp_wait(sp_ctx *ctx, int slot, sp_result *out);
  * device while it retires finished batches (the reference's tpool_wait has no such need: its
  * workers write their own output, secphase.c:194-216). */
 int sp_poll(sp_ctx *ctx, int slot);
+
+/* -w/--writeBam (secphase.c:182-189, 643-657): when on, the HMM evaluates the MAP state / quality
+ * of every base of every window's write-back range (ptMarker.c:763-786) instead of the marker
+ * rows only, and sp_wait returns the modified quality arrays in sp_result.baq_qual.  Scores,
+ * markers and the selected alignment are unchanged by the mode.  Costs ~700 B of HBM per window
+ * row while a batch is in flight: submit smaller batches (the CLI uses 512 read groups).
+ * Must be called with no batch in flight. */
+int sp_set_write_qual(sp_ctx *ctx, int on);
 
 /* Device-side stopwatch over several batches (bench.py): sp_mark records a CUDA event on slot 0's
  * stream (call it when the device is idle); sp_elapsed_since_mark gives the CUDA-event time from

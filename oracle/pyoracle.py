@@ -72,7 +72,7 @@ def _load(kind):
     L.oracle_kind.restype = C.c_char_p
     for name, rt in [("groups", C.c_int32), ("scores", C.c_double), ("extents", C.c_int32),
                      ("blocks", C.c_int32), ("block_off", C.c_int64), ("hmm", C.c_int32),
-                     ("hmm_state", C.c_int32), ("hmm_q", C.c_uint8)]:
+                     ("hmm_state", C.c_int32), ("hmm_q", C.c_uint8), ("qual", C.c_uint8)]:
         f = getattr(L, "oracle_out_" + name)
         f.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         f.restype = C.POINTER(rt)
@@ -174,6 +174,7 @@ def run(batch, params, refseq, kind=None, keep_hmm=False, seed=1, outputs=None):
         res["hmm"] = _take(L.oracle_out_hmm(out, C.byref(n)), n.value, HMM_W, np.int32)
         res["hmm_state"] = _take(L.oracle_out_hmm_state(out, C.byref(n)), n.value, 1, np.int32)
         res["hmm_q"] = _take(L.oracle_out_hmm_q(out, C.byref(n)), n.value, 1, np.uint8)
+        res["qual"] = _take(L.oracle_out_qual(out, C.byref(n)), n.value, 1, np.uint8)
         for st, nm in enumerate(("markers_pre", "markers_baq", "markers_final")):
             res[nm] = _take(L.oracle_out_markers(out, st, C.byref(n)), n.value, MARKER_W, np.int32)
             res[nm + "_off"] = _take(L.oracle_out_marker_off(out, st, C.byref(n)), n.value, 1, np.int64)

@@ -46,6 +46,7 @@ struct oracle_out {
     stHash *marker_blocks;   /* marker_blocks_all_haps_per_contig */
     int reads_modified_by_marker;
     vec groups, scores, extents, markers[3], marker_off[3], blocks, block_off, hmm, hmm_state, hmm_q;
+    vec qual;                /* every record's quality array as the job leaves it (what sam_write1 emits, secphase.c:182-189) */
     int32_t cur_aln_global; /* for the HMM trace */
 };
 
@@ -64,6 +65,7 @@ oracle_out *oracle_out_create(int keep_hmm_arrays) {
     vec_init(&o->hmm, sizeof(int32_t));
     vec_init(&o->hmm_state, sizeof(int32_t));
     vec_init(&o->hmm_q, sizeof(uint8_t));
+    vec_init(&o->qual, sizeof(uint8_t));
     return o;
 }
 
@@ -152,7 +154,7 @@ void oracle_out_destroy(oracle_out *o) {
     }
     free(o->groups.p); free(o->scores.p); free(o->extents.p);
     for (int s = 0; s < 3; s++) { free(o->markers[s].p); free(o->marker_off[s].p); }
-    free(o->blocks.p); free(o->block_off.p); free(o->hmm.p); free(o->hmm_state.p); free(o->hmm_q.p);
+    free(o->blocks.p); free(o->block_off.p); free(o->hmm.p); free(o->hmm_state.p); free(o->hmm_q.p); free(o->qual.p);
     free(o);
 }
 
@@ -169,6 +171,7 @@ GETTER(oracle_out_block_off, block_off, int64_t, 1)
 GETTER(oracle_out_hmm, hmm, int32_t, ORACLE_HMM_W)
 GETTER(oracle_out_hmm_state, hmm_state, int32_t, 1)
 GETTER(oracle_out_hmm_q, hmm_q, uint8_t, 1)
+GETTER(oracle_out_qual, qual, uint8_t, 1)
 const int32_t *oracle_out_markers(const oracle_out *o, int stage, int64_t *n) {
     if (n) *n = o->markers[stage].n / ORACLE_MARKER_W;
     return (const int32_t *) o->markers[stage].p;
@@ -379,6 +382,9 @@ int oracle_run(const sp_flat_batch *b, const oracle_params *p, const oracle_refs
             *(double *) vec_push(&out->scores, 1) = alns[i]->score;
             int32_t *e = (int32_t *) vec_push(&out->extents, 4);
             e[0] = alns[i]->rfs; e[1] = alns[i]->rfe; e[2] = alns[i]->rds_f; e[3] = alns[i]->rde_f;
+            /* the qualities the record carries when secphase.c:182-189 writes it with -w */
+            int lq = alns[i]->record->core.l_qseq;
+            if (lq > 0) memcpy(vec_push(&out->qual, lq), bam_get_qual(alns[i]->record), (size_t) lq);
         }
         stList_destruct(markers);
         for (int i = 0; i < n; i++) ptAlignment_destruct(alns[i]);

@@ -64,6 +64,7 @@ const int64_t *oracle_out_block_off(const oracle_out *o, int64_t *n);           
 const int32_t *oracle_out_hmm(const oracle_out *o, int64_t *n);                    /* [n][ORACLE_HMM_W] */
 const int32_t *oracle_out_hmm_state(const oracle_out *o, int64_t *n);              /* concatenated state[] */
 const uint8_t *oracle_out_hmm_q(const oracle_out *o, int64_t *n);                  /* concatenated q[] */
+const uint8_t *oracle_out_qual(const oracle_out *o, int64_t *n);                   /* records' final quality arrays, batch qual_pool layout */
 const char *oracle_kind(void); /* "reference" or "port" */
 
 #ifdef __cplusplus

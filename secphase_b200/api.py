@@ -50,6 +50,7 @@ class _CResult(C.Structure):
         ("marker_off", C.POINTER(C.c_int64)), ("marker", C.POINTER(C.c_int32)),
         ("hmm_instances", C.c_int64), ("hmm_cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ms_total", C.c_float), ("ms_hmm", C.c_float), ("ms_stage", C.c_float * 8), ("gpu_launches", C.c_int32),
+        ("baq_qual", C.POINTER(C.c_uint8)), ("baq_qual_bytes", C.c_int64),
     ]
 
 
@@ -99,6 +100,8 @@ def load_library(path=None):
     L.sp_host_free.argtypes = [C.c_void_p]
     L.sp_sm_partition.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.sp_sm_partition.restype = C.c_int
+    L.sp_set_write_qual.argtypes = [C.c_void_p, C.c_int]
+    L.sp_set_write_qual.restype = C.c_int
     L.sp_rng_seed.argtypes = [C.c_void_p, C.c_uint]
     L.sp_rng_next.argtypes = [C.c_void_p]
     L.sp_rng_next.restype = C.c_int
@@ -109,7 +112,7 @@ def load_library(path=None):
 EXPORTED_SYMBOLS = [
     "sp_params_default", "sp_params_preset", "sp_create", "sp_destroy", "sp_last_error", "sp_version",
     "sp_set_reference_ascii", "sp_set_reference_codes", "sp_submit", "sp_wait", "sp_poll", "sp_sm_partition", "sp_mark", "sp_elapsed_since_mark", "sp_upload", "sp_run_resident",
-    "sp_debug_table", "sp_hmm_batch", "sp_fp64_peak", "sp_rng_seed", "sp_rng_next", "sp_host_alloc", "sp_host_free",
+    "sp_set_write_qual", "sp_debug_table", "sp_hmm_batch", "sp_fp64_peak", "sp_rng_seed", "sp_rng_next", "sp_host_alloc", "sp_host_free",
 ]
 
 
@@ -262,12 +265,19 @@ class Secphase:
             out["markers_final_off"] = _take(r.marker_off, r.n_groups + 1, 1, np.int64)
             nm = int(out["markers_final_off"][-1]) if r.n_groups >= 0 else 0
             out["markers_final"] = _take(r.marker, nm, MARKER_W, np.int32)
+            if r.baq_qual:
+                out["baq_qual"] = _take(r.baq_qual, r.baq_qual_bytes, 1, np.uint8)
         return out
 
     def run(self, batch, slot=0):
         """Score every read group of `batch`; blocking convenience wrapper."""
         self.submit(batch, slot)
         return self.wait(slot)
+
+    def set_write_qual(self, on=True):
+        """-w/--writeBam mode (secphase.c:182-189): wait() then also returns `baq_qual`, the records'
+        quality arrays after calc_update_baq_all, laid out like the batch's qual_pool."""
+        self._ck(self._L.sp_set_write_qual(self._h, 1 if on else 0))
 
     def enable_debug_tables(self):
         self._L.sp_debug_table(self._h, 0, -1, None, None)

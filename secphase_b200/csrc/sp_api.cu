@@ -108,9 +108,11 @@ struct Slot {
     bool safe_caps = false;
     // device work tables
     DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, item_off, row_off, sdbl_off, score,
-        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter;
+        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out;
     // host results
-    PinBuf h_tot, h_gout, h_score, h_info, h_fin;
+    PinBuf h_tot, h_gout, h_score, h_info, h_fin, h_qual;
+    size_t qual_bytes = 0;  // size of the batch's quality pool (== of qual_out in full_baq mode)
+    bool full_baq = false;  // this batch was planned with SpConst::full_baq set
     SpBatchPtrs P;
     SpTotals tot;     // after the mid-pipeline read-back
     int state = 0;    // 0 idle, 1 uploaded, 2 in flight, 3 done
@@ -144,6 +146,7 @@ struct sp_ctx {
     Slot slot[SP_N_SLOTS];
     SpRng rng;
     bool debug_tables = false;
+    bool full_baq = false;  // sp_set_write_qual: --writeBam mode
     int sm_count = 0;
     size_t max_smem = 0;
     cudaEvent_t mark = nullptr;  // sp_mark / sp_elapsed_since_mark
@@ -394,9 +397,9 @@ void sp_destroy(sp_ctx *c) {
         DevBuf *bufs[] = {&S.d_in, &S.ops, &S.imk, &S.info, &S.blk, &S.iv, &S.nb, &S.gpos, &S.ent, &S.res, &S.baq,
                           &S.gP, &S.gout, &S.gcnt, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
                           &S.fin, &S.items, &S.rows, &S.order, &S.bins, &S.class_start, &S.s_pool, &S.fsave,
-                          &S.gband, &S.totals, &S.work_counter};
+                          &S.gband, &S.totals, &S.work_counter, &S.qual_out};
         for (DevBuf *b : bufs) b->release();
-        PinBuf *pins[] = {&S.h_in, &S.h_tot, &S.h_gout, &S.h_score, &S.h_info, &S.h_fin};
+        PinBuf *pins[] = {&S.h_in, &S.h_tot, &S.h_gout, &S.h_score, &S.h_info, &S.h_fin, &S.h_qual};
         for (PinBuf *b : pins) b->release();
         for (int k = 0; k < EV_N; k++)
             if (S.ev[k]) cudaEventDestroy(S.ev[k]);
@@ -577,6 +580,12 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
     pool(L.qual_pool, b->qual_pool);
     S.tag_pad_off = L.tag_pool.off + L.tag_pool.bytes;
     S.in_bytes = L.total;
+    S.qual_bytes = L.qual_pool.bytes;
+    S.full_baq = c->full_baq;
+    if (S.full_baq) {
+        if ((rc = S.qual_out.ensure(S.qual_bytes + 16))) return rc;
+        if ((rc = S.h_qual.ensure(S.qual_bytes + 16))) return rc;
+    }
 
     // device work tables
     const bool dbg = c->debug_tables;
@@ -770,6 +779,21 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
             return rc;
     }
     CK(cudaEventRecord(S.ev[EV_HMM], st));
+    if (S.full_baq && S.qual_bytes > 0) {
+        // --writeBam: the records' quality arrays as calc_update_baq_all leaves them (ptMarker.c:786,
+        // 709-720, 797-806): raw qualities, then every row of every HMM window, then the zeroed markers
+        uint8_t *qo = S.qual_out.as<uint8_t>();
+        CK(cudaMemcpyAsync(qo, P.qual_pool, S.qual_bytes, cudaMemcpyDeviceToDevice, st));
+        if (T.n_rows > 0) {
+            k_baq_rows<<<(T.n_rows + 255) / 256, 256, 0, st>>>(dC, S.items.as<SpItem>(), S.rows.as<SpRow>(), T.n_rows,
+                                                             P.qual_off, P.qual_pool, qo);
+            S.launches++;
+        }
+        if (P.G > 0 && T.n_items > 0) {
+            k_baq_zero<<<(P.G + 63) / 64, 64, 0, st>>>(P, qo);
+            S.launches++;
+        }
+    }
     if (P.G > 0) {
         k_score<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC, S.rows.as<SpRow>(), c->par.prim_margin_score,
                                                 (double) c->par.min_score, S.totals.as<SpTotals>());
@@ -842,6 +866,10 @@ static int enqueue_results(Slot &S) {
     CK(cudaMemcpyAsync(S.h_score.p, S.score.p, 8 * A, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(S.h_info.p, S.info.p, sizeof(SpAlnInfo) * A, cudaMemcpyDeviceToHost, st));
     S.d2h_bytes = (int64_t) (sizeof(SpTotals) + sizeof(SpGroupOut) * G + 8 * A + sizeof(SpAlnInfo) * A);
+    if (S.full_baq && S.qual_bytes > 0) {
+        CK(cudaMemcpyAsync(S.h_qual.p, S.qual_out.p, S.qual_bytes, cudaMemcpyDeviceToHost, st));
+        S.d2h_bytes += (int64_t) S.qual_bytes;
+    }
     return SP_OK;
 }
 
@@ -907,6 +935,21 @@ int sp_run_resident(sp_ctx *c, int slot) {
     if (rc) return rc;
     S.state = 2;
     hand_to_launcher(c, slot);
+    return SP_OK;
+}
+
+int sp_set_write_qual(sp_ctx *c, int on) {
+    if (!c) return SP_EINVAL;
+    for (int s = 0; s < SP_N_SLOTS; s++)
+        if (c->slot[s].state == 2) {
+            set_err("sp_set_write_qual: slot %d still has a batch in flight", s);
+            return SP_ESTATE;
+        }
+    CK(cudaSetDevice(c->device));
+    c->full_baq = on != 0;
+    c->hC.full_baq = on != 0;
+    CK(cudaMemcpy(c->dC.p, &c->hC, sizeof(SpConst), cudaMemcpyHostToDevice));
+    for (int s = 0; s < SP_N_SLOTS; s++) c->slot[s].state = c->slot[s].state == 1 ? 0 : c->slot[s].state;  // resident batches were planned for the other mode
     return SP_OK;
 }
 
@@ -1038,6 +1081,8 @@ int sp_wait(sp_ctx *c, int slot, sp_result *out) {
     out->h2d_bytes = S.h2d_bytes;
     out->d2h_bytes = S.d2h_bytes;
     out->gpu_launches = S.launches;
+    out->baq_qual = S.full_baq ? S.h_qual.as<uint8_t>() : nullptr;
+    out->baq_qual_bytes = S.full_baq ? (int64_t) S.qual_bytes : 0;
     float ms = 0;
     const int order[8] = {EV_START, EV_H2D, EV_WALK, EV_GROUP, EV_EMIT, EV_HMM, EV_SCORE, EV_END};
     for (int k = 0; k < 7; k++) {

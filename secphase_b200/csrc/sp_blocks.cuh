@@ -344,6 +344,27 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
             int n_rows = 0;
             // rows: this alignment's markers with base_idx in [sqs+10, sqe-11]; sqe-10 is written by the
             // HMM and then zeroed again (800-803), so it needs no row.
+            // full_baq (--writeBam): one row per base of the write-back range t in [10, l_query-10)
+            // (ptMarker.c:786), slot = first_row + t - 10; rows no M/=/X op visits keep
+            // expected == SP_INT_MIN, i.e. bq = set_q (763-764).
+            const bool full = C.full_baq != 0;
+            if (full) {
+                n_rows = l_query - 2 * SP_BLOCK_MARGIN;
+                if (n_rows < 0) n_rows = 0;
+                if (EMIT) {
+                    for (int t = 0; t < n_rows; t++) {
+                        SpRow r;
+                        r.item = item_idx;
+                        r.t = t + SP_BLOCK_MARGIN;
+                        r.entry = -1;
+                        r.expected = SP_INT_MIN;
+                        r.state = 0;
+                        r.q = 0;
+                        r.pmax = 0.0;
+                        rows[first_row + t] = r;
+                    }
+                }
+            }
             int jj = j;
             // the bq loop, ptMarker.c:767-785
             while (it_sqs <= blk.sqe || it_rfs <= blk.rfe) {
@@ -353,24 +374,36 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
                 y = y < 0 ? 0 : y;
                 if (sp_op_is_match(it_op)) {
                     const int len = sp_min(it_len, sp_min(it_sqe, blk.sqe) - sp_max(it_sqs, blk.sqs) + 1);
+                    if (full && EMIT) {
+                        const int t1 = sp_min(y + len, l_query - SP_BLOCK_MARGIN);
+                        for (int t = sp_max(y, SP_BLOCK_MARGIN); t < t1; t++)
+                            rows[first_row + t - SP_BLOCK_MARGIN].expected = x + (t - y);
+                    }
                     // markers with t in [y, y+len)
                     while (SP_MK_VALID(jj) && SP_MK_BASE(jj) - blk.sqs < y) jj += jstep;
                     while (SP_MK_VALID(jj) && SP_MK_BASE(jj) - blk.sqs < y + len) {
                         const int t = SP_MK_BASE(jj) - blk.sqs;
                         if (t >= SP_BLOCK_MARGIN && t < l_query - SP_BLOCK_MARGIN - 1) {
-                            if (EMIT) {
-                                SpRow r;
-                                r.item = item_idx;
-                                r.t = t;
-                                r.entry = (int32_t) (entry_base + (int64_t) jj * n + i);
-                                r.expected = x + (t - y);
-                                r.state = 0;
-                                r.q = 0;
-                                r.pmax = 0.0;
-                                rows[first_row + n_rows] = r;
-                                res[entry_base + (int64_t) jj * n + i] = first_row + n_rows;
+                            if (full) {
+                                if (EMIT) {
+                                    rows[first_row + t - SP_BLOCK_MARGIN].entry = (int32_t) (entry_base + (int64_t) jj * n + i);
+                                    res[entry_base + (int64_t) jj * n + i] = first_row + t - SP_BLOCK_MARGIN;
+                                }
+                            } else {
+                                if (EMIT) {
+                                    SpRow r;
+                                    r.item = item_idx;
+                                    r.t = t;
+                                    r.entry = (int32_t) (entry_base + (int64_t) jj * n + i);
+                                    r.expected = x + (t - y);
+                                    r.state = 0;
+                                    r.q = 0;
+                                    r.pmax = 0.0;
+                                    rows[first_row + n_rows] = r;
+                                    res[entry_base + (int64_t) jj * n + i] = first_row + n_rows;
+                                }
+                                n_rows++;
                             }
-                            n_rows++;
                         }
                         jj += jstep;
                     }

@@ -79,6 +79,9 @@ struct SpRow {  // one query row whose MAP state/q is consumed (a marker inside 
 // Scalars every kernel needs.
 struct SpConst {
     int32_t baq_flag, consensus, indel_threshold, min_q, set_q, flank_margin;
+    // --writeBam (secphase.c:182-189): the MAP state/q of EVERY row of the write-back range
+    // [10, l_query-10) of each HMM window is needed, not just the marker rows (ptMarker.c:763-786)
+    int32_t full_baq, pad0;
     double conf_b;
     // HMM constants derived on the host exactly as C evaluates them (float sub-expressions kept)
     double m0f;      // (double)(1 - d - d)   evaluated in float

@@ -392,6 +392,26 @@ __global__ void __launch_bounds__(64) k_score(SpBatchPtrs B, const SpConst *__re
     B.gout[g] = o;
 }
 
+// ---- --writeBam: BAQ-modified quality arrays (full_baq mode) --------------------------------
+// thread per HMM row: fully parallel, one byte read + one byte written per base of every window
+__global__ void __launch_bounds__(256) k_baq_rows(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
+                                                  const SpRow *__restrict__ rows, int n_rows,
+                                                  const int64_t *__restrict__ qual_off,
+                                                  const uint8_t *__restrict__ qual_pool, uint8_t *__restrict__ qual_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const SpRow R = rows[r];
+    const SpItem it = items[R.item];
+    const int64_t p = qual_off[it.aln] + it.q_sqs + R.t;
+    qual_out[p] = sp_baq_row_qual(*Cp, R, qual_pool[p]);
+}
+__global__ void __launch_bounds__(64) k_baq_zero(SpBatchPtrs B, uint8_t *qual_out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B.G) return;
+    SpGroupAlnView V = sp_make_view(B, g);
+    sp_baq_zero_group(V, B.gP[g], B.ent + B.gent_off[g], B.res + B.gent_off[g], qual_out);
+}
+
 // ---- reference encoding: ASCII -> codes 0..4 (seq_nt16_int[seq_nt16_table[c]], ptMarker.c:744)
 __global__ void k_encode_ref(const uint8_t *__restrict__ ascii, uint8_t *__restrict__ codes, int64_t n) {
     int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;

@@ -32,13 +32,35 @@ SP_HD int sp_resolve_q(const SpConst &C, const SpEntry &e, int res, const SpRow 
     if (res == SP_RES_ZERO) return 0;
     int bq;
     if (res == SP_RES_SETQ) {
-        bq = C.set_q;
+        bq = C.set_q & 255;  // uint8_t block_qual[] = set_q (ptMarker.c:747-748)
     } else {
         const SpRow r = rows[res];
         if (((r.state & 3) != 0) || ((r.state >> 2) != r.expected)) bq = 0;
         else bq = e.q < r.q ? e.q : r.q;
     }
     return bq < 94 ? bq : 93;
+}
+
+// --writeBam (secphase.c:182-189 writes the records after calc_update_baq_all has modified their
+// qualities in place).  One row of the write-back range of an HMM window, ptMarker.c:763-786:
+// qual[sqs+t] = min(bq[t], 93) with bq[t] = set_q where no M/=/X op visited the base, 0 where the
+// MAP state disagrees with the alignment, else min(raw quality, q[t]).
+SP_HD uint8_t sp_baq_row_qual(const SpConst &C, const SpRow &r, int raw_q) {
+    int bq;
+    if (r.expected == SP_INT_MIN) bq = C.set_q & 255;
+    else if (((r.state & 3) != 0) || ((r.state >> 2) != r.expected)) bq = 0;
+    else bq = raw_q < r.q ? raw_q : r.q;
+    return (uint8_t) (bq < 94 ? bq : 93);
+}
+// The markers calc_local_baq zeroes next to block edges (ptMarker.c:709-720, 797-806); runs after the
+// rows above (the trailing margin is zeroed after the block's write-back, 786 vs 797).
+SP_HD void sp_baq_zero_group(const SpGroupAlnView &G, int P, const SpEntry *entries, const int32_t *res,
+                             uint8_t *qual_out) {
+    const int n = G.n;
+    for (int p = 0; p < P; p++)
+        for (int i = 0; i < n; i++)
+            if (res[(int64_t) p * n + i] == SP_RES_ZERO)
+                qual_out[G.qual_off[G.a0 + i] + entries[(int64_t) p * n + i].base_idx] = 0;
 }
 
 // Writes the final list to fin[] as SP_MARKER_W-wide rows and returns the number of rows.

@@ -33,6 +33,7 @@ struct HsOut {
     std::vector<int64_t> block_off;
     std::vector<int32_t> items;  // [.][SP_HMM_W]
     std::vector<int32_t> rows;   // [.][4] item, t, state, q
+    std::vector<uint8_t> qual;   // full_baq mode: quality pool after the write-back (k_baq_rows, k_baq_zero)
     int64_t cells = 0;
     int32_t err = 0;
 };
@@ -73,6 +74,7 @@ HS_GET(hs_blocks, blocks, int32_t)
 HS_GET(hs_block_off, block_off, int64_t)
 HS_GET(hs_items, items, int32_t)
 HS_GET(hs_rows, rows, int32_t)
+HS_GET(hs_qual, qual, uint8_t)
 const int32_t *hs_markers(const HsOut *o, int st, int64_t *n) { *n = (int64_t) o->mk[st].size(); return o->mk[st].data(); }
 const int64_t *hs_marker_off(const HsOut *o, int st, int64_t *n) { *n = (int64_t) o->mk_off[st].size(); return o->mk_off[st].data(); }
 int64_t hs_cells(const HsOut *o) { return o->cells; }
@@ -178,11 +180,19 @@ int hs_walk_stats(const sp_flat_batch *b, const sp_params *p, int32_t *out /* [A
 }
 
 // Whole marker path for a batch; ref_codes: concatenated contigs (codes 0..4), contig_off[n+1].
+int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
+            int n_contigs, int safe_caps, unsigned rng_seed, int full_baq, HsOut *out);
 int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
            int n_contigs, int safe_caps, unsigned rng_seed, HsOut *out) {
+    return hs_run2(b, p, ref_codes, contig_off, n_contigs, safe_caps, rng_seed, 0, out);
+}
+// full_baq != 0: the --writeBam mode of sp_set_write_qual (rows for every base of the write-back range)
+int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
+            int n_contigs, int safe_caps, unsigned rng_seed, int full_baq, HsOut *out) {
     (void) n_contigs;
     SpConst C;
     sp_fill_const(*p, C);
+    C.full_baq = full_baq != 0;
     SpPlan pl;
     int rc = sp_make_plan(b, p->indel_threshold, safe_caps != 0, pl);
     if (rc != SP_OK) return rc;
@@ -349,6 +359,18 @@ int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes,
     for (int r = 0; r < row_off[G]; r++) {
         int32_t rr[4] = {rows[r].item, rows[r].t, rows[r].state, rows[r].q};
         out->rows.insert(out->rows.end(), rr, rr + 4);
+    }
+    if (full_baq) {  // run_phase_b: D2D copy of the raw pool, k_baq_rows, k_baq_zero
+        out->qual.assign(b->qual_pool, b->qual_pool + b->qual_off[A]);
+        for (int r = 0; r < row_off[G]; r++) {
+            const SpItem &I = items[rows[r].item];
+            const int64_t q = b->qual_off[I.aln] + I.q_sqs + rows[r].t;
+            out->qual[(size_t) q] = sp_baq_row_qual(C, rows[r], b->qual_pool[q]);
+        }
+        for (int g = 0; g < G; g++) {
+            SpGroupAlnView V = view(g);
+            sp_baq_zero_group(V, gP[g], ent.data() + pl.gent_off[g], res.data() + pl.gent_off[g], out->qual.data());
+        }
     }
     // K5 + host finalisation
     SpRng rng;

@@ -44,6 +44,11 @@ def lib():
         L.hs_run.argtypes = [C.POINTER(CFlatBatch), C.POINTER(SpParams), C.c_void_p, C.c_void_p, C.c_int,
                              C.c_int, C.c_uint, C.c_void_p]
         L.hs_run.restype = C.c_int
+        L.hs_run2.argtypes = [C.POINTER(CFlatBatch), C.POINTER(SpParams), C.c_void_p, C.c_void_p, C.c_int,
+                              C.c_int, C.c_uint, C.c_int, C.c_void_p]
+        L.hs_run2.restype = C.c_int
+        L.hs_qual.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.hs_qual.restype = C.POINTER(C.c_uint8)
         for name, rt in [("group", C.c_int32), ("score", C.c_double), ("extent", C.c_int32),
                          ("blocks", C.c_int32), ("block_off", C.c_int64), ("items", C.c_int32), ("rows", C.c_int32)]:
             f = getattr(L, "hs_" + name)
@@ -83,15 +88,15 @@ def params_from_oracle(op):
     return SpParams(**{k: getattr(op, k) for k, _ in SpParams._fields_})
 
 
-def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1):
+def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1, full_baq=False):
     L = lib()
     out = L.hs_out_create()
     try:
         cb = batch.as_c()
         ref_codes = np.ascontiguousarray(ref_codes, np.uint8)
         contig_off = np.ascontiguousarray(contig_off, np.int64)
-        rc = L.hs_run(C.byref(cb), C.byref(params), ref_codes.ctypes.data, contig_off.ctypes.data,
-                      len(contig_off) - 1, 1 if safe_caps else 0, seed, out)
+        rc = L.hs_run2(C.byref(cb), C.byref(params), ref_codes.ctypes.data, contig_off.ctypes.data,
+                       len(contig_off) - 1, 1 if safe_caps else 0, seed, 1 if full_baq else 0, out)
         if rc != 0:
             raise RuntimeError(f"hs_run failed: {rc}")
         n = C.c_int64()
@@ -106,6 +111,8 @@ def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1):
         for st, nm in enumerate(("markers_pre", "markers_baq", "markers_final")):
             r[nm] = _take(L.hs_markers(out, st, C.byref(n)), n.value, 6, np.int32)
             r[nm + "_off"] = _take(L.hs_marker_off(out, st, C.byref(n)), n.value, 1, np.int64)
+        if full_baq:
+            r["qual"] = _take(L.hs_qual(out, C.byref(n)), n.value, 1, np.uint8)
         r["cells"] = int(L.hs_cells(out))
         r["err"] = int(L.hs_err(out))
         return r

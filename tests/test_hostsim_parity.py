@@ -26,6 +26,34 @@ def test_stage_logic_bit_exact_vs_oracle(hostsim, oracle, name, spreset, ppreset
     assert len(got["items"]) == len(exp["hmm"])
 
 
+@pytest.mark.parametrize("name,spreset,ppreset,ng,over", CASES, ids=[c[0] for c in CASES])
+def test_write_qual_mode_bit_exact_vs_oracle(hostsim, oracle, name, spreset, ppreset, ng, over):
+    """-w/--writeBam mode (SpConst::full_baq): every record's quality array as calc_update_baq_all leaves
+    it (ptMarker.c:786, 709-720, 797-806) equals the reference's records byte for byte, and nothing else
+    the job returns changes with the mode."""
+    s, b, codes, off = make_case(spreset, ng, **over)
+    op = oracle.preset_params(ppreset)
+    exp = oracle.run(b, op, oracle_refseq(oracle, s))
+    got = hostsim.run(b, hostsim.params_from_oracle(op), codes, off, full_baq=True)
+    assert got["err"] == 0
+    bad = compare_results(exp, got, label="hostsim-full")
+    assert not bad, "\n".join(bad)
+    assert exp["qual"].shape == got["qual"].shape == b.qual_pool.shape
+    diff = np.flatnonzero(exp["qual"] != got["qual"])
+    assert diff.size == 0, f"{diff.size} quality bytes differ, first at {diff[:5]}: oracle={exp['qual'][diff[:5]]} got={got['qual'][diff[:5]]}"
+    # the mode really rewrites qualities where an HMM ran
+    if len(exp["hmm"]):
+        assert (exp["qual"] != b.qual_pool).any()
+    # every marker's post-BAQ quality is the byte of its record (calc_update_baq_all, ptMarker.c:823-830)
+    mk, mo = got["markers_baq"], got["markers_baq_off"]
+    for g in range(b.n_groups):
+        a0 = int(b.grp_aln_off[g])
+        rows = mk[int(mo[g]):int(mo[g + 1])]
+        if got["groups"][g, 9] and len(rows):
+            pos = b.qual_off[a0 + rows[:, 0]] + rows[:, 2]
+            assert np.array_equal(got["qual"][pos].astype(np.int32), rows[:, 3])
+
+
 def test_glibc_rand_emulation(hostsim):
     import ctypes
     libc = ctypes.CDLL("libc.so.6")
