@@ -323,7 +323,19 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    alg_bytes = 0.05 * iso_cells  # ~0.05 B per cell compulsory traffic
+    # Algorithmic HBM bytes of one launch set: reference window + packed query in
+    # (~0.05 B/cell) plus the per-row scaling factors, which must survive from the
+    # forward to the backward sweep: 8 B out + 8 B back in per query row (~0.35 B/cell at 41 cells/row)
+    alg_bytes = 0.4 * iso_cells
+    # measured DRAM traffic of the same launch set from the committed ncu --set full capture,
+    # scaled by band cells to this run's batch
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_k_hmm2.json")))
+        traffic = tr["dram_bytes_total"] * iso_cells / tr["band_cells"]
+        traffic_src = tr["source"]
+    except Exception:
+        traffic_src = None
     line = {
         "metric": "read_groups_per_sec", "value": value, "unit": "read-groups/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
@@ -347,7 +359,8 @@ def main():
         "clocks": clocks,
         "roofline": {"kernel": "k_hmm2 (all band-class launches of one step, forked on aux streams)", "bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops,
                      "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops if peak_tflops else None,
-                     "traffic": None,
+                     "traffic": traffic, "traffic_unit": "bytes per launch set (dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
                      "peak_source": "measured live: register-resident DFMA kernel, 2 flop/instr (MEASURED_PEAKS.json has no FP64 entry)",
                      "issue_slot_frac": iso_cells * FLOP_PER_CELL / (hmm_ms * 1e-3) / dadd_ops if dadd_ops else None,
                      "dadd_dmul_ops_per_s": dadd_ops, "kernel_ms_per_step": hmm_ms,

@@ -64,6 +64,12 @@ const sp_flat_batch *sph_batch_view(const sph_batch *b);
 /* per alignment of the batch: 0-based record ordinal in the BAM (for diagnostics) */
 const int64_t *sph_batch_record_index(const sph_batch *b);
 
+/* -w/--writeBam support: when on, sph_bam_next_batch also keeps every alignment's whole BAM record
+ * body (the bytes after block_size: refID .. aux) so that the record can be written back out
+ * (secphase.c:182-189).  sph_batch_records returns the pool and its [n_alns+1] offsets. */
+void sph_batch_keep_records(sph_batch *b, int on);
+const uint8_t *sph_batch_records(const sph_batch *b, const int64_t **off);
+
 /* Fills `b` with the next eligible read groups in file order: at most max_groups groups and
  * about max_bytes pool bytes (a single group larger than max_bytes is still taken alone).
  * Eligibility as secphase.c:285-288,336-337: consecutive records of one query name, unmapped
@@ -125,6 +131,24 @@ int64_t sph_blocks_export(const sph_blocks *t, int32_t *rows4, int64_t max_rows)
 int64_t sph_format_marker_record(char *buf, int64_t cap, const char *qname, int32_t qname_len, int32_t n_alns,
                                  const int32_t *flag, const double *score, const char *const *contig,
                                  const int32_t *pos, const int32_t *rfe, int32_t best_idx);
+
+/* ------------------------------------------------------------------ -w/--writeBam output */
+/* One alignment line as htslib's sam_format1 prints it (the reference opens the output with
+ * sam_open(path, "w"), secphase.c:651 -- mode "w" without 'b' is SAM *text*, whatever the file is
+ * called): QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL [TAG:TYPE:VALUE...] '\n'.
+ * rec/rec_len = BAM record body (after block_size).  qual_override (l_seq bytes, raw Phred) replaces
+ * the record's own QUAL when not NULL.  Returns the line length, or the needed length if > cap;
+ * negative on a malformed record. */
+int64_t sph_format_sam_record(char *buf, int64_t cap, const uint8_t *rec, int64_t rec_len, int32_t n_targets,
+                              const char *const *target_names, const uint8_t *qual_override);
+/* <outDir>/<prefix>.quality_modified.out.bam of secphase.c:643-657: header text of the input
+ * (sam_hdr_write), then the records of every scored read group with the qualities
+ * calc_update_baq_all left (sp_result.baq_qual).  The batch must have been read with
+ * sph_batch_keep_records on. */
+typedef struct sph_samw sph_samw;
+sph_samw *sph_samw_open(const char *path, const sph_bam *header_from);
+int sph_samw_write_batch(sph_samw *w, const sph_batch *b, const uint8_t *baq_qual);
+int sph_samw_close(sph_samw *w); /* also frees w */
 
 #ifdef __cplusplus
 }

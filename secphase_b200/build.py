@@ -61,7 +61,7 @@ HOST = os.path.join(HERE, "host")
 HOST_LIB = os.path.join(LIBDIR, "libsecphase_host.so")
 BINDIR = os.path.join(os.path.dirname(HERE), "bin")
 CLI = os.path.join(BINDIR, "secphase")
-HOST_SRCS = ["sph_common.cpp", "sph_bgzf.cpp", "sph_bam.cpp", "sph_fasta.cpp", "sph_output.cpp"]
+HOST_SRCS = ["sph_common.cpp", "sph_bgzf.cpp", "sph_bam.cpp", "sph_fasta.cpp", "sph_output.cpp", "sph_sam.cpp"]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-pthread"]
 
 

@@ -10,8 +10,13 @@
 // out.log appear in input order (the reference's order with -@1; with more workers its order is
 // completion order).
 //
+// -w/--writeBam (secphase.c:182-189, 643-657): the device then evaluates the BAQ of every base of
+// every realigned window (sp_set_write_qual) and the records of all scored read groups are written
+// to <outDir>/<prefix>.quality_modified.out.bam with the modified qualities -- as SAM text, which
+// is what the reference's sam_open(path, "w") produces despite the file name (sph_sam.cpp).
+//
 // Not available in this build (out of the hot path's scope): -v/--inputVcf variant
-// mode and -w/--writeBam; both stop with a message instead of being silently ignored.
+// mode; it stops with a message instead of being silently ignored.
 //
 // Extra long options (not in the reference): --gpus N (default 1; read groups are dealt to the
 // devices batch by batch, results merged in input order, no collective), --batchGroups N,
@@ -118,7 +123,7 @@ void usage(const char *program) {  // secphase.c:563-599, plus the three extra o
             "         --minVariantMargin, -g         Minimum margin for creating blocks around phased variants [Default: 50]\n");
     fprintf(stderr, "         --minGQ, -G         Minimum genotype quality of the phased variants [Default: 10]\n");
     fprintf(stderr,
-            "         --writeBam, -w         Write an output bam file with the base qualities modified by BAQ (not available in the B200 build)\n");
+            "         --writeBam, -w         Write an output bam file with the base qualities modified by BAQ\n");
     fprintf(stderr, "         --flankMargin, -F         Margin around each marker for the BAQ windows [Default: 500]\n");
     fprintf(stderr, "         --threads, -@         Number of host threads for BAM decoding [Default: 4]\n");
     fprintf(stderr, "         --gpus         Number of GPUs to shard read groups over [Default: 1]\n");
@@ -181,6 +186,7 @@ struct Done {
     std::vector<int32_t> extent;  // [A][4]
     std::vector<int64_t> marker_off;
     std::vector<int32_t> marker;
+    std::vector<uint8_t> baq_qual;  // -w: the records' qualities after BAQ (sp_result.baq_qual)
     int64_t hmm_instances = 0, hmm_cells = 0;
     double gpu_ms = 0, hmm_ms = 0;
     int launches = 0;
@@ -313,10 +319,8 @@ int main(int argc, char *argv[]) {
                 get_timestamp());
         return 1;
     }
-    if (write_bam) {
-        fprintf(stderr, "[%s] Error: -w/--writeBam is not part of the B200 build.\n", get_timestamp());
-        return 1;
-    }
+    // full-BAQ mode keeps ~700 B of HBM per window row while a batch is in flight (include/secphase_b200.h)
+    if (write_bam && batch_groups > 512) batch_groups = 512;
     if (threads < 1) threads = 1;
     if (n_gpus < 1) n_gpus = 1;
     if (batch_groups < 1) batch_groups = 1;
@@ -411,6 +415,10 @@ int main(int argc, char *argv[]) {
             fprintf(stderr, "[%s] Error: cannot load the assembly on GPU %d: %s\n", get_timestamp(), d, sp_last_error());
             return 1;
         }
+        if (write_bam && sp_set_write_qual(ctx[(size_t) d], 1) != SP_OK) {
+            fprintf(stderr, "[%s] Error: GPU %d: %s\n", get_timestamp(), d, sp_last_error());
+            return 1;
+        }
     }
     if (fa) sph_fasta_free(fa);
     fa = nullptr;
@@ -433,8 +441,18 @@ int main(int argc, char *argv[]) {
     std::vector<sph_batch *> all_batches;
     for (int i = 0; i < n_batches; i++) {
         sph_batch *hb = sph_batch_create(sp_host_alloc, sp_host_free);
+        if (write_bam) sph_batch_keep_records(hb, 1);
         all_batches.push_back(hb);
         free_q.push(hb);
+    }
+    sph_samw *bam_fo = nullptr;  // secphase.c:643-657
+    if (write_bam) {
+        std::string p = dirPath + "/" + prefix + ".quality_modified.out.bam";
+        bam_fo = sph_samw_open(p.c_str(), bam);
+        if (!bam_fo) {
+            fprintf(stderr, "[%s] Error: %s\n", get_timestamp(), sph_last_error());
+            return 1;
+        }
     }
     fprintf(stderr, "[%s] Started parsing alignments\n", get_timestamp());
 
@@ -492,6 +510,7 @@ int main(int argc, char *argv[]) {
                 dn->extent.assign(r.extent, r.extent + (size_t) r.n_alns * 4);
                 dn->marker_off.assign(r.marker_off, r.marker_off + r.n_groups + 1);
                 dn->marker.assign(r.marker, r.marker + (size_t) r.marker_off[r.n_groups] * SP_MARKER_W);
+                if (r.baq_qual) dn->baq_qual.assign(r.baq_qual, r.baq_qual + r.baq_qual_bytes);
                 dn->hmm_instances = r.hmm_instances;
                 dn->hmm_cells = r.hmm_cells;
                 dn->gpu_ms = r.ms_total;
@@ -551,6 +570,11 @@ int main(int argc, char *argv[]) {
     auto emit = [&](Done *dn) {
         const sp_flat_batch *b = sph_batch_view(dn->hb);
         const int G = b->n_groups;
+        // secphase.c:182-189: every record of every job of the marker branch, qualities as BAQ left them
+        if (bam_fo && marker_mode && b->n_alns > 0) {
+            if (sph_samw_write_batch(bam_fo, dn->hb, dn->baq_qual.empty() ? nullptr : dn->baq_qual.data()) != SPH_OK)
+                shared.fail(std::string("writing the output bam: ") + sph_last_error());
+        }
         for (int g = 0; g < G; g++) {
             const int a0 = b->grp_aln_off[g], n = b->grp_aln_off[g + 1] - a0;
             const int32_t *row = &dn->group[(size_t) g * SP_GROUP_W];
@@ -621,6 +645,7 @@ int main(int argc, char *argv[]) {
     reader.join();
     for (auto &t : gpu_threads) t.join();
     for (auto &kv : parked) delete kv.second;
+    if (bam_fo && sph_samw_close(bam_fo) != SPH_OK) shared.fail("closing the output bam failed");
     if (shared.is_failed()) {
         fprintf(stderr, "[%s] Error: %s\n", get_timestamp(), shared.error.c_str());
         fclose(output_log_file);

@@ -59,6 +59,11 @@ struct sph_batch {
     std::vector<int64_t> qname_off, cigar_off, tag_off, seq_off, qual_off, rec_index;
     std::vector<char> qname_pool;
     sp_flat_batch view;
+    // -w/--writeBam: the whole BAM record bodies (everything after block_size), needed to write the
+    // records back out with modified qualities (secphase.c:182-189)
+    bool keep_records = false;
+    std::vector<uint8_t> rec_pool;
+    std::vector<int64_t> rec_off;
 
     // `scale` extrapolates from what is packed so far to the full batch (>= 1): page-locked
     // allocations are slow and cudaFreeHost synchronises the device, so a pool is sized once for
@@ -88,6 +93,8 @@ struct sph_batch {
         flag.clear(); tid.clear(); pos.clear(); l_qseq.clear(); n_cigar.clear(); tag_kind.clear();
         rec_index.clear();
         qname_pool.clear();
+        rec_pool.clear();
+        rec_off.assign(1, 0);
         refresh();
     }
     int64_t bytes() const { return (int64_t) (cigar.len + tag.len + seq.len + qual.len); }
@@ -183,6 +190,10 @@ int sph_bam::pack_pending(sph_batch *b) {
             b->flag.push_back(a.flag); b->tid.push_back(a.tid); b->pos.push_back(a.pos);
             b->l_qseq.push_back(a.l_qseq); b->n_cigar.push_back(a.n_cigar); b->tag_kind.push_back(a.tag_kind);
             b->rec_index.push_back(a.rec_index);
+            if (b->keep_records) {
+                b->rec_pool.insert(b->rec_pool.end(), a.rec, a.rec + a.body_len);
+                b->rec_off.push_back((int64_t) b->rec_pool.size());
+            }
             b->cigar_off.push_back((int64_t) (oc / 4));
             b->tag_off.push_back((int64_t) ot);
             b->seq_off.push_back((int64_t) os);
@@ -438,6 +449,11 @@ void sph_batch_destroy(sph_batch *b) {
 }
 const sp_flat_batch *sph_batch_view(const sph_batch *b) { return &b->view; }
 const int64_t *sph_batch_record_index(const sph_batch *b) { return b->rec_index.data(); }
+void sph_batch_keep_records(sph_batch *b, int on) { b->keep_records = on != 0; }
+const uint8_t *sph_batch_records(const sph_batch *b, const int64_t **off) {
+    if (off) *off = b->rec_off.data();
+    return b->rec_pool.data();
+}
 
 int sph_bam_set_contig_limits(sph_bam *r, const int64_t *len_by_tid) {
     if (!r || !len_by_tid) return SPH_EINVAL;

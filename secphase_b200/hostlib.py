@@ -88,6 +88,18 @@ def lib():
                                            C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_char_p),
                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]
     L.sph_format_marker_record.restype = C.c_int64
+    L.sph_batch_keep_records.argtypes = [C.c_void_p, C.c_int]
+    L.sph_batch_records.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int64))]
+    L.sph_batch_records.restype = C.POINTER(C.c_uint8)
+    L.sph_bam_header_text.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.sph_bam_header_text.restype = C.c_void_p
+    L.sph_format_sam_record.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                        C.POINTER(C.c_char_p), C.c_void_p]
+    L.sph_format_sam_record.restype = C.c_int64
+    L.sph_samw_open.argtypes = [C.c_char_p, C.c_void_p]
+    L.sph_samw_open.restype = C.c_void_p
+    L.sph_samw_write_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sph_samw_close.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -143,11 +155,14 @@ def write_fasta(path, names, seq_ptrs, lens, line_width=60):
 class BamReader:
     """Iterates the eligible read groups of a BAM as FlatBatch objects (numpy copies)."""
 
-    def __init__(self, path, threads=4):
+    def __init__(self, path, threads=4, keep_records=False):
         self._h = lib().sph_bam_open(os.fsencode(path), threads)
         if not self._h:
             raise HostError(_err())
         self._b = lib().sph_batch_create(None, None)
+        self.keep_records = keep_records
+        if keep_records:  # -w/--writeBam: whole record bodies travel with the batch
+            lib().sph_batch_keep_records(self._b, 1)
         n = lib().sph_bam_n_targets(self._h)
         self.names = [lib().sph_bam_target_name(self._h, i).decode() for i in range(n)]
         self.lens = [int(lib().sph_bam_target_len(self._h, i)) for i in range(n)]
@@ -166,7 +181,18 @@ class BamReader:
         fb = FlatBatch.from_c(lib().sph_batch_view(self._b).contents)
         ri = lib().sph_batch_record_index(self._b)
         fb.record_index = np.ctypeslib.as_array(ri, shape=(fb.n_alns,)).copy()
+        if self.keep_records:
+            off = C.POINTER(C.c_int64)()
+            pool = lib().sph_batch_records(self._b, C.byref(off))
+            fb.rec_off = np.ctypeslib.as_array(off, shape=(fb.n_alns + 1,)).copy()
+            fb.rec_pool = np.ctypeslib.as_array(pool, shape=(max(int(fb.rec_off[-1]), 1),))[:int(fb.rec_off[-1])].copy()
         return fb
+
+    def header_text(self):
+        n = C.c_int64()
+        p = lib().sph_bam_header_text(self._h, C.byref(n))
+        return C.string_at(p, n.value).decode() if p and n.value else ""
+
 
     def __iter__(self):
         while True:
@@ -268,3 +294,40 @@ def format_marker_record(qname, flags, scores, contigs, pos, rfe, best_idx):
     buf = C.create_string_buffer(need + 1)
     lib().sph_format_marker_record(buf, need, q, len(q), n, cf, cs, cc, cp, ce, best_idx)
     return buf.raw[:need].decode()
+
+
+def format_sam_record(rec, names, qual=None):
+    """One SAM text line (htslib sam_format1) of a BAM record body; qual (uint8 Phred) overrides QUAL."""
+    rec = np.ascontiguousarray(np.frombuffer(bytes(rec), np.uint8))
+    n = len(names)
+    cn = (C.c_char_p * max(n, 1))(*[x.encode() for x in names])
+    q = None if qual is None else np.ascontiguousarray(qual, np.uint8)
+    qp = None if q is None else q.ctypes.data
+    need = lib().sph_format_sam_record(None, 0, rec.ctypes.data, len(rec), n, cn, qp)
+    if need < 0:
+        raise HostError(_err())
+    buf = C.create_string_buffer(need + 1)
+    lib().sph_format_sam_record(buf, need, rec.ctypes.data, len(rec), n, cn, qp)
+    return buf.raw[:need].decode()
+
+
+class SamWriter:
+    """<prefix>.quality_modified.out.bam of secphase.c:643-657 (SAM text, see sph_sam.cpp)."""
+
+    def __init__(self, path, reader):
+        self._w = lib().sph_samw_open(os.fsencode(path), reader._h)
+        if not self._w:
+            raise HostError(_err())
+
+    def write_current_batch(self, reader, baq_qual=None):
+        """Writes the records of the batch `reader.next_batch()` returned last (keep_records=True)."""
+        q = None if baq_qual is None else np.ascontiguousarray(baq_qual, np.uint8)
+        if lib().sph_samw_write_batch(self._w, reader._b, None if q is None else q.ctypes.data) != 0:
+            raise HostError(_err())
+
+    def close(self):
+        if self._w:
+            rc = lib().sph_samw_close(self._w)
+            self._w = None
+            if rc != 0:
+                raise HostError("closing the SAM output failed")

@@ -48,8 +48,6 @@ def test_out_of_scope_modes_say_so(small_inputs):
     d, _, _, bam, fa = small_inputs
     r = run_cli(["-i", bam, "-f", fa, "-v", "x.vcf", "-o", str(d / "o2")])
     assert r.returncode == 1 and "variant mode" in r.stderr
-    r = run_cli(["-i", bam, "-f", fa, "-w", "-o", str(d / "o3")])
-    assert r.returncode == 1 and "writeBam" in r.stderr
 
 
 def test_missing_inputs(small_inputs):
@@ -153,3 +151,41 @@ def test_cli_two_gpus_same_output(tmp_path, oracle):
         assert r.returncode == 0, r.stderr
         outs.append([(d / f"secphase.{f}").read_bytes() for f in OUT_FILES])
     assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,flags,n_groups,over", [
+    ("hifi", ["--hifi"], 120, dict(locus_len=300000)),
+    ("ont", ["--ont"], 30, dict(locus_len=300000, clip_prob=0.8, hard_clip_prob=0.5)),
+])
+def test_cli_write_bam(tmp_path, oracle, preset, flags, n_groups, over):
+    """-w/--writeBam (secphase.c:182-189, 643-657): <prefix>.quality_modified.out.bam holds the input
+    header and every record of every scored read group with the qualities the reference's own
+    calc_update_baq_all leaves in the records; the other outputs do not change with -w."""
+    if "reference" not in oracle.available_kinds():
+        pytest.skip("oracle/_ref not built")
+    from tests.test_host_sam import py_sam_line
+    s, b, _, _ = make_case(preset, n_groups, **over)
+    bam, fa = str(tmp_path / "in.bam"), str(tmp_path / "asm.fa")
+    hostlib.write_bam(bam, s.names, s.lens, b)
+    hostlib.write_fasta(fa, s.names, [s.contig_ptr(i) for i in range(s.n_contigs)], s.lens)
+    exp_dir = tmp_path / "exp"
+    exp_dir.mkdir()
+    exp = oracle.run(b, oracle.preset_params(preset), oracle_refseq(oracle, s), kind="reference",
+                     outputs=(str(exp_dir), "ref"))
+    want = []
+    for g in range(b.n_groups):
+        for a in range(int(b.grp_aln_off[g]), int(b.grp_aln_off[g + 1])):
+            q = exp["qual"][int(b.qual_off[a]):int(b.qual_off[a + 1])]
+            want.append(py_sam_line(b, g, a, s.names, qual=q))
+    assert (exp["qual"] != b.qual_pool).any()
+    for variant, extra in (("one_batch", []), ("many_batches", ["--batchGroups", "7", "-@", "2"])):
+        out_dir = tmp_path / f"got_{variant}"
+        r = run_cli(["-i", bam, "-f", fa, "-o", str(out_dir), "-P", "t", "-w"] + flags + extra)
+        assert r.returncode == 0, r.stderr
+        lines = (out_dir / "t.quality_modified.out.bam").read_text().splitlines(keepends=True)
+        head = [ln for ln in lines if ln.startswith("@")]
+        assert [ln.split("\t")[1] for ln in head if ln.startswith("@SQ")] == [f"SN:{n}" for n in s.names]
+        assert lines[len(head):] == want, variant
+        for f in OUT_FILES:
+            assert (out_dir / f"t.{f}").read_bytes() == (exp_dir / f"ref.{f}").read_bytes(), (variant, f)

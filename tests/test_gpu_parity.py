@@ -30,6 +30,39 @@ def test_pipeline_bit_exact_vs_oracle(sp, oracle, name, spreset, ppreset, ng, ov
     assert got["gpu_launches"] >= 5
 
 
+@pytest.mark.parametrize("name,spreset,ppreset,ng,over", CASES, ids=[c[0] for c in CASES])
+def test_write_qual_mode_bit_exact_vs_oracle(sp, oracle, name, spreset, ppreset, ng, over):
+    """-w/--writeBam mode (sp_set_write_qual): the quality array of every record as the reference's
+    calc_update_baq_all leaves it (what sam_write1 emits, secphase.c:182-189), byte for byte; scores,
+    markers and selection are unchanged by the mode; switching the mode off again restores the
+    marker-rows-only path on the same context."""
+    s, b, codes, off = make_case(spreset, ng, **over)
+    ref = oracle_refseq(oracle, s)
+    exp = oracle.run(b, oracle.preset_params(ppreset), ref, keep_hmm=False)
+    with sp.Secphase(ppreset) as eng:
+        eng.set_reference_codes(codes, off)
+        eng.set_write_qual(True)
+        got = eng.run_debug(b)
+        bad = compare_results(exp, got, label="cuda-full")
+        assert not bad, "\n".join(bad)
+        assert got["baq_qual"].shape == exp["qual"].shape == b.qual_pool.shape
+        diff = np.flatnonzero(exp["qual"] != got["baq_qual"])
+        assert diff.size == 0, f"{diff.size} quality bytes differ, first at {diff[:5]}"
+        if len(exp["hmm"]):
+            assert (got["baq_qual"] != b.qual_pool).any()
+            # one HMM row per base of each window's write-back range [10, l_query-10)
+            assert len(got["rows"]) == int((exp["hmm"][:, 2] - 20).sum())
+        assert got["hmm_instances"] == len(exp["hmm"])
+        # through a second slot and with the pools in page-locked memory
+        got2 = eng.run(sp.pin_batch(b), slot=1)
+        assert np.array_equal(got2["baq_qual"], exp["qual"])
+        eng.set_write_qual(False)
+        got3 = eng.run_debug(b)
+        assert "baq_qual" not in got3
+        assert not compare_results(exp, got3, label="cuda-after-full")
+        assert len(got3["rows"]) < len(got["rows"]) or len(exp["hmm"]) == 0
+
+
 def test_reference_ascii_upload_matches_codes(sp, oracle):
     s, b, codes, off = make_case("hifi", 30, locus_len=200000, n_rate=1e-3)
     with sp.Secphase("hifi") as e1, sp.Secphase("hifi") as e2:

@@ -54,17 +54,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--extra", action="append", default=[], help="extra CLI flag (repeatable), e.g. --extra=-w")
     args = ap.parse_args()
     work = tempfile.mkdtemp(prefix="sp_cli_bench_")
     try:
         t0 = time.perf_counter()
         bam, fa = make_inputs(work, args.preset, args.groups, args.locus_len, threads=args.threads)
         gen_s = time.perf_counter() - t0
-        runs = [run_cli(bam, fa, os.path.join(work, f"out{i}"), args.preset, args.threads, args.gpus)
+        runs = [run_cli(bam, fa, os.path.join(work, f"out{i}"), args.preset, args.threads, args.gpus, extra=args.extra)
                 for i in range(args.repeat)]
         best = min(runs, key=lambda x: x["score_s"])
         print(json.dumps({
-            "preset": args.preset, "groups": best["read_groups"], "bam_bytes": os.path.getsize(bam),
+            "preset": args.preset, "extra": args.extra, "groups": best["read_groups"], "bam_bytes": os.path.getsize(bam),
             "host_threads": args.threads, "gpus": args.gpus, "generate_s": round(gen_s, 2),
             "setup_s": best["setup_s"], "score_s": best["score_s"], "total_s": best["total_s"],
             "groups_per_s_scoring": best["read_groups"] / best["score_s"],

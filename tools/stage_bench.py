@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--groups", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--locus-len", type=int, default=20_000_000)
+    ap.add_argument("--write-qual", action="store_true", help="-w/--writeBam mode: BAQ of every window base")
     args = ap.parse_args()
     import secphase_b200
     from tools.parity import encode_reference
@@ -31,6 +32,8 @@ def main():
     ppreset = "ont" if args.preset == "ont" else "hifi"
     with secphase_b200.Secphase(ppreset) as eng:
         eng.set_reference_codes(codes, off)
+        if args.write_qual:
+            eng.set_write_qual(True)
         eng.upload(batch, 0)
         st = []
         for i in range(args.iters + 2):
@@ -40,7 +43,7 @@ def main():
                 st.append(r)
         ms = np.mean([x["ms_stage"] for x in st], axis=0)
         cells = st[0]["hmm_cells"]
-        out = {"preset": args.preset, "groups": args.groups, "hmm_instances": st[0]["hmm_instances"], "cells": cells,
+        out = {"preset": args.preset, "write_qual": bool(args.write_qual), "groups": args.groups, "hmm_instances": st[0]["hmm_instances"], "cells": cells,
                "stage_ms": dict(zip(["h2d", "walk", "group", "emit_sort", "hmm", "score", "d2h"], [round(float(x), 3) for x in ms[:7]])),
                "hmm_gcups": cells / (ms[4] * 1e-3) / 1e9, "total_ms": float(np.mean([x["ms_total"] for x in st])),
                "groups_per_s_serial": args.groups / (float(np.mean([x["ms_total"] for x in st])) * 1e-3)}
