@@ -371,7 +371,7 @@ def main():
         "stage_ms_isolated": dict(zip(["h2d", "walk", "group", "emit_sort", "hmm", "score", "d2h"], stage_ms[:7])),
         "setup_s": setup_s,
     }
-    if rank == 0 and not args.no_cpu_baseline and world >= 1:
+    if rank == 0 and not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N=1 leg only
         threads = os.cpu_count() or 1
         # bounded sample: whole batches of the same workload until ~12 s of CPU work are done
         n_cpu = args.cpu_sample or min(args.groups, 1024 * threads)

@@ -61,6 +61,7 @@ HOST = os.path.join(HERE, "host")
 HOST_LIB = os.path.join(LIBDIR, "libsecphase_host.so")
 BINDIR = os.path.join(os.path.dirname(HERE), "bin")
 CLI = os.path.join(BINDIR, "secphase")
+CORRECT_BAM = os.path.join(BINDIR, "correct_bam")  # consumer of out.log (programs/src/correct_bam.c)
 HOST_SRCS = ["sph_common.cpp", "sph_bgzf.cpp", "sph_bam.cpp", "sph_fasta.cpp", "sph_output.cpp", "sph_sam.cpp"]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-pthread"]
 
@@ -83,6 +84,10 @@ def build_host(force=False):
     main = os.path.join(HOST, "secphase_main.cpp")
     if force or _stale(CLI, [main, HOST_LIB, LIB] + inc):
         subprocess.check_call([cxx] + CXX_FLAGS + ["-o", CLI, main, "-L" + LIBDIR, "-lsecphase_host", "-lsecphase_b200",
+                                                  "-Wl,-rpath,$ORIGIN/../secphase_b200/lib"])
+    cb_main = os.path.join(HOST, "correct_bam_main.cpp")
+    if force or _stale(CORRECT_BAM, [cb_main, HOST_LIB] + hdrs):
+        subprocess.check_call([cxx] + CXX_FLAGS + ["-o", CORRECT_BAM, cb_main, "-L" + LIBDIR, "-lsecphase_host", "-lz",
                                                   "-Wl,-rpath,$ORIGIN/../secphase_b200/lib"])
     return HOST_LIB, CLI
 

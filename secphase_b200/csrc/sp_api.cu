@@ -108,7 +108,7 @@ struct Slot {
     bool safe_caps = false;
     // device work tables
     DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, item_off, row_off, sdbl_off, score,
-        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out;
+        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out, set_base;
     // host results
     PinBuf h_tot, h_gout, h_score, h_info, h_fin, h_qual;
     size_t qual_bytes = 0;  // size of the batch's quality pool (== of qual_out in full_baq mode)
@@ -345,7 +345,13 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
         cudaFuncSetAttribute(k_hmm2<1, 43>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
         cudaFuncSetAttribute(k_hmm2<1, 45>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
         cudaFuncSetAttribute(k_hmm2<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
+        cudaFuncSetAttribute(k_hmm2<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<1, 41, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<1, 43, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<1, 45, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hmm2<3, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
         set_err("sp_create: cudaFuncSetAttribute(k_hmm) failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
         return nullptr;
@@ -397,7 +403,7 @@ void sp_destroy(sp_ctx *c) {
         DevBuf *bufs[] = {&S.d_in, &S.ops, &S.imk, &S.info, &S.blk, &S.iv, &S.nb, &S.gpos, &S.ent, &S.res, &S.baq,
                           &S.gP, &S.gout, &S.gcnt, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
                           &S.fin, &S.items, &S.rows, &S.order, &S.bins, &S.class_start, &S.s_pool, &S.fsave,
-                          &S.gband, &S.totals, &S.work_counter, &S.qual_out};
+                          &S.gband, &S.totals, &S.work_counter, &S.qual_out, &S.set_base};
         for (DevBuf *b : bufs) b->release();
         PinBuf *pins[] = {&S.h_in, &S.h_tot, &S.h_gout, &S.h_score, &S.h_info, &S.h_fin, &S.h_qual};
         for (PinBuf *b : pins) b->release();
@@ -648,9 +654,10 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
 // whose band falls back to global memory when it outgrows shared memory.  Every class is an
 // independent launch on its own auxiliary stream, widest (= fewest, slowest instances) first, so
 // that a handful of wide instances overlaps with the bulk instead of trailing it.
-template <int NW, int NC>
+template <int NW, int NC, bool IL>
 static void launch_hmm2(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first, int cnt, const uint8_t *ref,
-                        const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride) {
+                        const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride,
+                        const int64_t *set_base, int set_first) {
     const int nblk = (cnt + 31) / 32;
     const int ncell = sp_h2_cells(sp_class_bw(cls));
     const size_t slab = (size_t) ncell * 32 * 24;
@@ -659,20 +666,38 @@ static void launch_hmm2(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first,
     if (wpc > nblk) wpc = nblk;
     int grid = (nblk + wpc - 1) / wpc;
     if (grid > c->hmm_sms) grid = c->hmm_sms;
-    k_hmm2<NW, NC><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(),
+    k_hmm2<NW, NC, IL><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(),
                                                    first, cnt, ncell, ref, qbytes, seq_pool, seq_off,
-                                                   S.s_pool.as<double>(), S.fsave.as<double>(), fs_stride,
-                                                   S.rows.as<SpRow>(), S.work_counter.as<int>() + cls);
+                                                   S.s_pool.as<double>(), S.fsave.as<double>(),
+                                                   set_base ? (int64_t) (2 * sp_class_bw(cls) + 1) * 64 : fs_stride,
+                                                   S.rows.as<SpRow>(), S.work_counter.as<int>() + cls, set_base, set_first);
 }
 
+// `interleaved`: the -w mode's lane-interleaved forward-row pool (set bases from k_fs_sets), else
+// every instance keeps its rows to itself at row0 * fs_stride
 static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_count, int max_bw, const uint8_t *ref,
-                      const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride) {
+                      const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride,
+                      bool interleaved = false) {
     int rc;
     if ((rc = S.work_counter.ensure(sizeof(int) * SP_N_CLASSES))) return rc;
     CK(cudaMemsetAsync(S.work_counter.p, 0, sizeof(int) * SP_N_CLASSES, st));
     int first[SP_N_CLASSES + 1];
     first[0] = 0;
     for (int cls = 0; cls < SP_N_CLASSES; cls++) first[cls + 1] = first[cls] + class_count[cls];
+    SpSetPlan sets;
+    memset(&sets, 0, sizeof(sets));
+    if (interleaved) {
+        for (int cls = 0; cls < SP_N_CLASSES; cls++) {
+            sets.first_item[cls] = first[cls];
+            sets.count[cls] = class_count[cls];
+            sets.cells[cls] = 2 * sp_class_bw(cls) + 1;
+            sets.first_set[cls + 1] = sets.first_set[cls] + (class_count[cls] + 31) / 32;
+        }
+        if ((rc = S.set_base.ensure(8 * (size_t) (sets.first_set[SP_N_CLASSES] + 1)))) return rc;
+        k_fs_sets<<<1, 1024, 0, st>>>(sets, S.items.as<SpItem>(), S.order.as<int32_t>(), S.set_base.as<int64_t>());
+        S.launches++;
+    }
+    const int64_t *set_base = interleaved ? S.set_base.as<int64_t>() : nullptr;
     CK(cudaEventRecord(S.ev_fork, st));
     int used = 0;
     for (int cls = SP_N_CLASSES - 1; cls >= 0; cls--) {
@@ -684,7 +709,15 @@ static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_
         const int bwc = sp_class_bw(cls);
         if (bwc != 0) {
             const int nw = sp_h2_words(bwc);
-#define SP_LAUNCH(NW, NC) launch_hmm2<NW, NC>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride)
+#define SP_LAUNCH(NW, NC)                                                                                          \
+    do {                                                                                                           \
+        if (interleaved)                                                                                           \
+            launch_hmm2<NW, NC, true>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride,  \
+                                      set_base, sets.first_set[cls]);                                              \
+        else                                                                                                       \
+            launch_hmm2<NW, NC, false>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, \
+                                       nullptr, 0);                                                                \
+    } while (0)
             switch (sp_class_unrolled_cells(cls)) {
                 case 41: SP_LAUNCH(1, 41); break;
                 case 43: SP_LAUNCH(1, 43); break;
@@ -762,7 +795,21 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
     if ((rc = S.order.ensure(4 * (size_t) (T.n_items + 1)))) return rc;
     if ((rc = S.s_pool.ensure(8 * (size_t) (T.s_doubles + 2)))) return rc;
     const int64_t fs_stride = 2 * (2 * (int64_t) T.max_bw + 1);
-    if ((rc = S.fsave.ensure(8 * (size_t) ((int64_t) T.n_rows * fs_stride + 2)))) return rc;
+    // -w mode: every lane of a warp saves and re-reads every row in lock step, so the forward rows of a
+    // 32-instance set are interleaved lane by lane (coalesced 512-byte accesses) instead of each
+    // instance keeping ~650-byte rows to itself.  Needs the shared-memory-band kernel for every
+    // instance and window lengths the length sort resolves exactly (see k_fs_sets).
+    const bool interleaved = S.full_baq && T.n_items > 0 && T.class_count[SP_N_CLASSES - 1] == 0 &&
+                             T.max_lq <= SP_SORT_LBINS - 2 && !getenv("SECPHASE_B200_NO_INTERLEAVE");  // (tests: both layouts)
+    if (interleaved) {
+        int64_t dbl = 0;  // sum over sets of (longest instance's rows) <= max rows + class rows / 32, per class
+        for (int cls = 0; cls + 1 < SP_N_CLASSES; cls++)
+            if (T.class_count[cls] > 0)
+                dbl += (int64_t) (2 * sp_class_bw(cls) + 1) * 64 * (T.max_lq + T.class_rows[cls] / 32 + 2);
+        if ((rc = S.fsave.ensure(8 * (size_t) (dbl + 2)))) return rc;
+    } else if ((rc = S.fsave.ensure(8 * (size_t) ((int64_t) T.n_rows * fs_stride + 2)))) {
+        return rc;
+    }
     if (P.G > 0 && T.n_items > 0) {
         k_emit<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC, S.items.as<SpItem>(), S.rows.as<SpRow>());
         const int nbins = (SP_N_CLASSES + 1) * SP_SORT_LBINS;
@@ -775,7 +822,8 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
     }
     CK(cudaEventRecord(S.ev[EV_EMIT], st));
     if (T.n_items > 0) {
-        if ((rc = launch_hmm(c, S, st, T.class_count, T.max_bw, P.ref, nullptr, P.seq_pool, P.seq_off, fs_stride)))
+        if ((rc = launch_hmm(c, S, st, T.class_count, T.max_bw, P.ref, nullptr, P.seq_pool, P.seq_off, fs_stride,
+                             interleaved)))
             return rc;
     }
     CK(cudaEventRecord(S.ev[EV_HMM], st));

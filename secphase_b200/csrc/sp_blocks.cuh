@@ -288,6 +288,8 @@ struct SpEmitCounts {
     int64_t s_doubles;  // sum over items of (l_query + 2)
     int32_t max_bw;
     int32_t class_count[SP_N_CLASSES];  // instances with at least one marker row, per band class
+    int32_t class_rows[SP_N_CLASSES];   // their rows (sizes the lane-interleaved forward-row pool of the -w mode)
+    int32_t max_lq;                     // longest window of the group
 };
 
 template <bool EMIT>
@@ -442,7 +444,11 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
             cnt.cells += sp_hmm_cells(l_ref, l_query, bw);
             cnt.s_doubles += l_query + 2;
             if (bw > cnt.max_bw) cnt.max_bw = bw;
-            if (n_rows > 0) cnt.class_count[sp_band_class(bw)] += 1;
+            if (n_rows > 0) {
+                cnt.class_count[sp_band_class(bw)] += 1;
+                cnt.class_rows[sp_band_class(bw)] += n_rows;
+            }
+            if (l_query > cnt.max_lq) cnt.max_lq = l_query;
         }
         while (SP_MK_VALID(j) && SP_MK_BASE(j) <= blk.sqe) {
             if (blk.sqe - SP_BLOCK_MARGIN <= SP_MK_BASE(j)) {

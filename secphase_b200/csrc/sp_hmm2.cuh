@@ -154,16 +154,21 @@ SP_HD int sp_query_decode(const SpHmmIn &in, int i0, uint32_t raw) {
     return (int) ((0x4444444344424104ull >> (nib << 2)) & 0xf);
 }
 
-// rinv[i], i = 1..l_query : 1/s[i].   fsave + r*fs_stride : scaled forward (M,I) of marker row r, [o*2+{0,1}].
+// rinv[i], i = 1..l_query : 1/s[i].   fsave + r*fs_stride + o*fs_cs : scaled forward (M,I) of consumed row r,
+// cell o, as one 16-byte pair.  Marker-row mode keeps each instance's rows to itself (fs_cs = 2, rows
+// back to back); the --writeBam mode, where every lane saves and re-reads every row in lock step,
+// interleaves the 32 lanes of a warp (fs_cs = 64, lane offset folded into fsave) so that each
+// (row, cell) is one coalesced 512-byte access.
 //
 // NC > 0 selects the fully unrolled row bodies for bands of exactly NC = 2*bw+1 cells: for the rows
 // where every lane of the warp has a full, sliding band (bw+2 <= i <= Lr-bw) the D plane (forward)
 // lives in registers and every cell index is a compile-time constant, which removes a third of
 // the shared-memory traffic and all per-chunk address / mask arithmetic.  full_warp says that all
 // 32 lanes are inside this function (the fast path takes warp-uniform decisions by vote).
-template <int STRIDE, int NW, int NC, int NCRF_ = SP_H2_NCRF, int NCRB_ = SP_H2_NCRB>
+template <int STRIDE, int NW, int NC, int FS_CS = 2, int NCRF_ = SP_H2_NCRF, int NCRB_ = SP_H2_NCRB>
 SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<STRIDE> B, double *rinv, double *fsave,
                             int64_t fs_stride, SpRow *rows, int n_rows, bool full_warp) {
+    constexpr int fs_cs = FS_CS;  // doubles between consecutive cells of a saved forward row
     constexpr int U = SP_H2_U;
     const int Lr = in.l_ref, Lq = in.l_query;
     const int bw = sp_hmm_bw(Lr, Lq, in.par_bw);
@@ -228,7 +233,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
             v.x = SP_DDIV(v.x, sum);
             v.y = SP_DDIV(v.y, sum);
             B.mi[o * STRIDE] = v;
-            if (fs) { fs[o * 2 + 0] = v.x; fs[o * 2 + 1] = v.y; }
+            if (fs) *reinterpret_cast<SpD2 *>(fs + (int64_t) o * fs_cs) = v;
         }
         if (fs) nr++;  // only the stand-alone API asks for row 1
         rinv[1] = SP_DDIV(1., sum);
@@ -390,8 +395,10 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
             double *fs = fsave + (int64_t) nr * fs_stride;
             for (int o = 0; o < n; o++) {
                 const SpD2 a = B.mi[o * STRIDE];
-                fs[o * 2 + 0] = SP_DMUL(a.x, ri);
-                fs[o * 2 + 1] = SP_DMUL(a.y, ri);
+                SpD2 v;
+                v.x = SP_DMUL(a.x, ri);
+                v.y = SP_DMUL(a.y, ri);
+                *reinterpret_cast<SpD2 *>(fs + (int64_t) o * fs_cs) = v;
             }
             nr++;
             t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
@@ -421,16 +428,29 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         const double *fs = fsave + (int64_t) ri * fs_stride;
         double sum = 0., mx = 0.;
         int max_k = -1;
-        for (int o = 0; o < n; o++) {
-            const SpD2 a = B.mi[o * STRIDE];
-            double bm = a.x, bi = a.y;
-            if (scale) { bm = SP_DMUL(bm, y); bi = SP_DMUL(bi, y); }
-            double z = SP_DMUL(fs[o * 2 + 0], bm);
-            if (z > mx) { mx = z; max_k = (beg + o - 1) << 2 | 0; }
-            sum = SP_DADD(sum, z);
-            z = SP_DMUL(fs[o * 2 + 1], bi);
-            if (z > mx) { mx = z; max_k = (beg + o - 1) << 2 | 1; }
-            sum = SP_DADD(sum, z);
+        // the saved forward row comes from global memory: fetch MAPC cells ahead of the (serial, in
+        // the reference's order) max/sum chain so that the loads overlap instead of each stalling it
+        constexpr int MAPC = FS_CS == 64 ? 4 : 1;  // (marker-row mode: a handful of rows, keep the registers)
+        for (int o0 = 0; o0 < n; o0 += MAPC) {
+            SpD2 fv[MAPC];
+#pragma unroll
+            for (int j = 0; j < MAPC; j++)
+                if (o0 + j < n) fv[j] = *reinterpret_cast<const SpD2 *>(fs + (int64_t) (o0 + j) * fs_cs);
+#pragma unroll
+            for (int j = 0; j < MAPC; j++) {
+                const int o = o0 + j;
+                if (o < n) {
+                    const SpD2 a = B.mi[o * STRIDE];
+                    double bm = a.x, bi = a.y;
+                    if (scale) { bm = SP_DMUL(bm, y); bi = SP_DMUL(bi, y); }
+                    double z = SP_DMUL(fv[j].x, bm);
+                    if (z > mx) { mx = z; max_k = (beg + o - 1) << 2 | 0; }
+                    sum = SP_DADD(sum, z);
+                    z = SP_DMUL(fv[j].y, bi);
+                    if (z > mx) { mx = z; max_k = (beg + o - 1) << 2 | 1; }
+                    sum = SP_DADD(sum, z);
+                }
+            }
         }
         mx = SP_DDIV(mx, sum);
         rows[ri].state = max_k;

@@ -29,6 +29,8 @@ struct SpTotals {  // device-side counters of one batch, read back once mid-pipe
     int32_t class_count[SP_N_CLASSES];
     int32_t fin_rows;  // compact final-marker rows reserved so far
     int32_t err;
+    int32_t max_lq, pad1;
+    int64_t class_rows[SP_N_CLASSES];
 };
 
 struct SpBatchPtrs {
@@ -153,17 +155,19 @@ __global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__re
 __global__ void __launch_bounds__(1024) k_scan_groups(SpBatchPtrs B, SpTotals *tot) {
     __shared__ int32_t s_items[1024], s_rows[1024];
     __shared__ int64_t s_sd[1024], s_cells[1024];
-    __shared__ int32_t s_cls[SP_N_CLASSES], s_maxbw;
+    __shared__ int32_t s_cls[SP_N_CLASSES], s_maxbw, s_maxlq;
+    __shared__ unsigned long long s_crows[SP_N_CLASSES];
     const int t = threadIdx.x, G = B.G;
     const int per = (G + 1023) / 1024;
     const int g0 = t * per, g1 = min(G, g0 + per);
-    if (t < SP_N_CLASSES) s_cls[t] = 0;
-    if (t == 0) s_maxbw = 0;
+    if (t < SP_N_CLASSES) { s_cls[t] = 0; s_crows[t] = 0; }
+    if (t == 0) { s_maxbw = 0; s_maxlq = 0; }
     __syncthreads();
-    int32_t li = 0, lr = 0, lbw = 0;
+    int32_t li = 0, lr = 0, lbw = 0, llq = 0;
     int64_t ls = 0, lc = 0;
     int32_t lcls[SP_N_CLASSES];
-    for (int k = 0; k < SP_N_CLASSES; k++) lcls[k] = 0;
+    int64_t lcr[SP_N_CLASSES];
+    for (int k = 0; k < SP_N_CLASSES; k++) { lcls[k] = 0; lcr[k] = 0; }
     for (int g = g0; g < g1; g++) {
         const SpEmitCounts c = B.gcnt[g];
         li += c.n_items;
@@ -171,15 +175,20 @@ __global__ void __launch_bounds__(1024) k_scan_groups(SpBatchPtrs B, SpTotals *t
         ls += c.s_doubles;
         lc += c.cells;
         lbw = max(lbw, c.max_bw);
-        for (int k = 0; k < SP_N_CLASSES; k++) lcls[k] += c.class_count[k];
+        llq = max(llq, c.max_lq);
+        for (int k = 0; k < SP_N_CLASSES; k++) { lcls[k] += c.class_count[k]; lcr[k] += c.class_rows[k]; }
     }
     s_items[t] = li;
     s_rows[t] = lr;
     s_sd[t] = ls;
     s_cells[t] = lc;
     atomicMax(&s_maxbw, lbw);
+    atomicMax(&s_maxlq, llq);
     for (int k = 0; k < SP_N_CLASSES; k++)
-        if (lcls[k]) atomicAdd(&s_cls[k], lcls[k]);
+        if (lcls[k]) {
+            atomicAdd(&s_cls[k], lcls[k]);
+            atomicAdd(&s_crows[k], (unsigned long long) lcr[k]);
+        }
     __syncthreads();
     // Hillis-Steele inclusive scan
     for (int d = 1; d < 1024; d <<= 1) {
@@ -207,7 +216,8 @@ __global__ void __launch_bounds__(1024) k_scan_groups(SpBatchPtrs B, SpTotals *t
         tot->s_doubles = s_sd[1023];
         tot->cells = s_cells[1023];
         tot->max_bw = s_maxbw;
-        for (int k = 0; k < SP_N_CLASSES; k++) tot->class_count[k] = s_cls[k];
+        tot->max_lq = s_maxlq;
+        for (int k = 0; k < SP_N_CLASSES; k++) { tot->class_count[k] = s_cls[k]; tot->class_rows[k] = (int64_t) s_crows[k]; }
         B.item_off[G] = s_items[1023];
         B.row_off[G] = s_rows[1023];
         B.sdbl_off[G] = s_sd[1023];
@@ -322,13 +332,14 @@ __global__ void __launch_bounds__(32) k_hmm(const SpConst *__restrict__ Cp, cons
 // instances from a global counter in (band class, length)-sorted order, i.e. longest first, so the
 // SMs drain together.  Per-warp slab in dynamic shared memory: ncell x 32 double2 (M,I) followed
 // by ncell x 32 double (D), lane-interleaved; see sp_hmm2.cuh.
-template <int NW, int NC>
+template <int NW, int NC, bool IL = false>
 __global__ void __launch_bounds__(224, 1) k_hmm2(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
                                               const int32_t *__restrict__ order, int first, int count, int ncell,
                                               const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qbytes,
                                               const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,
                                               double *__restrict__ s_pool, double *__restrict__ fsave, int64_t fs_stride,
-                                              SpRow *rows, int *work_counter) {
+                                              SpRow *rows, int *work_counter, const int64_t *__restrict__ set_base,
+                                              int set_first) {
     extern __shared__ double2 smem2[];
     const int lane = threadIdx.x & 31;
     double2 *slab = smem2 + (size_t) (threadIdx.x >> 5) * ncell * 48;  // ncell*32*(16+8) bytes per warp
@@ -364,11 +375,53 @@ __global__ void __launch_bounds__(224, 1) k_hmm2(const SpConst *__restrict__ Cp,
             in.l_ref = it.l_ref;
             in.l_query = it.l_query;
             in.par_bw = it.par_bw;
-            sp_hmm2_instance<32, NW, NC>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride,
-                                         fs_stride, rows + it.row0, it.n_rows, w * 32 + 32 <= count);
+            if constexpr (IL)  // -w mode: forward rows of the warp's 32 instances interleaved lane by lane (fs_stride = cells*64)
+                sp_hmm2_instance<32, NW, NC, 64>(*Cp, in, B, s_pool + it.s_off, fsave + set_base[set_first + w] + 2 * lane,
+                                                 fs_stride, rows + it.row0, it.n_rows, w * 32 + 32 <= count);
+            else
+                sp_hmm2_instance<32, NW, NC>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride,
+                                             fs_stride, rows + it.row0, it.n_rows, w * 32 + 32 <= count);
         }
         __syncwarp();
     }
+}
+
+// -w mode: offset (in doubles) of every 32-instance set's lane-interleaved forward-row block.  Sets are
+// numbered class by class in launch order; within a class instances are sorted by descending window
+// length, so a set's longest instance is its first (valid while all windows are below the sort's last
+// length bin, which the launcher checks).  One CTA; set_base[n_sets] receives the total.
+struct SpSetPlan {
+    int32_t first_item[SP_N_CLASSES], count[SP_N_CLASSES], first_set[SP_N_CLASSES + 1], cells[SP_N_CLASSES];
+};
+__global__ void __launch_bounds__(1024) k_fs_sets(SpSetPlan pl, const SpItem *__restrict__ items,
+                                                  const int32_t *__restrict__ order, int64_t *set_base) {
+    __shared__ int64_t s[1024];
+    const int t = threadIdx.x;
+    const int n_sets = pl.first_set[SP_N_CLASSES];
+    const int per = (n_sets + 1023) / 1024;
+    const int s0 = min(n_sets, t * per), s1 = min(n_sets, s0 + per);
+    auto size_of = [&](int k) -> int64_t {
+        int c = 0;
+        while (c + 1 < SP_N_CLASSES && k >= pl.first_set[c + 1]) c++;
+        const SpItem it = items[order[pl.first_item[c] + (k - pl.first_set[c]) * 32]];
+        return (int64_t) it.n_rows * pl.cells[c] * 64;
+    };
+    int64_t l = 0;
+    for (int k = s0; k < s1; k++) l += size_of(k);
+    s[t] = l;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        int64_t a = t >= d ? s[t - d] : 0;
+        __syncthreads();
+        s[t] += a;
+        __syncthreads();
+    }
+    int64_t run = s[t] - l;
+    for (int k = s0; k < s1; k++) {
+        set_base[k] = run;
+        run += size_of(k);
+    }
+    if (t == 1023) set_base[n_sets] = s[1023];
 }
 
 __global__ void __launch_bounds__(64) k_score(SpBatchPtrs B, const SpConst *__restrict__ Cp, const SpRow *rows,

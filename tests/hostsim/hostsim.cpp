@@ -40,10 +40,28 @@ struct HsOut {
 
 // the instantiation launch_hmm() (sp_api.cu) picks for a band half-width; `unrolled` = what a full
 // warp of that class runs, otherwise what a partial last warp runs
+// `il_lane` >= 0: the -w mode's lane-interleaved forward-row block (k_hmm2<.,.,true>), this instance
+// playing lane il_lane of its 32-instance set; fsave then points at the set's block
 static void hs_hmm2_dispatch(const SpConst &C, const SpHmmIn &in, const SpBand2<1> &B, int bw, double *rinv,
-                             double *fsave, SpRow *rows, int n_rows, bool unrolled) {
+                             double *fsave, SpRow *rows, int n_rows, bool unrolled, int il_lane = -1) {
     const int64_t fss = 2 * (2 * bw + 1);
     const int cls = sp_band_class(bw);
+    if (il_lane >= 0) {
+        const int64_t rs = (int64_t) (2 * sp_class_bw(cls) + 1) * 64;
+        double *fl = fsave + 2 * il_lane;
+        switch (sp_class_unrolled_cells(cls)) {
+            case 41: sp_hmm2_instance<1, 1, 41, 64>(C, in, B, rinv, fl, rs, rows, n_rows, unrolled); return;
+            case 43: sp_hmm2_instance<1, 1, 43, 64>(C, in, B, rinv, fl, rs, rows, n_rows, unrolled); return;
+            case 45: sp_hmm2_instance<1, 1, 45, 64>(C, in, B, rinv, fl, rs, rows, n_rows, unrolled); return;
+            default: break;
+        }
+        switch (sp_h2_words(sp_class_bw(cls))) {
+            case 1: sp_hmm2_instance<1, 1, 0, 64>(C, in, B, rinv, fl, rs, rows, n_rows, false); break;
+            case 2: sp_hmm2_instance<1, 2, 0, 64>(C, in, B, rinv, fl, rs, rows, n_rows, false); break;
+            default: sp_hmm2_instance<1, 3, 0, 64>(C, in, B, rinv, fl, rs, rows, n_rows, false); break;
+        }
+        return;
+    }
     switch (sp_class_unrolled_cells(cls)) {
         case 41: sp_hmm2_instance<1, 1, 41>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
         case 43: sp_hmm2_instance<1, 1, 43>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
@@ -326,6 +344,11 @@ int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         if (cnt.n_items != gcnt[g].n_items || cnt.n_rows != gcnt[g].n_rows) out->err |= 0x100;
     }
     // K4: one "lane" per item
+    bool all_h2 = true;
+    for (int it = 0; it < item_off[G]; it++) {
+        const SpItem &I = items[it];
+        if (sp_hmm_bw(I.l_ref, I.l_query, I.par_bw) > SP_H2_MAXBW || I.l_query > 2046) all_h2 = false;
+    }
     for (int it = 0; it < item_off[G]; it++) {
         const SpItem &I = items[it];
         const int bw = sp_hmm_bw(I.l_ref, I.l_query, I.par_bw);
@@ -333,7 +356,11 @@ int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         std::vector<double> band((size_t) W * 3, 0.0);
         std::vector<uint32_t> code((size_t) W, 0);
         std::vector<double> s((size_t) I.l_query + 2, 0.0);
-        std::vector<double> fsave((size_t) I.n_rows * 2 * (2 * bw + 1) + 2, 0.0);
+        // the launcher's choice (run_phase_b): lane-interleaved rows in -w mode when every instance runs
+        // the shared-memory-band kernel
+        const int il_lane = (full_baq && all_h2) ? it % 32 : -1;
+        std::vector<double> fsave(il_lane >= 0 ? (size_t) I.n_rows * (2 * sp_class_bw(sp_band_class(bw)) + 1) * 64 + 2
+                                               : (size_t) I.n_rows * 2 * (2 * bw + 1) + 2, 0.0);
         SpHmmIn in;
         in.ref = ref_codes + I.ref_off;
         in.qbytes = nullptr;
@@ -347,7 +374,7 @@ int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
             for (auto &v : mi) v.x = v.y = 0.0;
             SpBand2<1> B2;
             B2.mi = mi.data() + 1; B2.d = dd.data() + 1;
-            hs_hmm2_dispatch(C, in, B2, bw, s.data(), fsave.data(), rows.data() + I.row0, I.n_rows, true);
+            hs_hmm2_dispatch(C, in, B2, bw, s.data(), fsave.data(), rows.data() + I.row0, I.n_rows, true, il_lane);
         } else {
             SpBand<1> B;
             B.row = band.data(); B.code = code.data(); B.W = W;

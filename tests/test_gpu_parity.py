@@ -63,6 +63,36 @@ def test_write_qual_mode_bit_exact_vs_oracle(sp, oracle, name, spreset, ppreset,
         assert len(got3["rows"]) < len(got["rows"]) or len(exp["hmm"]) == 0
 
 
+def test_write_qual_lane_private_layout(sp, oracle, monkeypatch):
+    """The -w mode's fallback layout (instances keep their forward rows to themselves: used when a batch
+    has bands too wide for the shared-memory kernel or windows longer than the length sort resolves)."""
+    monkeypatch.setenv("SECPHASE_B200_NO_INTERLEAVE", "1")
+    for spreset, ppreset, ng, over in (("hifi", "hifi", 60, dict(locus_len=300000)), ("stress", "hifi", 16, dict(locus_len=300000))):
+        s, b, codes, off = make_case(spreset, ng, **over)
+        exp = oracle.run(b, oracle.preset_params(ppreset), oracle_refseq(oracle, s))
+        with sp.Secphase(ppreset) as eng:
+            eng.set_reference_codes(codes, off)
+            eng.set_write_qual(True)
+            got = eng.run(b)
+        assert np.array_equal(got["baq_qual"], exp["qual"])
+        assert np.array_equal(got["scores"].view(np.int64), exp["scores"].view(np.int64))
+
+
+def test_write_qual_without_consensus_long_windows(sp, oracle):
+    """-q without -c: the HMM windows are whole confident blocks (thousands of bases), beyond the
+    length-sorted range of the interleaved layout -> the launcher must fall back, results unchanged."""
+    s, b, codes, off = make_case("hifi", 6, locus_len=200000, len_mean=4000, len_sd=500, len_min=3000)
+    op = oracle.preset_params("hifi", consensus=0)
+    exp = oracle.run(b, op, oracle_refseq(oracle, s))
+    with sp.Secphase("hifi", consensus=0) as eng:
+        eng.set_reference_codes(codes, off)
+        eng.set_write_qual(True)
+        got = eng.run(b)
+    assert np.array_equal(got["baq_qual"], exp["qual"])
+    assert np.array_equal(got["scores"].view(np.int64), exp["scores"].view(np.int64))
+    assert int(exp["hmm"][:, 2].max()) > 2046 or len(exp["hmm"]) == 0
+
+
 def test_reference_ascii_upload_matches_codes(sp, oracle):
     s, b, codes, off = make_case("hifi", 30, locus_len=200000, n_rate=1e-3)
     with sp.Secphase("hifi") as e1, sp.Secphase("hifi") as e2:
