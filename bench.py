@@ -53,17 +53,30 @@ def parse_args():
     ap.add_argument("--pool", type=int, default=3, help="distinct pre-generated batches cycled through the steps")
     ap.add_argument("--cpu-sample", type=int, default=0, help="read groups of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--preset", default="hifi", choices=["hifi", "ont", "stress"],
+                    help="workload family: hifi = BASELINE configs[2] (the bench line); ont / stress = configs[1] / [4], "
+                         "for the profiles only")
     return ap.parse_args()
 
 
 def workload_name(args):
+    if args.preset == "ont":
+        return (f"ont (BASELINE configs[1] shape): synthetic diploid 2x{args.locus_len / 1e6:g} Mb, simulated ONT reads "
+                f"N(30 kb, 8 kb), primary + 1 secondary, --ont preset; step = {args.groups} read groups per GPU")
+    if args.preset == "stress":
+        return (f"stress (BASELINE configs[4] shape): near-identical repeat copies, up to 8 secondaries per read, "
+                f"homopolymer-rich, --hifi preset; step = {args.groups} read groups per GPU")
     return (f"chr-hifi-30x (BASELINE configs[2]): synthetic diploid 2x{args.locus_len / 1e6:g} Mb, simulated HiFi "
             f"reads N(15 kb, 2 kb), primary + 1 secondary, --hifi preset; step = {args.groups} read groups per GPU")
 
 
 def make_synth(args):
     from tools.synth.pysynth import Synth, default_cfg
-    return Synth(default_cfg("hifi", locus_len=args.locus_len, seed=20240603))
+    return Synth(default_cfg(args.preset, locus_len=args.locus_len, seed=20240603))
+
+
+def params_preset(args):
+    return "ont" if args.preset == "ont" else "hifi"
 
 
 class ClockSampler:
@@ -162,7 +175,7 @@ def run_reference_arm(args):
     times, groups, cells = [], 0, 0
     kind = "port"
     for i in range(n_steps):
-        g, c, dt, kind = cpu_reference_run(synth, [batches[i % len(batches)]], "hifi", threads)
+        g, c, dt, kind = cpu_reference_run(synth, [batches[i % len(batches)]], params_preset(args), threads)
         if i >= args.warmup:
             times.append(dt)
             groups += g
@@ -213,7 +226,7 @@ def main():
     t_setup = time.perf_counter()
     synth = make_synth(args)
     codes, off = encode_reference(synth)
-    eng = secphase_b200.Secphase("hifi", device=local)
+    eng = secphase_b200.Secphase(params_preset(args), device=local)
     eng.set_reference_codes(codes, off)
     # shard by query-name range: rank r owns groups [r*span, (r+1)*span)
     span = args.groups * args.pool
@@ -330,7 +343,10 @@ def main():
     # measured DRAM traffic of the same launch set from the committed ncu --set full capture,
     # scaled by band cells to this run's batch
     traffic = None
+    traffic_src = None
     try:
+        if args.preset != "hifi":
+            raise KeyError("the capture is of the HiFi workload")
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_k_hmm2.json")))
         traffic = tr["dram_bytes_total"] * iso_cells / tr["band_cells"]
         traffic_src = tr["source"]
@@ -381,7 +397,7 @@ def main():
         i = 0
         while dt < 12.0 and i < 8:
             sample = batches[i % len(batches)].group_slice(0, n_cpu)
-            g1, c1, dt1, kind = cpu_reference_run(synth, [sample], "hifi", threads)
+            g1, c1, dt1, kind = cpu_reference_run(synth, [sample], params_preset(args), threads)
             g, c, dt, i = g + g1, c + c1, dt + dt1, i + 1
         line["cpu_baseline"] = {"value": g / dt, "unit": "read-groups/s", "cores": threads, "kind": kind,
                                 "sample": f"{i} x the first {n_cpu} read groups of a step ({g} groups, {dt:.1f} s), "

@@ -147,6 +147,7 @@ struct sp_ctx {
     SpRng rng;
     bool debug_tables = false;
     bool full_baq = false;  // sp_set_write_qual: --writeBam mode
+    bool streams_ready = false;  // ensure_streams
     int sm_count = 0;
     size_t max_smem = 0;
     cudaEvent_t mark = nullptr;  // sp_mark / sp_elapsed_since_mark
@@ -258,6 +259,33 @@ static bool make_stream(sp_ctx *c, CUgreenCtx g, cudaStream_t *out) {
     return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking) == cudaSuccess;
 }
 
+// The SM partition and the streams inside it are created at the first batch, because the right split
+// depends on the data: the integer stages (walk / group / emit) are thread-per-alignment latency
+// chains whose cost grows with the cs/MD text, the HMM with the band cells.  HiFi read groups carry
+// ~3 KB of tag text and are best served by 8 SMs of integer work against 140 of HMM; ONT groups carry
+// ~17 KB and want 24 (measured: profiles/r01_sm_partition_sweep_v13.json).  SECPHASE_B200_INT_SMS=<n>
+// overrides (0 = no partition); the driver rounds the request up to its own granularity.
+static int ensure_streams(sp_ctx *c, const sp_flat_batch *hint) {
+    if (c->streams_ready) return SP_OK;
+    int want = 8;
+    if (hint && hint->n_groups > 0 && hint->tag_off[hint->n_alns] / hint->n_groups > 8192) want = 24;
+    if (const char *e = getenv("SECPHASE_B200_INT_SMS")) want = atoi(e);
+    if (want >= c->sm_count) want = 0;
+    partition_sms(c, want);
+    bool ok = true;
+    for (int s = 0; s < SP_N_SLOTS && ok; s++) {
+        Slot &S = c->slot[s];
+        ok = ok && make_stream(c, c->g_int, &S.stream);
+        for (int k = 0; k < SP_N_AUX && ok; k++) ok = ok && make_stream(c, c->g_hmm, &S.aux[k]);
+    }
+    if (!ok) {
+        set_err("could not create streams: %s", cudaGetErrorString(cudaGetLastError()));
+        return SP_ECUDA;
+    }
+    c->streams_ready = true;
+    return SP_OK;
+}
+
 static void launcher_main(sp_ctx *c);
 
 // ------------------------------------------------------------------------------------------
@@ -356,28 +384,17 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
         delete c;
         return nullptr;
     }
-    // SECPHASE_B200_INT_SMS: SMs set aside for the integer stages (0 = no partition); the driver
-    // rounds the request up to its own granularity
-    {
-        const char *e = getenv("SECPHASE_B200_INT_SMS");
-        int want = e ? atoi(e) : 8;
-        if (want >= c->sm_count) want = 0;
-        partition_sms(c, want);
-    }
     bool ok = true;
     for (int s = 0; s < SP_N_SLOTS && ok; s++) {
         Slot &S = c->slot[s];
-        ok = ok && make_stream(c, c->g_int, &S.stream);
         for (int k = 0; k < EV_N; k++) ok = ok && cudaEventCreate(&S.ev[k]) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&S.ev_a, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
-        for (int k = 0; k < SP_N_AUX && ok; k++) {
-            ok = ok && make_stream(c, c->g_hmm, &S.aux[k]);
+        for (int k = 0; k < SP_N_AUX && ok; k++)
             ok = ok && cudaEventCreateWithFlags(&S.ev_join[k], cudaEventDisableTiming) == cudaSuccess;
-        }
     }
     if (!ok) {
-        set_err("sp_create: could not create streams/events: %s", cudaGetErrorString(cudaGetLastError()));
+        set_err("sp_create: could not create events: %s", cudaGetErrorString(cudaGetLastError()));
         sp_destroy(c);
         return nullptr;
     }
@@ -536,7 +553,13 @@ static InLayout make_layout(const sp_flat_batch *b, const SpPlan &pl) {
 }
 
 static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
-    int rc = sp_make_plan(b, c->par.indel_threshold, S.safe_caps, S.plan);
+    // the plan scans every cs/MD byte once: a few threads when the batch carries a lot of tag text (ONT)
+    int plan_threads = 1;
+    if (b->n_alns > 0 && b->tag_off[b->n_alns] > ((int64_t) 4 << 20)) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        plan_threads = hw >= 16 ? 8 : hw >= 4 ? (int) hw / 2 : 1;
+    }
+    int rc = sp_make_plan(b, c->par.indel_threshold, S.safe_caps, S.plan, plan_threads);
     if (rc != SP_OK) {
         set_err("malformed batch (code %d): groups need 1..%d alignments, CIGAR ops limited to MIDSH=X", rc,
                 SP_MAX_ALN_PER_GROUP);
@@ -930,6 +953,7 @@ int sp_submit(sp_ctx *c, const sp_flat_batch *b, int slot) {
         return SP_ESTATE;
     }
     CK(cudaSetDevice(c->device));
+    if (int erc = ensure_streams(c, b)) return erc;
     Slot &S = c->slot[slot];
     if (S.state == 2) {
         set_err("slot %d still in flight; call sp_wait first", slot);
@@ -954,6 +978,7 @@ int sp_upload(sp_ctx *c, const sp_flat_batch *b, int slot) {
     if (!c || !b || slot < 0 || slot >= SP_N_SLOTS) return SP_EINVAL;
     if (c->n_contigs == 0) return SP_ESTATE;
     CK(cudaSetDevice(c->device));
+    if (int erc = ensure_streams(c, b)) return erc;
     Slot &S = c->slot[slot];
     S.safe_caps = false;
     int rc = stage_batch(c, S, b);
@@ -1004,6 +1029,7 @@ int sp_set_write_qual(sp_ctx *c, int on) {
 int sp_mark(sp_ctx *c) {
     if (!c) return SP_EINVAL;
     CK(cudaSetDevice(c->device));
+    if (int erc = ensure_streams(c, nullptr)) return erc;
     if (!c->mark) CK(cudaEventCreate(&c->mark));
     CK(cudaEventRecord(c->mark, c->slot[0].stream));
     return SP_OK;
@@ -1022,6 +1048,10 @@ int sp_elapsed_since_mark(sp_ctx *c, int slot, float *ms) {
 
 int sp_sm_partition(sp_ctx *c, int32_t *int_sms, int32_t *hmm_sms) {
     if (!c) return SP_EINVAL;
+    if (!c->streams_ready) {  // decided at the first batch; before that report the request a HiFi batch would get
+        if (cudaSetDevice(c->device) != cudaSuccess) return SP_ECUDA;
+        if (int erc = ensure_streams(c, nullptr)) return erc;
+    }
     if (int_sms) *int_sms = c->int_sms;
     if (hmm_sms) *hmm_sms = c->hmm_sms;
     return c->partitioned ? 1 : 0;
@@ -1296,6 +1326,7 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
             }
         }
     }
+    if (int erc = ensure_streams(c, nullptr)) return erc;
     Slot &S = c->slot[0];
     if (S.state == 2) {
         set_err("sp_hmm_batch uses slot 0, which still has a batch in flight");

@@ -17,6 +17,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "../../include/secphase_b200.h"
@@ -36,8 +38,60 @@ struct SpPlan {
     int64_t total_ops = 0, total_imk = 0, total_pos = 0, total_ent = 0, total_blk = 0, total_iv = 0;
 };
 
-// returns SP_OK or a negative error
-inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_caps, SpPlan &pl) {
+// Per-alignment counts from the record text alone (the only O(bytes) part of planning; independent
+// per alignment, so large batches are counted by a few threads).
+struct SpAlnCounts {
+    int64_t ntok, nmis;
+    int32_t cb, rc;
+};
+inline void sp_count_alignment(const sp_flat_batch *b, int a, int indel_threshold, SpAlnCounts &o) {
+    // byte classes: bit0 = starts a cs token (: * + -), bit1 = cs mismatch (*), bit2 = MD token
+    // (upper-case letter, ^, digit), bit3 = MD mismatch (upper-case letter)
+    static const struct Tab {
+        uint8_t t[256];
+        Tab() {
+            memset(t, 0, sizeof(t));
+            t[(uint8_t) ':'] |= 1; t[(uint8_t) '*'] |= 1 | 2; t[(uint8_t) '+'] |= 1; t[(uint8_t) '-'] |= 1;
+            for (int c = 'A'; c <= 'Z'; c++) t[c] |= 4 | 8;
+            for (int c = '0'; c <= '9'; c++) t[c] |= 4;
+            t[(uint8_t) '^'] |= 4;
+        }
+    } tab;
+    o.ntok = o.nmis = 0;
+    o.cb = 1;
+    o.rc = SP_OK;
+    const int nc = b->n_cigar[a];
+    if (nc < 1) { o.rc = SP_EINVAL; return; }
+    const uint32_t *cig = b->cigar_pool + b->cigar_off[a];
+    for (int k = 0; k < nc; k++) {
+        const int op = (int) (cig[k] & 15), len = (int) (cig[k] >> 4);
+        if (op == SP_CSOFT || op == SP_CHARD) o.cb++;
+        else if ((op == SP_CINS || op == SP_CDEL) && len > indel_threshold) o.cb++;
+        else if (op == SP_CREF_SKIP || op == SP_CPAD || op > SP_CDIFF) { o.rc = SP_EUNSUPPORTED; return; }
+    }
+    const uint8_t *t = (const uint8_t *) b->tag_pool + b->tag_off[a];
+    const int64_t tl = b->tag_off[a + 1] - b->tag_off[a];
+    const int kind = b->tag_kind ? b->tag_kind[a] : 0;
+    int64_t ntok = 0, nmis = 0;
+    if (kind == 0) {
+        for (int64_t k = 0; k < tl; k++) {
+            const uint8_t f = tab.t[t[k]];
+            ntok += f & 1;
+            nmis += (f >> 1) & 1;
+        }
+    } else {
+        for (int64_t k = 0; k < tl; k++) {
+            const uint8_t f = tab.t[t[k]];
+            ntok += (f >> 2) & 1;
+            nmis += (f >> 3) & 1;
+        }
+    }
+    o.ntok = ntok;
+    o.nmis = nmis;
+}
+
+// returns SP_OK or a negative error.  n_threads > 1: the per-alignment text scan runs on that many threads.
+inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_caps, SpPlan &pl, int n_threads = 1) {
     const int G = b->n_groups, A = b->n_alns;
     if (G < 0 || A < 0) return SP_EINVAL;
     pl.G = G;
@@ -51,49 +105,42 @@ inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_c
     pl.gblk_off.assign((size_t) G + 1, 0);
     pl.giv_off.assign((size_t) G + 1, 0);
     pl.gblk_cap.assign((size_t) G, 0);
-    int64_t ops = 0, imk = 0, pos = 0, ent = 0, blk = 0, iv = 0;
     for (int g = 0; g < G; g++) {
         const int a0 = b->grp_aln_off[g], a1 = b->grp_aln_off[g + 1];
         const int n = a1 - a0;
         if (n < 1 || n > SP_MAX_ALN_PER_GROUP || a0 < 0 || a1 > A) return SP_EINVAL;
+    }
+    std::vector<SpAlnCounts> cnt((size_t) A);
+    if (n_threads > 1 && A >= 4 * n_threads) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([&, t] {
+                // contiguous ranges balanced by tag bytes
+                const int64_t total = b->tag_off[A], lo = total * t / n_threads, hi = total * (t + 1) / n_threads;
+                int a = (int) (std::lower_bound(b->tag_off, b->tag_off + A, lo) - b->tag_off);
+                const int a_end = t + 1 == n_threads ? A : (int) (std::lower_bound(b->tag_off, b->tag_off + A, hi) - b->tag_off);
+                for (; a < a_end; a++) sp_count_alignment(b, a, indel_threshold, cnt[(size_t) a]);
+            });
+        for (auto &x : th) x.join();
+    } else {
+        for (int a = 0; a < A; a++) sp_count_alignment(b, a, indel_threshold, cnt[(size_t) a]);
+    }
+    int64_t ops = 0, imk = 0, pos = 0, ent = 0, blk = 0, iv = 0;
+    for (int g = 0; g < G; g++) {
+        const int a0 = b->grp_aln_off[g], a1 = b->grp_aln_off[g + 1];
+        const int n = a1 - a0;
         int64_t msum = 0, cbsum = 0;
         for (int a = a0; a < a1; a++) {
+            const SpAlnCounts &c = cnt[(size_t) a];
+            if (c.rc != SP_OK) return c.rc;
             pl.aln_grp[(size_t) a] = g;
-            const int nc = b->n_cigar[a];
-            if (nc < 1) return SP_EINVAL;
-            const uint32_t *cig = b->cigar_pool + b->cigar_off[a];
-            int cb = 1;
-            for (int k = 0; k < nc; k++) {
-                const int op = (int) (cig[k] & 15), len = (int) (cig[k] >> 4);
-                if (op == SP_CSOFT || op == SP_CHARD) cb++;
-                else if ((op == SP_CINS || op == SP_CDEL) && len > indel_threshold) cb++;
-                else if (op == SP_CREF_SKIP || op == SP_CPAD || op > SP_CDIFF) return SP_EUNSUPPORTED;
-            }
-            const char *t = b->tag_pool + b->tag_off[a];
-            const int64_t tl = b->tag_off[a + 1] - b->tag_off[a];
-            const int kind = b->tag_kind ? b->tag_kind[a] : 0;
-            int64_t ntok = 0, nmis = 0;
-            if (kind == 0) {
-                for (int64_t k = 0; k < tl; k++) {
-                    const char c = t[k];
-                    nmis += (c == '*');
-                    ntok += (c == ':') | (c == '*') | (c == '+') | (c == '-');
-                }
-            } else {
-                for (int64_t k = 0; k < tl; k++) {
-                    const char c = t[k];
-                    const bool up = (c >= 'A' && c <= 'Z');
-                    nmis += up;
-                    ntok += up | (c == '^') | (c >= '0' && c <= '9');
-                }
-            }
             pl.ops_off[(size_t) a] = ops;
-            ops += nc + ntok + 2;  // +1 spare, +1 sentinel
+            ops += b->n_cigar[a] + c.ntok + 2;  // +1 spare, +1 sentinel
             pl.imk_off[(size_t) a] = imk;
-            imk += nmis;
-            pl.cb_cap[(size_t) a] = cb;
-            msum += nmis;
-            cbsum += cb;
+            imk += c.nmis;
+            pl.cb_cap[(size_t) a] = c.cb;
+            msum += c.nmis;
+            cbsum += c.cb;
         }
         const int64_t P = msum;
         int64_t cap = safe_caps ? (int64_t) n * P + cbsum + 2 * n + 8 : P + cbsum + 2 * n + 8;
