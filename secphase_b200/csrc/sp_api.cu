@@ -90,7 +90,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 enum { EV_START = 0, EV_H2D, EV_WALK, EV_GROUP, EV_EMIT, EV_HMM, EV_SCORE, EV_END, EV_N };
 
-#define SP_N_AUX 4
+#define SP_N_AUX 9  // one per band class that a batch typically populates (3 slots x 10 streams stay under the 32 hardware queues)
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaStream_t aux[SP_N_AUX] = {};  // the HMM class launches fork onto these and join back
@@ -367,19 +367,18 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
         delete c;
         return nullptr;
     }
-    if (cudaFuncSetAttribute(k_hmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<1, 41>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<1, 43>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<1, 45>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<1, 41, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<1, 43, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<1, 45, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hmm2<3, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) != cudaSuccess) {
+    bool attr_ok = cudaFuncSetAttribute(k_hmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) == cudaSuccess;
+#define SP_ATTR(NW, NC)                                                                                                    \
+    attr_ok = attr_ok &&                                                                                                   \
+              cudaFuncSetAttribute(k_hmm2<NW, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) == cudaSuccess && \
+              cudaFuncSetAttribute(k_hmm2<NW, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) == cudaSuccess
+    SP_ATTR(1, 0); SP_ATTR(2, 0); SP_ATTR(3, 0);
+    SP_ATTR(1, 41); SP_ATTR(1, 43); SP_ATTR(1, 45);
+#if SP_N_EXACT_CLASSES > 3
+    SP_ATTR(1, 47); SP_ATTR(1, 49); SP_ATTR(1, 51);
+#endif
+#undef SP_ATTR
+    if (!attr_ok) {
         set_err("sp_create: cudaFuncSetAttribute(k_hmm) failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
         return nullptr;
@@ -745,6 +744,11 @@ static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_
                 case 41: SP_LAUNCH(1, 41); break;
                 case 43: SP_LAUNCH(1, 43); break;
                 case 45: SP_LAUNCH(1, 45); break;
+#if SP_N_EXACT_CLASSES > 3
+                case 47: SP_LAUNCH(1, 47); break;
+                case 49: SP_LAUNCH(1, 49); break;
+                case 51: SP_LAUNCH(1, 51); break;
+#endif
                 default:
                     if (nw == 1) SP_LAUNCH(1, 0);
                     else if (nw == 2) SP_LAUNCH(2, 0);

@@ -107,20 +107,29 @@ enum { SP_GERR_BLOCK_CAP = 1, SP_GERR_MARKER_CAP = 2, SP_GERR_OP_CAP = 4, SP_GER
 
 // Band classes of the HMM kernels: instances of one class share a launch (same shared-memory
 // slab per warp).  Classes 0..SP_N_CLASSES-2 run the shared-memory-band kernel (sp_hmm2.cuh).
-// The first three are exact band half-widths 20, 21, 22 (|Lr-Lq| = 0, 1, 2 with the presets'
-// -b20: 89 % of HiFi instances) and get the fully unrolled row bodies; the other bounds are
-// where one more warp's slab stops fitting an SM (5,4,3,2,1 warps of 2*bw+3 cells x 768 B in
-// 227 KB).  The last class is the generic kernel (sp_hmm.cuh), sized per launch.
-#define SP_N_CLASSES 9
+// The first SP_N_EXACT_CLASSES are exact band half-widths 20, 21, 22 (|Lr-Lq| = 0, 1, 2 with the
+// presets' -b20: 87 % of the band cells of the HiFi workload) and get the fully unrolled row bodies;
+// the other bounds are where one more warp's slab stops fitting an SM (5,4,3,2,1 warps of 2*bw+3
+// cells x 768 B in 227 KB).  The last class is the generic kernel (sp_hmm.cuh), sized per launch.
+// -DSP_N_EXACT_CLASSES=6 adds unrolled bodies for bw 23..25 (another 11 % of the cells): measured
+// +3 % with three batches in flight but a longer single-batch launch set (three more small
+// launches, each one poorly averaged round), so it is not the default (profiles/r01_exact_classes_v17.json).
+#ifndef SP_N_EXACT_CLASSES
+#define SP_N_EXACT_CLASSES 3
+#endif
+#define SP_N_CLASSES (SP_N_EXACT_CLASSES + 6)
 SP_HD int sp_class_bw(int cls) {
-    return cls == 0 ? 20 : cls == 1 ? 21 : cls == 2 ? 22 : cls == 3 ? 27 : cls == 4 ? 36 : cls == 5 ? 48 : cls == 6 ? 62
-           : cls == 7 ? 94 : 0;
+    return cls < SP_N_EXACT_CLASSES ? 20 + cls
+           : cls == SP_N_EXACT_CLASSES ? 27 : cls == SP_N_EXACT_CLASSES + 1 ? 36 : cls == SP_N_EXACT_CLASSES + 2 ? 48
+           : cls == SP_N_EXACT_CLASSES + 3 ? 62 : cls == SP_N_EXACT_CLASSES + 4 ? 94 : 0;
 }
 SP_HD int sp_band_class(int bw) {
-    return bw <= 20 ? 0 : bw <= 21 ? 1 : bw <= 22 ? 2 : bw <= 27 ? 3 : bw <= 36 ? 4 : bw <= 48 ? 5 : bw <= 62 ? 6
-           : bw <= 94 ? 7 : 8;
+    return bw <= 20 ? 0 : bw <= 20 + SP_N_EXACT_CLASSES - 1 ? bw - 20
+           : SP_N_EXACT_CLASSES + (bw <= 27 ? 0 : bw <= 36 ? 1 : bw <= 48 ? 2 : bw <= 62 ? 3 : bw <= 94 ? 4 : 5);
 }
-SP_HD int sp_class_unrolled_cells(int cls) { return cls <= 2 ? 2 * sp_class_bw(cls) + 1 : 0; }  // NC of sp_hmm2_instance
+SP_HD int sp_class_unrolled_cells(int cls) {  // NC of sp_hmm2_instance
+    return cls < SP_N_EXACT_CLASSES ? 2 * sp_class_bw(cls) + 1 : 0;
+}
 
 SP_HD int sp_min(int a, int b) { return a < b ? a : b; }
 SP_HD int sp_max(int a, int b) { return b < a ? a : b; }

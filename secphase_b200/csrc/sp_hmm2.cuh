@@ -36,6 +36,9 @@
 #ifndef SP_H2_NCRF
 #define SP_H2_NCRF 64  // forward: D of cells < NCRF in registers (clamped to NC)
 #endif
+#ifndef SP_H2_NCRF_WIDE
+#define SP_H2_NCRF_WIDE 24  // the same for the unrolled bodies of bands wider than 45 cells (register budget)
+#endif
 #ifndef SP_H2_NCRB
 #define SP_H2_NCRB -1  // backward: bI of cells < NCRB in registers; -1 = no unrolled backward body at all
 #endif
@@ -165,7 +168,8 @@ SP_HD int sp_query_decode(const SpHmmIn &in, int i0, uint32_t raw) {
 // lives in registers and every cell index is a compile-time constant, which removes a third of
 // the shared-memory traffic and all per-chunk address / mask arithmetic.  full_warp says that all
 // 32 lanes are inside this function (the fast path takes warp-uniform decisions by vote).
-template <int STRIDE, int NW, int NC, int FS_CS = 2, int NCRF_ = SP_H2_NCRF, int NCRB_ = SP_H2_NCRB>
+template <int STRIDE, int NW, int NC, int FS_CS = 2, int NCRF_ = (NC > 45 ? SP_H2_NCRF_WIDE : SP_H2_NCRF),
+          int NCRB_ = SP_H2_NCRB>
 SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<STRIDE> B, double *rinv, double *fsave,
                             int64_t fs_stride, SpRow *rows, int n_rows, bool full_warp) {
     constexpr int fs_cs = FS_CS;  // doubles between consecutive cells of a saved forward row

@@ -53,6 +53,9 @@ static void hs_hmm2_dispatch(const SpConst &C, const SpHmmIn &in, const SpBand2<
             case 41: sp_hmm2_instance<1, 1, 41, 64>(C, in, B, rinv, fl, rs, rows, n_rows, unrolled); return;
             case 43: sp_hmm2_instance<1, 1, 43, 64>(C, in, B, rinv, fl, rs, rows, n_rows, unrolled); return;
             case 45: sp_hmm2_instance<1, 1, 45, 64>(C, in, B, rinv, fl, rs, rows, n_rows, unrolled); return;
+            case 47: sp_hmm2_instance<1, 1, 47, 64>(C, in, B, rinv, fl, rs, rows, n_rows, unrolled); return;
+            case 49: sp_hmm2_instance<1, 1, 49, 64>(C, in, B, rinv, fl, rs, rows, n_rows, unrolled); return;
+            case 51: sp_hmm2_instance<1, 1, 51, 64>(C, in, B, rinv, fl, rs, rows, n_rows, unrolled); return;
             default: break;
         }
         switch (sp_h2_words(sp_class_bw(cls))) {
@@ -66,6 +69,9 @@ static void hs_hmm2_dispatch(const SpConst &C, const SpHmmIn &in, const SpBand2<
         case 41: sp_hmm2_instance<1, 1, 41>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
         case 43: sp_hmm2_instance<1, 1, 43>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
         case 45: sp_hmm2_instance<1, 1, 45>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
+        case 47: sp_hmm2_instance<1, 1, 47>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
+        case 49: sp_hmm2_instance<1, 1, 49>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
+        case 51: sp_hmm2_instance<1, 1, 51>(C, in, B, rinv, fsave, fss, rows, n_rows, unrolled); return;
         default: break;
     }
     switch (sp_h2_words(sp_class_bw(cls))) {
