@@ -20,7 +20,20 @@ cat $out/${tag}_bench_ref.json
 for p in ont stress; do
   timeout 300 python tools/stage_bench.py --preset $p --groups 2048 >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
 done
+timeout 300 python tools/stage_bench.py --preset hifi --groups 4096 --write-qual >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
 cat $out/${tag}_stage.json
+# pipelined throughput of the other BASELINE configs (ONT, stress): bench.py --preset, 3 batches in flight
+( timeout 300 python bench.py --preset ont --groups 8192 --locus-len 20000000 --steps 9 --warmup 3 --no-cpu-baseline ) > $out/${tag}_bench_ont.json 2> $out/${tag}_bench_ont.err
+( timeout 300 python bench.py --preset stress --groups 8192 --locus-len 20000000 --steps 6 --warmup 3 --no-cpu-baseline ) > $out/${tag}_bench_stress.json 2> $out/${tag}_bench_stress.err
+python - <<PY
+import json
+for n in ("ont", "stress"):
+    try:
+        d = json.load(open("$out/${tag}_bench_%s.json" % n))
+        print(n, "value %.0f e2e %.0f gcups %.1f" % (d["value"], d["e2e"]["value"], d["gcups"]), d["config"]["sm_partition"])
+    except Exception as e:
+        print(n, "failed", e)
+PY
 ( timeout 400 python tools/cli_bench.py --groups 32768 ) > $out/${tag}_cli.json 2> $out/${tag}_cli.err
 tail -c 1500 $out/${tag}_cli.json
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv \
