@@ -101,9 +101,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def count(self, t0, t1=None):
+        return sum(1 for t, _ in self.lines if t >= t0 and (t1 is None or t <= t1))
+
+    def stop(self, t0=None, t1=None):
+        """Summary over the samples that arrived in [t0, t1] (the timed regions; default: all)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -112,7 +116,9 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if (t0 is not None and t < t0) or (t1 is not None and t > t1):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -259,10 +265,13 @@ def main():
         """CUDA-event time from the mark to the end of the last batch on any slot used by n steps."""
         return max(eng.elapsed_since_mark(s) for s in range(min(n, n_slots)))
 
-    resident_steps(args.warmup)
+    # nvidia-smi needs a second or two before its first sample: start it ahead of the warm-up and keep only
+    # the samples that arrive inside the measured phases
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    resident_steps(args.warmup)
+    barrier()
+    t_meas0 = time.perf_counter()
     eng.mark()
     t0 = time.perf_counter()
     stats = resident_steps(args.steps)
@@ -309,7 +318,12 @@ def main():
         r = eng.wait(0, copy=False)
         if i >= 2:
             iso.append(r)
-    clocks = sampler.stop()
+    # the measured phases are short (~1.5 s); if the sampler caught fewer than three readings under load,
+    # keep the same resident workload running (untimed) until it has
+    t_load1 = time.perf_counter()
+    while sampler.proc and sampler.count(t_meas0) < 3 and time.perf_counter() - t_load1 < 6.0:
+        resident_steps(n_slots)
+    clocks = sampler.stop(t_meas0, time.perf_counter())
     # ---- roofline denominators, measured live ------------------------------------------------
     dfma_ops, _ = eng.fp64_peak(0)
     dadd_ops, _ = eng.fp64_peak(1)

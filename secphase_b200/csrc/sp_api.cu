@@ -1026,7 +1026,8 @@ int sp_set_write_qual(sp_ctx *c, int on) {
     c->full_baq = on != 0;
     c->hC.full_baq = on != 0;
     CK(cudaMemcpy(c->dC.p, &c->hC, sizeof(SpConst), cudaMemcpyHostToDevice));
-    for (int s = 0; s < SP_N_SLOTS; s++) c->slot[s].state = c->slot[s].state == 1 ? 0 : c->slot[s].state;  // resident batches were planned for the other mode
+    for (int s = 0; s < SP_N_SLOTS; s++)
+        if (c->slot[s].state == 1) c->slot[s].state = 0;  // an uploaded (resident) batch was planned for the other mode
     return SP_OK;
 }
 
