@@ -34,12 +34,35 @@ if ROOT not in sys.path:
 # three slots x five streams per context: enough hardware queues that they do not alias (must be in
 # the environment before the first CUDA call of the process, which is torch's)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+# stdout carries exactly one JSON line: NCCL's debug output goes to stderr (its version banner is a
+# plain printf, see _claim_stdout)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
 FLOP_PER_CELL = 41  # 19 forward + 18 backward + 4 MAP
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """From here on file descriptor 1 points at stderr, so nothing a library prints (NCCL's version banner,
+    torchrun notices) can land on stdout; emit_line() writes the one JSON line to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def parse_args():
@@ -200,12 +223,13 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": "read-groups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
 def main():
     args = parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -418,7 +442,7 @@ def main():
                                           "thread pool over read groups",
                                 "gcups": c / dt / 1e9, "seconds": dt}
     if rank == 0:
-        print(json.dumps(line))
+        emit_line(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
