@@ -175,6 +175,26 @@ int hs_hmm2(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *qu
     return 0;
 }
 
+// Signature of the batch plan (every table offset) computed with n_threads text-scan threads: the plan must
+// not depend on the thread count.
+uint64_t hs_plan_sig(const sp_flat_batch *b, int indel_threshold, int safe_caps, int n_threads, int *rc_out) {
+    SpPlan pl;
+    const int rc = sp_make_plan(b, indel_threshold, safe_caps != 0, pl, n_threads);
+    if (rc_out) *rc_out = rc;
+    if (rc != SP_OK) return 0;
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {
+        const uint8_t *q = (const uint8_t *) p;
+        for (size_t i = 0; i < n; i++) h = (h ^ q[i]) * 1099511628211ull;
+    };
+    mix(pl.aln_grp.data(), 4 * pl.aln_grp.size()); mix(pl.ops_off.data(), 8 * pl.ops_off.size());
+    mix(pl.imk_off.data(), 8 * pl.imk_off.size()); mix(pl.cb_cap.data(), 4 * pl.cb_cap.size());
+    mix(pl.gpos_off.data(), 8 * pl.gpos_off.size()); mix(pl.gent_off.data(), 8 * pl.gent_off.size());
+    mix(pl.gblk_off.data(), 8 * pl.gblk_off.size()); mix(pl.giv_off.data(), 8 * pl.giv_off.size());
+    mix(pl.gblk_cap.data(), 4 * pl.gblk_cap.size());
+    return h;
+}
+
 // Diagnostic: refined-op / initial-marker counts of every alignment against the planned capacities.
 int hs_walk_stats(const sp_flat_batch *b, const sp_params *p, int32_t *out /* [A][5]: n_ops, cap, n_imk, cap, err */) {
     SpConst C;

@@ -47,6 +47,8 @@ def lib():
         L.hs_run2.argtypes = [C.POINTER(CFlatBatch), C.POINTER(SpParams), C.c_void_p, C.c_void_p, C.c_int,
                               C.c_int, C.c_uint, C.c_int, C.c_void_p]
         L.hs_run2.restype = C.c_int
+        L.hs_plan_sig.argtypes = [C.POINTER(CFlatBatch), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.hs_plan_sig.restype = C.c_uint64
         L.hs_qual.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.hs_qual.restype = C.POINTER(C.c_uint8)
         for name, rt in [("group", C.c_int32), ("score", C.c_double), ("extent", C.c_int32),
@@ -155,3 +157,11 @@ def hmm(params, ref, query, par_bw, rows_t, want_s=False):
     if want_s:
         out["s"] = s
     return out
+
+
+def plan_signature(batch, indel_threshold, n_threads, safe_caps=False):
+    """(rc, hash of every offset table of the batch plan) -- sp_make_plan with n_threads scan threads."""
+    cb = batch.as_c()
+    rc = C.c_int()
+    h = lib().hs_plan_sig(C.byref(cb), indel_threshold, 1 if safe_caps else 0, n_threads, C.byref(rc))
+    return rc.value, int(h)

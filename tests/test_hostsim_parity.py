@@ -54,6 +54,24 @@ def test_write_qual_mode_bit_exact_vs_oracle(hostsim, oracle, name, spreset, ppr
             assert np.array_equal(got["qual"][pos].astype(np.int32), rows[:, 3])
 
 
+@pytest.mark.parametrize("preset,over", [("hifi", {}), ("ont", {}), ("ont", dict(use_md=1)), ("stress", {})])
+def test_plan_independent_of_scan_threads(hostsim, preset, over):
+    """The launcher scans text-heavy batches (ONT) with several threads: same plan as with one."""
+    s, b, _, _ = make_case(preset, 37, locus_len=300000, **over)
+    thr = 20 if preset == "ont" else 10
+    rc1, h1 = hostsim.plan_signature(b, thr, 1)
+    assert rc1 == 0
+    for nt in (2, 3, 8, 64):
+        assert hostsim.plan_signature(b, thr, nt) == (0, h1)
+    assert hostsim.plan_signature(b, thr, 4, safe_caps=True)[0] == 0
+    assert hostsim.plan_signature(b.group_slice(0, 0), thr, 8)[0] == 0
+    # an unsupported CIGAR op is reported the same way from any thread
+    bad = b.group_slice(0, 12)
+    bad.cigar_pool = bad.cigar_pool.copy()
+    bad.cigar_pool[int(bad.cigar_off[5])] = (7 << 4) | 3   # 7N
+    assert hostsim.plan_signature(bad, thr, 1)[0] == hostsim.plan_signature(bad, thr, 8)[0] == -6   # SP_EUNSUPPORTED
+
+
 def test_glibc_rand_emulation(hostsim):
     import ctypes
     libc = ctypes.CDLL("libc.so.6")
