@@ -839,6 +839,10 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
     }
     if (P.G > 0 && T.n_items > 0) {
         k_emit<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC, S.items.as<SpItem>(), S.rows.as<SpRow>());
+        if (S.full_baq) {  // -w: k_emit laid out the windows only; their per-base rows are filled in parallel
+            k_fill_rows<<<(T.n_items * 32 + 255) / 256, 256, 0, st>>>(P, S.items.as<SpItem>(), T.n_items, S.rows.as<SpRow>());
+            S.launches++;
+        }
         const int nbins = (SP_N_CLASSES + 1) * SP_SORT_LBINS;
         CK(cudaMemsetAsync(S.bins.p, 0, 4 * (size_t) nbins, st));
         k_sort_hist<<<(T.n_items + 255) / 256, 256, 0, st>>>(S.items.as<SpItem>(), T.n_items, S.bins.as<int32_t>());
@@ -1309,6 +1313,8 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
         I.row0 = (int32_t) row_off[j];
         I.n_rows = (int32_t) (row_off[j + 1] - row_off[j]);
         I.query_off = query_off[j];
+        I.op_first = 0;
+        I.op_last = -1;
         I.s_off = s_total;
         s_total += l_query[j] + 2;
         if (ref_off[j] + l_ref[j] > ref_total) ref_total = ref_off[j] + l_ref[j];

@@ -349,48 +349,32 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
             // full_baq (--writeBam): one row per base of the write-back range t in [10, l_query-10)
             // (ptMarker.c:786), slot = first_row + t - 10; rows no M/=/X op visits keep
             // expected == SP_INT_MIN, i.e. bq = set_q (763-764).
+            // The rows themselves are then written by sp_fill_row (one thread per row) from the range of
+            // refined ops this loop examines, recorded in the SpItem.
             const bool full = C.full_baq != 0;
             if (full) {
                 n_rows = l_query - 2 * SP_BLOCK_MARGIN;
                 if (n_rows < 0) n_rows = 0;
-                if (EMIT) {
-                    for (int t = 0; t < n_rows; t++) {
-                        SpRow r;
-                        r.item = item_idx;
-                        r.t = t + SP_BLOCK_MARGIN;
-                        r.entry = -1;
-                        r.expected = SP_INT_MIN;
-                        r.state = 0;
-                        r.q = 0;
-                        r.pmax = 0.0;
-                        rows[first_row + t] = r;
-                    }
-                }
             }
             int jj = j;
+            const int op_first = o < 0 ? 0 : o;
+            int op_last = op_first - 1;
             // the bq loop, ptMarker.c:767-785
             while (it_sqs <= blk.sqe || it_rfs <= blk.rfe) {
                 int x = it_rfs - blk.rfs;
                 x = x < 0 ? 0 : x;
                 int y = it_sqs - blk.sqs;
                 y = y < 0 ? 0 : y;
+                if (o > op_last) op_last = o;
                 if (sp_op_is_match(it_op)) {
                     const int len = sp_min(it_len, sp_min(it_sqe, blk.sqe) - sp_max(it_sqs, blk.sqs) + 1);
-                    if (full && EMIT) {
-                        const int t1 = sp_min(y + len, l_query - SP_BLOCK_MARGIN);
-                        for (int t = sp_max(y, SP_BLOCK_MARGIN); t < t1; t++)
-                            rows[first_row + t - SP_BLOCK_MARGIN].expected = x + (t - y);
-                    }
                     // markers with t in [y, y+len)
                     while (SP_MK_VALID(jj) && SP_MK_BASE(jj) - blk.sqs < y) jj += jstep;
                     while (SP_MK_VALID(jj) && SP_MK_BASE(jj) - blk.sqs < y + len) {
                         const int t = SP_MK_BASE(jj) - blk.sqs;
                         if (t >= SP_BLOCK_MARGIN && t < l_query - SP_BLOCK_MARGIN - 1) {
                             if (full) {
-                                if (EMIT) {
-                                    rows[first_row + t - SP_BLOCK_MARGIN].entry = (int32_t) (entry_base + (int64_t) jj * n + i);
-                                    res[entry_base + (int64_t) jj * n + i] = first_row + t - SP_BLOCK_MARGIN;
-                                }
+                                if (EMIT) res[entry_base + (int64_t) jj * n + i] = first_row + t - SP_BLOCK_MARGIN;
                             } else {
                                 if (EMIT) {
                                     SpRow r;
@@ -437,6 +421,8 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
                 it.n_rows = n_rows;
                 it.query_off = -1;
                 it.s_off = s_base + cnt.s_doubles;
+                it.op_first = op_first;
+                it.op_last = op_last;
                 items[item_idx] = it;
             }
             cnt.n_items += 1;
@@ -459,4 +445,36 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
     }
 #undef SP_MK_VALID
 #undef SP_MK_BASE
+}
+
+// --writeBam mode: row k (query row t = k + 10) of an HMM window, as the bq loop of calc_local_baq sees
+// the base (ptMarker.c:767-785): `expected` = x + (t - y) if one of the refined ops that loop examined
+// (SpItem::op_first..op_last) is an M/=/X op covering the base, else SP_INT_MIN (bq stays set_q, 763-764).
+// One thread per row; the op is found by binary search on the ops' stored-SEQ starts.
+SP_HD SpRow sp_fill_row(const SpItem &it, int item_idx, int k, const SpOp *ops, bool rev, int blk_rfs) {
+    SpRow r;
+    r.item = item_idx;
+    r.t = k + SP_BLOCK_MARGIN;
+    r.entry = -1;
+    r.expected = SP_INT_MIN;
+    r.state = 0;
+    r.q = 0;
+    r.pmax = 0.0;
+    const int blk_sqs = it.q_sqs, blk_sqe = it.q_sqs + it.l_query - 1;
+    const int p = blk_sqs + r.t;
+    int lo = it.op_first, hi = it.op_last;  // last op in [lo, hi] with sqs <= p (zero-length ops sort before the op that owns the base)
+    if (lo > hi || ops[lo].sqs > p) return r;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (ops[mid].sqs <= p) lo = mid; else hi = mid - 1;
+    }
+    const SpOpView v = sp_op_view(ops, lo, rev);
+    if (!sp_op_is_match(v.op) || p > v.sqe) return r;
+    int x = v.rfs - blk_rfs;
+    x = x < 0 ? 0 : x;
+    int y = v.sqs - blk_sqs;
+    y = y < 0 ? 0 : y;
+    const int len = sp_min(v.len, sp_min(v.sqe, blk_sqe) - sp_max(v.sqs, blk_sqs) + 1);
+    if (r.t >= y && r.t < y + len) r.expected = x + (r.t - y);
+    return r;
 }

@@ -64,6 +64,7 @@ struct SpItem {  // one probaln_glocal call of calc_local_baq, ptMarker.c:725-75
     int32_t n_rows;
     int64_t query_off;  // stand-alone API: offset into a byte-per-base query pool; pipeline: -1
     int64_t s_off;      // this instance's slice of the scaling-factor pool (l_query+2 doubles)
+    int32_t op_first, op_last;  // refined ops the bq loop of ptMarker.c:767-785 examined for this window
 };
 
 struct SpRow {  // one query row whose MAP state/q is consumed (a marker inside an HMM window)

@@ -242,6 +242,18 @@ __global__ void __launch_bounds__(64) k_emit(SpBatchPtrs B, const SpConst *__res
     }
 }
 
+// -w mode: the rows of every HMM window (warp per instance, lane per row), see sp_fill_row
+__global__ void __launch_bounds__(256) k_fill_rows(SpBatchPtrs B, const SpItem *__restrict__ items, int n_items, SpRow *rows) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_items) return;
+    const SpItem it = items[w];
+    const int a = it.aln;
+    const SpOp *ops = B.ops + B.ops_off[a];
+    const bool rev = (B.flag[a] & SP_FREVERSE) != 0;
+    const int blk_rfs = (int) (it.ref_off - B.contig_off[B.tid[a]]);
+    for (int k = lane; k < it.n_rows; k += 32) rows[it.row0 + k] = sp_fill_row(it, w, k, ops, rev, blk_rfs);
+}
+
 // ---- instance ordering: key = class * LBINS + (LBINS-1 - min(l_query, LBINS-1)) --------------
 __device__ __forceinline__ int sp_item_key(const SpItem &it) {
     const int bw = sp_hmm_bw(it.l_ref, it.l_query, it.par_bw);

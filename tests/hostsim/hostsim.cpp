@@ -369,6 +369,15 @@ int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         }
         if (cnt.n_items != gcnt[g].n_items || cnt.n_rows != gcnt[g].n_rows) out->err |= 0x100;
     }
+    if (full_baq) {  // k_fill_rows
+        for (int w = 0; w < item_off[G]; w++) {
+            const SpItem &it = items[w];
+            const int a = it.aln;
+            const int blk_rfs = (int) (it.ref_off - contig_off[b->tid[a]]);
+            for (int k = 0; k < it.n_rows; k++)
+                rows[it.row0 + k] = sp_fill_row(it, w, k, ops.data() + pl.ops_off[a], (b->flag[a] & SP_FREVERSE) != 0, blk_rfs);
+        }
+    }
     // K4: one "lane" per item
     bool all_h2 = true;
     for (int it = 0; it < item_off[G]; it++) {
