@@ -414,6 +414,14 @@ void sp_destroy(sp_ctx *c) {
     }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+#ifdef SP_PROFILE_GROUP
+    {
+        unsigned long long h[8] = {};
+        cudaMemcpyFromSymbol(h, sp_prof, sizeof(h));
+        fprintf(stderr, "[secphase_b200:prof] thread-cycles: k_group markers %llu, consensus %llu, emit-count %llu; k_emit %llu\n",
+                h[0], h[1], h[2], h[3]);
+    }
+#endif
     for (int s = 0; s < SP_N_SLOTS; s++) {
         Slot &S = c->slot[s];
         DevBuf *bufs[] = {&S.d_in, &S.ops, &S.imk, &S.info, &S.blk, &S.iv, &S.nb, &S.gpos, &S.ent, &S.res, &S.baq,

@@ -99,9 +99,19 @@ __global__ void __launch_bounds__(128) k_walk(SpBatchPtrs B, const SpConst *__re
     B.nb[a] = info.n_cb;
 }
 
+#ifdef SP_PROFILE_GROUP  // tuning aid: clock64 split of the thread-per-group stages (summed over threads)
+__device__ unsigned long long sp_prof[8];
+#define SP_PROF_T0() long long prof_t = clock64()
+#define SP_PROF(k) do { long long t_ = clock64(); atomicAdd(&sp_prof[k], (unsigned long long) (t_ - prof_t)); prof_t = t_; } while (0)
+#else
+#define SP_PROF_T0() ((void) 0)
+#define SP_PROF(k) ((void) 0)
+#endif
+
 __global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__restrict__ Cp) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= B.G) return;
+    SP_PROF_T0();
     const SpConst &C = *Cp;
     SpGroupAlnView V = sp_make_view(B, g);
     SpGroupOut o;
@@ -112,6 +122,7 @@ __global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__re
     int32_t *gpos = B.gpos + B.gpos_off[g];
     SpEntry *ent = B.ent + B.gent_off[g];
     const int P = sp_group_markers(V, gpos, ent, (int) (B.gpos_off[g + 1] - B.gpos_off[g]), counts, &err);
+    SP_PROF(0);
     B.gP[g] = P;
     o.n_init = counts[0];
     o.n_after_allmm = counts[1];
@@ -130,6 +141,7 @@ __global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__re
     memset(&cnt, 0, sizeof(cnt));
     if (P > 0) {
         conf_len = sp_consensus_loop(C, V, P, gpos, W, &margin, &err);
+        SP_PROF(1);
         if (conf_len > 0 || !C.consensus) {
             scored = true;
             if (C.baq_flag) {
@@ -143,6 +155,7 @@ __global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__re
     } else {
         for (int i = 0; i < V.n; i++) W.nb[i] = 0;  // secphase.c:161: no markers, no confident blocks
     }
+    SP_PROF(2);
     B.gcnt[g] = cnt;
     o.margin_eff = margin;
     o.conf_len = conf_len;
@@ -230,6 +243,7 @@ __global__ void __launch_bounds__(64) k_emit(SpBatchPtrs B, const SpConst *__res
     const SpConst &C = *Cp;
     const SpGroupOut o = B.gout[g];
     if (!o.scored || !C.baq_flag) return;
+    SP_PROF_T0();
     SpGroupAlnView V = sp_make_view(B, g);
     SpEmitCounts cnt;
     memset(&cnt, 0, sizeof(cnt));
@@ -240,6 +254,7 @@ __global__ void __launch_bounds__(64) k_emit(SpBatchPtrs B, const SpConst *__res
                                 B.nb[a], B.contig_off[B.tid[a]], 0, cnt, B.res + B.gent_off[g], items,
                                 B.item_off[g], rows, B.row_off[g], B.sdbl_off[g]);
     }
+    SP_PROF(3);
 }
 
 // -w mode: the rows of every HMM window (warp per instance, lane per row), see sp_fill_row
