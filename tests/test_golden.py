@@ -21,6 +21,7 @@ def load(path):
     batch = FlatBatch(**{f: z["in_" + f] for f, _ in _FIELDS})
     exp = {t: (z["out_" + t].view(np.float64) if t == "scores" else z["out_" + t]) for t in OUT_TABLES}
     exp["hmm"] = z["out_hmm"]
+    exp["qual"] = z["out_qual"]
     lens = [int(x) for x in z["ref_lens"]]
     off = np.zeros(len(lens) + 1, np.int64)
     off[1:] = np.cumsum(lens)
@@ -40,6 +41,7 @@ def test_oracle_reproduces_golden(oracle, path):
     bad = compare_results(exp, got, label="oracle")
     assert not bad, "\n".join(bad)
     assert np.array_equal(exp["hmm"], got["hmm"])  # incl. the hashes of every state[] / q[] array
+    assert np.array_equal(exp["qual"], got["qual"])
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -50,6 +52,11 @@ def test_kernel_logic_on_host_reproduces_golden(oracle, path):
     assert got["err"] == 0
     bad = compare_results(exp, got, label="hostsim")
     assert not bad, "\n".join(bad)
+    # -w/--writeBam mode: the records' quality arrays
+    full = pyhostsim.run(batch, pyhostsim.params_from_oracle(oracle.preset_params(preset)), ASCII2CODE[ascii_], off,
+                         full_baq=True)
+    assert np.array_equal(full["qual"], exp["qual"])
+    assert not compare_results(exp, full, label="hostsim-full")
 
 
 @pytest.mark.gpu
@@ -69,3 +76,8 @@ def test_cuda_reproduces_golden(path):
         again = eng.run(secphase_b200.pin_batch(batch))
         assert np.array_equal(again["scores"].view(np.int64), exp["scores"].view(np.int64))
         assert np.array_equal(again["groups"], exp["groups"])
+        # -w/--writeBam mode: the records' quality arrays as the reference leaves them
+        eng.set_write_qual(True)
+        full = eng.run(batch)
+        assert np.array_equal(full["baq_qual"], exp["qual"])
+        assert np.array_equal(full["scores"].view(np.int64), exp["scores"].view(np.int64))

@@ -27,7 +27,8 @@ CASES = [
      dict(locus_len=60000, len_mean=5000, len_sd=2000, len_min=1500, clip_prob=0.9, hard_clip_prob=0.9, use_md=1)),
 ]
 OUT_TABLES = ["groups", "scores", "extents", "blocks", "block_off", "hmm", "markers_pre", "markers_pre_off",
-              "markers_baq", "markers_baq_off", "markers_final", "markers_final_off"]
+              "markers_baq", "markers_baq_off", "markers_final", "markers_final_off",
+              "qual"]  # qual: every record's quality array as the job leaves it (the -w/--writeBam output)
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
