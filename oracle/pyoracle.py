@@ -3,8 +3,14 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module; the product package (secphase_b200/) never does.
 
-kind="reference": oracle/_ref/libsecphase_ref.so -- the reference's own marker-path sources.
-kind="port":      oracle/liboracle_port.so       -- plain-C restatement (oracle/secphase_port.c).
+kind="reference": oracle/_ref/libsecphase_ref.so -- the reference's OWN marker-path sources (cigar_it.c,
+                  ptAlignment.c, ptMarker.c, ptBlock.c, common.c, compiled unmodified against oracle/shim)
+                  + the restated probaln_glocal (oracle/probaln_port.c).  Built where /root/reference is
+                  mounted; the .so travels with the repo snapshot to the GPU box.
+kind="port":      oracle/liboracle_port.so -- reserved for a plain-C restatement of the whole marker path
+                  exporting the same entry points (oracle/secphase_port.c, not written: the marker path is
+                  checked against the reference's own code instead, and against the golden fixtures that
+                  code wrote, tests/golden/, where the library is absent).
 """
 import ctypes as C
 import os

@@ -5,8 +5,8 @@
  *                                    (/root/reference/programs/submodules/{cigar_it,ptAlignment,
  *                                    ptMarker,ptBlock,common}/ *.c, compiled unmodified) + shim +
  *                                    probaln_port.c, driven the way secphase.c:156-219 drives them;
- *   oracle/liboracle_port.so         the plain-C restatement of the same path (oracle/secphase_port.c).
- * Both export the same entry points so tests can diff them against each other and against CUDA.
+ *   oracle/liboracle_port.so         reserved name for a plain-C restatement of the same path exporting the
+ *                                    same entry points (not written; see oracle/pyoracle.py).
  */
 #ifndef ORACLE_REF_DRIVER_H
 #define ORACLE_REF_DRIVER_H
