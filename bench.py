@@ -157,10 +157,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(synth, batches, preset, threads):
+def cpu_reference_run(synth, batches, preset, threads, keep=None):
     """Time the CPU oracle over `batches` (list of FlatBatch) with a thread pool over read groups
     (the reference's own parallelism: task-parallel over read groups, tpool.c).  Returns
-    (groups, cells, seconds, kind)."""
+    (groups, cells, seconds, kind).  keep: a dict that receives the oracle's scores and selected
+    indices in group order (used to check the GPU results of the same groups, never timed work)."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import pyoracle
@@ -181,12 +182,16 @@ def cpu_reference_run(synth, batches, preset, threads):
     def work(c):
         r = pyoracle.run(c, params, ref, kind=kind, seed=None)
         h = r["hmm"]
-        return int(h[:, 4].astype(np.int64).sum() + (h[:, 5].astype(np.int64) << 31).sum())
+        return int(h[:, 4].astype(np.int64).sum() + (h[:, 5].astype(np.int64) << 31).sum()), r["scores"], r["groups"][:, 0]
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
-        cells = sum(ex.map(work, chunks))
+        parts = list(ex.map(work, chunks))
     dt = time.perf_counter() - t0
+    cells = sum(p[0] for p in parts)
+    if keep is not None:
+        keep["scores"] = np.concatenate([p[1] for p in parts])
+        keep["best"] = np.concatenate([p[2] for p in parts])
     return sum(b.n_groups for b in batches), cells, dt, kind
 
 
@@ -433,14 +438,29 @@ def main():
         dt = 0.0
         kind = "port"
         i = 0
+        parity = None
         while dt < 12.0 and i < 8:
             sample = batches[i % len(batches)].group_slice(0, n_cpu)
-            g1, c1, dt1, kind = cpu_reference_run(synth, [sample], params_preset(args), threads)
+            keep = {} if i == 0 else None
+            g1, c1, dt1, kind = cpu_reference_run(synth, [sample], params_preset(args), threads, keep=keep)
             g, c, dt, i = g + g1, c + c1, dt + dt1, i + 1
+            if keep is not None:
+                # the same read groups through the GPU path: alignment scores (bit patterns) and the selected
+                # alignment must equal the reference's -- at the benchmark's own batch size
+                gpu = eng.run(sample, slot=0)
+                same_s = bool(np.array_equal(gpu["scores"].view(np.int64), keep["scores"].view(np.int64)))
+                # (stress: several secondaries can tie, and the reference then draws from an unseeded rand())
+                same_b = bool(np.array_equal(gpu["groups"][:, 0], keep["best"])) if args.preset != "stress" else None
+                parity = {"read_groups_checked": int(sample.n_groups), "alignments_checked": int(sample.n_alns),
+                          "scores_bit_exact": same_s, "selected_alignment_equal": same_b,
+                          "selected_secondaries": int((gpu["groups"][:, 0] != gpu["groups"][:, 1]).sum())}
+                if not same_s or same_b is False:
+                    sys.stderr.write("bench.py: GPU results differ from the CPU reference on the checked batch\n")
         line["cpu_baseline"] = {"value": g / dt, "unit": "read-groups/s", "cores": threads, "kind": kind,
                                 "sample": f"{i} x the first {n_cpu} read groups of a step ({g} groups, {dt:.1f} s), "
                                           "thread pool over read groups",
                                 "gcups": c / dt / 1e9, "seconds": dt}
+        line["parity_vs_cpu_reference"] = parity
     if rank == 0:
         emit_line(line)
     eng.close()
