@@ -136,7 +136,8 @@ int sp_poll(sp_ctx *ctx, int slot);
  * rows only, and sp_wait returns the modified quality arrays in sp_result.baq_qual.  Scores,
  * markers and the selected alignment are unchanged by the mode.  Costs ~700 B of HBM per window
  * row while a batch is in flight: submit smaller batches (the CLI uses 512 read groups).
- * Must be called with no batch in flight. */
+ * Must be called with no batch in flight; batches uploaded with sp_upload before the switch have to
+ * be uploaded again, and results of completed batches must have been read. */
 int sp_set_write_qual(sp_ctx *ctx, int on);
 
 /* Device-side stopwatch over several batches (bench.py): sp_mark records a CUDA event on slot 0's

@@ -1038,8 +1038,10 @@ int sp_set_write_qual(sp_ctx *c, int on) {
     c->full_baq = on != 0;
     c->hC.full_baq = on != 0;
     CK(cudaMemcpy(c->dC.p, &c->hC, sizeof(SpConst), cudaMemcpyHostToDevice));
+    // staged / resident batches were planned (tables, row counts) for the other mode: they must be
+    // uploaded again before they can run, and their result tables are no longer handed out
     for (int s = 0; s < SP_N_SLOTS; s++)
-        if (c->slot[s].state == 1) c->slot[s].state = 0;  // an uploaded (resident) batch was planned for the other mode
+        if (c->slot[s].state == 1 || c->slot[s].state == 3) c->slot[s].state = 0;
     return SP_OK;
 }
 
