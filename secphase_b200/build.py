@@ -62,6 +62,7 @@ HOST_LIB = os.path.join(LIBDIR, "libsecphase_host.so")
 BINDIR = os.path.join(os.path.dirname(HERE), "bin")
 CLI = os.path.join(BINDIR, "secphase")
 CORRECT_BAM = os.path.join(BINDIR, "correct_bam")  # consumer of out.log (programs/src/correct_bam.c)
+INDEX_TOOL = os.path.join(BINDIR, "secphase_index")  # programs/src/secphase_index.c
 HOST_SRCS = ["sph_common.cpp", "sph_bgzf.cpp", "sph_bam.cpp", "sph_fasta.cpp", "sph_output.cpp", "sph_sam.cpp"]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-pthread"]
 
@@ -89,6 +90,9 @@ def build_host(force=False):
     if force or _stale(CORRECT_BAM, [cb_main, HOST_LIB] + hdrs):
         subprocess.check_call([cxx] + CXX_FLAGS + ["-o", CORRECT_BAM, cb_main, "-L" + LIBDIR, "-lsecphase_host", "-lz",
                                                   "-Wl,-rpath,$ORIGIN/../secphase_b200/lib"])
+    ix_main = os.path.join(HOST, "secphase_index_main.cpp")
+    if force or _stale(INDEX_TOOL, [ix_main]):
+        subprocess.check_call([cxx] + CXX_FLAGS + ["-o", INDEX_TOOL, ix_main, "-lz"])
     return HOST_LIB, CLI
 
 
