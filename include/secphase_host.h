@@ -147,6 +147,8 @@ int64_t sph_format_sam_record(char *buf, int64_t cap, const uint8_t *rec, int64_
  * sph_batch_keep_records on. */
 typedef struct sph_samw sph_samw;
 sph_samw *sph_samw_open(const char *path, const sph_bam *header_from);
+/* the same with `threads` workers formatting the records of each batch in parallel (output unchanged) */
+sph_samw *sph_samw_open_mt(const char *path, const sph_bam *header_from, int threads);
 int sph_samw_write_batch(sph_samw *w, const sph_batch *b, const uint8_t *baq_qual);
 int sph_samw_close(sph_samw *w); /* also frees w */
 

@@ -448,7 +448,7 @@ int main(int argc, char *argv[]) {
     sph_samw *bam_fo = nullptr;  // secphase.c:643-657
     if (write_bam) {
         std::string p = dirPath + "/" + prefix + ".quality_modified.out.bam";
-        bam_fo = sph_samw_open(p.c_str(), bam);
+        bam_fo = sph_samw_open_mt(p.c_str(), bam, threads);
         if (!bam_fo) {
             fprintf(stderr, "[%s] Error: %s\n", get_timestamp(), sph_last_error());
             return 1;

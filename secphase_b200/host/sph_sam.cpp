@@ -10,7 +10,9 @@
 // with integer types folded to 'i' and floats printed with %g.
 #include <cerrno>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -181,7 +183,8 @@ struct sph_samw {
     FILE *fp = nullptr;
     std::vector<std::string> names;
     std::vector<const char *> name_ptr;
-    std::string buf;
+    std::unique_ptr<WorkerPool> pool;  // formats the records of a batch in parallel (text is ~2.5 bytes per base)
+    std::vector<std::string> parts;
 };
 
 extern "C" {
@@ -198,7 +201,9 @@ int64_t sph_format_sam_record(char *buf, int64_t cap, const uint8_t *rec, int64_
     return (int64_t) s.size();
 }
 
-sph_samw *sph_samw_open(const char *path, const sph_bam *hdr) {
+sph_samw *sph_samw_open(const char *path, const sph_bam *hdr) { return sph_samw_open_mt(path, hdr, 1); }
+
+sph_samw *sph_samw_open_mt(const char *path, const sph_bam *hdr, int threads) {
     if (!path || !hdr) return nullptr;
     FILE *fp = fopen(path, "w");
     if (!fp) {
@@ -207,6 +212,7 @@ sph_samw *sph_samw_open(const char *path, const sph_bam *hdr) {
     }
     sph_samw *w = new sph_samw();
     w->fp = fp;
+    if (threads > 1) w->pool.reset(new WorkerPool(threads));
     const int32_t n = sph_bam_n_targets(hdr);
     for (int32_t i = 0; i < n; i++) w->names.emplace_back(sph_bam_target_name(hdr, i));
     for (const std::string &nm : w->names) w->name_ptr.push_back(nm.c_str());
@@ -239,19 +245,32 @@ int sph_samw_write_batch(sph_samw *w, const sph_batch *b, const uint8_t *baq_qua
         set_error("sph_samw_write_batch: the batch was read without sph_batch_keep_records");
         return SPH_EINVAL;
     }
-    w->buf.clear();
-    for (int32_t a = 0; a < v->n_alns; a++) {
-        if (!format_record(w->buf, pool + off[a], off[a + 1] - off[a], (int32_t) w->names.size(), w->name_ptr.data(),
-                           baq_qual ? baq_qual + v->qual_off[a] : nullptr)) {
-            set_error("malformed BAM record (alignment %d of the batch)", a);
+    // records are formatted in chunks (in parallel when the writer has a pool) and written in order
+    const int32_t chunk = 16;
+    const int64_t n_chunks = ((int64_t) v->n_alns + chunk - 1) / chunk;
+    w->parts.resize((size_t) n_chunks);
+    std::vector<int32_t> bad((size_t) n_chunks, -1);
+    auto work = [&](int64_t k) {
+        std::string &out = w->parts[(size_t) k];
+        out.clear();
+        const int32_t a1 = std::min<int64_t>(v->n_alns, (k + 1) * chunk);
+        for (int32_t a = (int32_t) (k * chunk); a < a1; a++)
+            if (!format_record(out, pool + off[a], off[a + 1] - off[a], (int32_t) w->names.size(), w->name_ptr.data(),
+                               baq_qual ? baq_qual + v->qual_off[a] : nullptr)) {
+                bad[(size_t) k] = a;
+                return;
+            }
+    };
+    if (w->pool) w->pool->parallel_for(n_chunks, work);
+    else for (int64_t k = 0; k < n_chunks; k++) work(k);
+    for (int64_t k = 0; k < n_chunks; k++) {
+        if (bad[(size_t) k] >= 0) {
+            set_error("malformed BAM record (alignment %d of the batch)", bad[(size_t) k]);
             return SPH_EFORMAT;
         }
-        if (w->buf.size() > ((size_t) 8 << 20)) {
-            if (fwrite(w->buf.data(), 1, w->buf.size(), w->fp) != w->buf.size()) return SPH_EIO;
-            w->buf.clear();
-        }
+        const std::string &out = w->parts[(size_t) k];
+        if (!out.empty() && fwrite(out.data(), 1, out.size(), w->fp) != out.size()) return SPH_EIO;
     }
-    if (!w->buf.empty() && fwrite(w->buf.data(), 1, w->buf.size(), w->fp) != w->buf.size()) return SPH_EIO;
     return SPH_OK;
 }
 

@@ -98,6 +98,8 @@ def lib():
     L.sph_format_sam_record.restype = C.c_int64
     L.sph_samw_open.argtypes = [C.c_char_p, C.c_void_p]
     L.sph_samw_open.restype = C.c_void_p
+    L.sph_samw_open_mt.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    L.sph_samw_open_mt.restype = C.c_void_p
     L.sph_samw_write_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sph_samw_close.argtypes = [C.c_void_p]
     _lib = L
@@ -314,8 +316,8 @@ def format_sam_record(rec, names, qual=None):
 class SamWriter:
     """<prefix>.quality_modified.out.bam of secphase.c:643-657 (SAM text, see sph_sam.cpp)."""
 
-    def __init__(self, path, reader):
-        self._w = lib().sph_samw_open(os.fsencode(path), reader._h)
+    def __init__(self, path, reader, threads=1):
+        self._w = lib().sph_samw_open_mt(os.fsencode(path), reader._h, threads)
         if not self._w:
             raise HostError(_err())
 

@@ -46,7 +46,7 @@ def test_records_kept_and_formatted(tmp_path, monkeypatch, preset, over):
     exp_lines = []
     a_base = g_base = 0
     with hostlib.BamReader(p, threads=3, keep_records=True) as r:
-        w = hostlib.SamWriter(out, r)
+        w = hostlib.SamWriter(out, r, threads=1 if preset == "hifi" else 4)
         while True:
             fb = r.next_batch(7)
             if fb is None:
