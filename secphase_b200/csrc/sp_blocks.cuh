@@ -325,7 +325,20 @@ SP_HD void sp_emit_alignment(const SpConst &C, const SpGroupAlnView &G, int i, i
     }
     for (int b = 0; b < n_blocks; b++) {
         const SpBlock blk = blocks[b];
+        // advance to the first op that reaches the block in both coordinates (ptMarker.c:703-705).  The ops'
+        // ends only grow along the table, so after a few steps the rest of the way is bisected: ONT
+        // alignments have ~130 refined ops between consecutive windows, HiFi ~5.
+        int skipped = 0;
         while (it_sqe < blk.sqs || it_rfe < blk.rfs) {
+            if (++skipped > 8 && o + 2 < n_ops) {
+                int lo = o + 1, hi = n_ops - 1;  // first op in [lo, hi] with sqe >= blk.sqs and rfe >= blk.rfs, hi if none
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const SpOp nx = ops[mid + 1];
+                    if (nx.sqs - 1 >= blk.sqs && nx.rfs - 1 >= blk.rfs) hi = mid; else lo = mid + 1;
+                }
+                o = lo - 1;
+            }
             if (it_next() == 0) break;
         }
         while (SP_MK_VALID(j) && SP_MK_BASE(j) < blk.sqs + SP_BLOCK_MARGIN) {
