@@ -20,6 +20,25 @@ struct SpIv {  // interval in read-forward coordinates
 };
 
 SP_HD void sp_sort_blocks_by_rds(SpBlock *b, int n) {
+    // The lists arrive sorted by stored-SEQ start, i.e. ascending in read-forward coordinates for a forward
+    // alignment (nothing to do) and strictly descending for a reverse one (reverse in place: same result as
+    // the insertion sort below, which would need n^2/2 moves for it -- a quarter of the block traffic of the
+    // margin loop on read groups with many secondaries).
+    bool asc = true, desc = true;
+    for (int i = 1; i < n; i++) {
+        const bool gt = b[i - 1].rds_f > b[i].rds_f;
+        asc = asc && !gt;
+        desc = desc && gt;
+    }
+    if (asc) return;
+    if (desc) {
+        for (int i = 0, j = n - 1; i < j; i++, j--) {
+            const SpBlock t = b[i];
+            b[i] = b[j];
+            b[j] = t;
+        }
+        return;
+    }
     for (int i = 1; i < n; i++) {
         SpBlock x = b[i];
         int j = i - 1;
