@@ -194,7 +194,7 @@ int main(int argc, char *argv[]) {
             fprintf(stderr, "[%s] Error: truncated BAM record\n", get_timestamp());
             return 1;
         }
-        const size_t l_qname = rec[8];
+        const size_t l_qname = std::min<size_t>(rec[8], block_size - 32);  // never past the record
         const std::string name((const char *) rec.data() + 32, strnlen((const char *) rec.data() + 32, l_qname));
         if (!have_first) {
             first_name = name;
