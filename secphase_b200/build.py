@@ -63,7 +63,7 @@ BINDIR = os.path.join(os.path.dirname(HERE), "bin")
 CLI = os.path.join(BINDIR, "secphase")
 CORRECT_BAM = os.path.join(BINDIR, "correct_bam")  # consumer of out.log (programs/src/correct_bam.c)
 INDEX_TOOL = os.path.join(BINDIR, "secphase_index")  # programs/src/secphase_index.c
-HOST_SRCS = ["sph_common.cpp", "sph_bgzf.cpp", "sph_bam.cpp", "sph_fasta.cpp", "sph_output.cpp", "sph_sam.cpp"]
+HOST_SRCS = ["sph_common.cpp", "sph_bgzf.cpp", "sph_inflate.cpp", "sph_bam.cpp", "sph_fasta.cpp", "sph_output.cpp", "sph_sam.cpp"]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-pthread"]
 
 

@@ -199,6 +199,8 @@ bool BgzfReader::fill(Chunk *c) {
     std::atomic<int> bad{0};
     const uint8_t *comp = comp_.data();
     uint8_t *dst = c->buf;
+    static const bool use_zlib_only = getenv("SPH_ZLIB_INFLATE") != nullptr;
+    const size_t comp_cap = comp_.size();
     pool_->parallel_for((nb + per - 1) / per, [&](int64_t t) {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
@@ -208,6 +210,11 @@ bool BgzfReader::fill(Chunk *c) {
         }
         for (int64_t i = t * per; i < std::min(nb, (t + 1) * per); i++) {
             const BlockRef &r = blocks[(size_t) i];
+            // fast path (sph_inflate.cpp), accepted only with a matching CRC32; anything else goes to zlib below
+            if (!use_zlib_only && r.comp_off + r.comp_len + 8 <= comp_cap &&
+                fast_inflate(comp + r.comp_off, r.comp_len, dst + r.uoff, r.ulen) &&
+                (uint32_t) crc32(crc32(0L, Z_NULL, 0), dst + r.uoff, r.ulen) == r.crc)
+                continue;
             zs.next_in = const_cast<Bytef *>(comp + r.comp_off);
             zs.avail_in = r.comp_len;
             zs.next_out = dst + r.uoff;

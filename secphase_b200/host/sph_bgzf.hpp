@@ -59,6 +59,11 @@ private:
     std::string err_text_;
 };
 
+// Raw-deflate decoder for one whole BGZF block (sph_inflate.cpp): true iff exactly out_len bytes were
+// produced from a well-formed stream.  `in` must have 8 readable bytes after in_len.  Callers verify the
+// CRC32 and fall back to zlib on false.
+bool fast_inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
+
 // Buffers written bytes and emits them as BGZF blocks of <= 0xff00 payload bytes, deflated in
 // parallel on the pool; close() appends the 28-byte end-of-file marker.
 class BgzfWriter {
