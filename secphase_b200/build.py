@@ -76,6 +76,8 @@ def build_host(force=False):
     `secphase` executable that links it together with libsecphase_b200.so."""
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(BINDIR, exist_ok=True)
+    if not os.path.exists(LIB):  # the secphase executable links the GPU library: build it first
+        build()
     cxx = os.environ.get("CXX", "g++")
     inc = [os.path.join(os.path.dirname(HERE), "include", f) for f in ("secphase_host.h", "secphase_b200.h", "sp_flat_batch.h")]
     hdrs = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + inc
