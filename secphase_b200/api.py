@@ -102,6 +102,12 @@ def load_library(path=None):
     L.sp_sm_partition.restype = C.c_int
     L.sp_set_write_qual.argtypes = [C.c_void_p, C.c_int]
     L.sp_set_write_qual.restype = C.c_int
+    L.sp_poll.argtypes = [C.c_void_p, C.c_int]
+    L.sp_poll.restype = C.c_int
+    L.sp_mark.argtypes = [C.c_void_p]
+    L.sp_mark.restype = C.c_int
+    L.sp_elapsed_since_mark.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+    L.sp_elapsed_since_mark.restype = C.c_int
     L.sp_rng_seed.argtypes = [C.c_void_p, C.c_uint]
     L.sp_rng_next.argtypes = [C.c_void_p]
     L.sp_rng_next.restype = C.c_int

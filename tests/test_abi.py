@@ -31,6 +31,19 @@ def test_library_exports_every_declared_symbol():
     assert set(secphase_b200.api.EXPORTED_SYMBOLS) == set(declared_functions())
 
 
+def test_every_binding_is_typed():
+    """ctypes passes an untyped Python int as a 32-bit C int, which truncates a 64-bit sp_ctx*: every
+    entry point that takes arguments must have argtypes set by load_library()."""
+    import secphase_b200
+    L = secphase_b200.load_library()
+    for name in secphase_b200.api.EXPORTED_SYMBOLS:
+        fn = getattr(L, name)
+        if name in ("sp_last_error", "sp_version"):  # no parameters
+            assert fn.restype is ctypes.c_char_p
+            continue
+        assert fn.argtypes is not None, f"{name}: argtypes not set"
+
+
 def test_host_library_exports_every_declared_symbol():
     """include/secphase_host.h <-> libsecphase_host.so (BAM/FASTA ingest, BED/out.log writers)."""
     from secphase_b200 import hostlib
