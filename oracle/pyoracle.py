@@ -88,6 +88,8 @@ def _load(kind):
         L.oracle_out_save.restype = C.c_int
         L.oracle_merge_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
         L.oracle_merge_blocks.restype = C.c_int64
+        L.oracle_select.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OracleParams), C.c_void_p]
+        L.oracle_select.restype = C.c_int
     L.oracle_out_markers.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
     L.oracle_out_markers.restype = C.POINTER(C.c_int32)
     L.oracle_out_marker_off.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
@@ -140,6 +142,23 @@ def merge_blocks(rows, mode):
     k = L.oracle_merge_blocks(rows.ctypes.data, len(rows), mode, out.ctypes.data, cap)
     assert k <= cap
     return out[:k]
+
+
+def select(grp_aln_off, flag, scores, params, seed=1):
+    """The reference's own get_best_record_index over already-scored groups, in group order, with one
+    rand() stream seeded like a fresh process (srand(1) == never seeded): the selection a single-worker
+    run of the reference makes.  Needs kind="reference"."""
+    L = _load("reference")
+    gao = np.ascontiguousarray(grp_aln_off, np.int32)
+    fl = np.ascontiguousarray(flag, np.int32)
+    sc = np.ascontiguousarray(scores, np.float64)
+    best = np.zeros(len(gao) - 1, np.int32)
+    if seed is not None:
+        L.oracle_srand(seed)
+    rc = L.oracle_select(len(gao) - 1, gao.ctypes.data, fl.ctypes.data, sc.ctypes.data, C.byref(params), best.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"oracle_select failed: {rc}")
+    return best
 
 
 def run(batch, params, refseq, kind=None, keep_hmm=False, seed=1, outputs=None):

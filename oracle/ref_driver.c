@@ -183,6 +183,30 @@ const int64_t *oracle_out_marker_off(const oracle_out *o, int stage, int64_t *n)
 const char *oracle_kind(void) { return "reference"; }
 void oracle_srand(unsigned seed) { srand(seed); }
 
+/* The reference's own get_best_record_index (ptAlignment.c:137-177) replayed over already-scored
+ * groups in group order with the process's rand() stream: lets a multi-threaded oracle run (whose
+ * rand() draws interleave arbitrarily) be given the selection a single-worker run would make. */
+int oracle_select(int32_t n_groups, const int32_t *grp_aln_off, const int32_t *flag, const double *score,
+                  const oracle_params *p, int32_t *best_out) {
+    ptAlignment store[16];
+    bam1_t recs[16];
+    ptAlignment *alns[16];
+    for (int32_t g = 0; g < n_groups; g++) {
+        const int a0 = grp_aln_off[g], n = grp_aln_off[g + 1] - a0;
+        if (n < 1 || n > 16) return -1;
+        for (int i = 0; i < n; i++) {
+            memset(&store[i], 0, sizeof(store[i]));
+            memset(&recs[i], 0, sizeof(recs[i]));
+            recs[i].core.flag = (uint16_t) flag[a0 + i];
+            store[i].record = &recs[i];
+            store[i].score = score[a0 + i];
+            alns[i] = &store[i];
+        }
+        best_out[g] = get_best_record_index(alns, n, p->prim_margin_score, (double) p->min_score, p->prim_margin_random);
+    }
+    return 0;
+}
+
 /* ---------------------------------------------------------------- helpers */
 static uint32_t fnv32(const void *p, size_t n) {
     const uint8_t *b = (const uint8_t *) p;

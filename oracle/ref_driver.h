@@ -42,6 +42,9 @@ void oracle_out_destroy(oracle_out *o);
 /* run every group of `b` in order; rand() state is whatever the process has (see oracle_srand) */
 int oracle_run(const sp_flat_batch *b, const oracle_params *p, const oracle_refseq *ref, oracle_out *out);
 void oracle_srand(unsigned seed);
+/* get_best_record_index (ptAlignment.c:137-177) over scored groups, in order, on the current rand() stream */
+int oracle_select(int32_t n_groups, const int32_t *grp_aln_off, const int32_t *flag, const double *score,
+                  const oracle_params *p, int32_t *best_out);
 
 /* Text outputs (reference kind only): after oracle_out_enable_outputs, oracle_run also does what
  * secphase.c:194-216 does for every group whose selected alignment is a secondary, with the

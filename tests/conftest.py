@@ -50,4 +50,17 @@ CASES = [
     ("ont_short_hardclip", "ont", "ont", 60,
      dict(locus_len=300000, len_mean=8000, len_sd=3000, len_min=1500, clip_prob=0.9, hard_clip_prob=0.9)),
     ("hifi_md", "hifi", "hifi", 60, dict(locus_len=300000, use_md=1)),
+    # several secondaries tie at the top score: the rand() tie-break (ptAlignment.c:156-170) is exercised
+    ("stress_ties", "stress", "hifi", 48, dict(locus_len=300000, snv_rate=1e-4, indel_rate=2e-5, long_indel_rate=2e-6)),
 ]
+
+
+def count_top_score_ties(batch, scores):
+    """Read groups in which more than one secondary holds the maximum secondary score."""
+    t = 0
+    for g in range(batch.n_groups):
+        a0, a1 = int(batch.grp_aln_off[g]), int(batch.grp_aln_off[g + 1])
+        sec = [scores[a] for a in range(a0, a1) if batch.flag[a] & 256]
+        if len(sec) > 1 and sec.count(max(sec)) > 1:
+            t += 1
+    return t

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from tests.conftest import CASES, make_case, oracle_refseq
+from tests.conftest import CASES, count_top_score_ties, make_case, oracle_refseq
 from tools.parity import compare_results
 
 pytestmark = pytest.mark.gpu
@@ -28,6 +28,35 @@ def test_pipeline_bit_exact_vs_oracle(sp, oracle, name, spreset, ppreset, ng, ov
     cells = int(exp["hmm"][:, 4].astype(np.int64).sum() + (exp["hmm"][:, 5].astype(np.int64) << 31).sum())
     assert got["hmm_cells"] == cells
     assert got["gpu_launches"] >= 5
+
+
+def test_top_score_ties_follow_the_reference_rand_stream(sp, oracle):
+    """Several secondaries with the same top score: the reference picks rand() % count of them
+    (ptAlignment.c:156-170) on a never-seeded glibc stream.  The case must really contain ties, the
+    selection must equal the reference's own get_best_record_index in group order, and a group's
+    selection must not depend on how the batch was cut (the stream position is carried over)."""
+    name, spreset, ppreset, ng, over = [c for c in CASES if c[0] == "stress_ties"][0]
+    s, b, codes, off = make_case(spreset, ng, **over)
+    ref = oracle_refseq(oracle, s)
+    op = oracle.preset_params(ppreset)
+    exp = oracle.run(b, op, ref)
+    n_ties = count_top_score_ties(b, exp["scores"])
+    assert n_ties >= 1, "the tie case holds no tie"
+    with sp.Secphase(ppreset) as eng:
+        eng.set_reference_codes(codes, off)
+        got = eng.run(b)
+    assert np.array_equal(got["scores"].view(np.int64), exp["scores"].view(np.int64))
+    assert np.array_equal(got["groups"][:, 0], exp["groups"][:, 0])
+    assert np.array_equal(got["groups"][:, 0], oracle.select(b.grp_aln_off, b.flag, exp["scores"], op))
+    tied_swaps = int((got["groups"][:, 0] != got["groups"][:, 1]).sum())
+    assert tied_swaps >= 1
+    with sp.Secphase(ppreset) as eng:  # two batches on two slots: one rand() stream in submission order
+        eng.set_reference_codes(codes, off)
+        h = ng // 2
+        eng.submit(b.group_slice(0, h), slot=0)
+        eng.submit(b.group_slice(h, ng), slot=1)
+        parts = [eng.wait(0), eng.wait(1)]
+    assert np.array_equal(np.concatenate([p["groups"][:, 0] for p in parts]), exp["groups"][:, 0])
 
 
 @pytest.mark.parametrize("name,spreset,ppreset,ng,over", CASES, ids=[c[0] for c in CASES])

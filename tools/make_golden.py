@@ -25,6 +25,10 @@ CASES = [
      dict(locus_len=60000, len_mean=8000, len_sd=2000, len_min=3000, eqx=1, n_rate=2e-4, clip_prob=0.8)),
     ("ont_hardclip_md", "ont", "ont", 10,
      dict(locus_len=60000, len_mean=5000, len_sd=2000, len_min=1500, clip_prob=0.9, hard_clip_prob=0.9, use_md=1)),
+    # near-identical repeat copies: several secondaries share the top score, so get_best_record_index draws
+    # rand() % count (ptAlignment.c:156-170) -- pins the tie-break replay
+    ("stress_ties", "stress", "hifi", 12,
+     dict(locus_len=60000, len_mean=7000, len_sd=2000, len_min=3000, snv_rate=1e-4, indel_rate=2e-5, long_indel_rate=2e-6)),
 ]
 OUT_TABLES = ["groups", "scores", "extents", "blocks", "block_off", "hmm", "markers_pre", "markers_pre_off",
               "markers_baq", "markers_baq_off", "markers_final", "markers_final_off",
@@ -39,7 +43,10 @@ def main():
         pyoracle.build()
     assert "reference" in pyoracle.available_kinds(), "oracle/_ref needs /root/reference"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = set(sys.argv[1:])  # `python tools/make_golden.py <name>...` (re)writes just those fixtures
     for name, spreset, ppreset, ng, over in CASES:
+        if only and name not in only:
+            continue
         s = Synth(default_cfg(spreset, **over))
         b = s.generate(0, ng)
         ref = pyoracle.make_refseq(s.names, [s.contig_ptr(i) for i in range(s.n_contigs)], s.lens)
