@@ -122,6 +122,34 @@ def test_write_qual_without_consensus_long_windows(sp, oracle):
     assert int(exp["hmm"][:, 2].max()) > 2046 or len(exp["hmm"]) == 0
 
 
+def test_reference_windows_beyond_2_32(sp, oracle):
+    """BASELINE configs[3] addressing (a 2 x 3.1 Gb assembly is a 6.2 GB replica per GPU): with 18 filler
+    contigs of N (4.32e9 codes > 2^32) ahead of the real ones, every window the kernels fetch -- contig_off,
+    SpItem::ref_off, the HMM's reference pointer -- lies beyond 32 bits.  Results must equal the
+    reference's on the un-shifted assembly (fai_fetch of {ctg}:s-e addresses by contig, ptMarker.c:736-744)."""
+    import copy
+    s, b, codes, off = make_case("hifi", 40, locus_len=300000)
+    exp = oracle.run(b, oracle.preset_params("hifi"), oracle_refseq(oracle, s), keep_hmm=False)
+    n_fill, fill_len = 18, 240_000_000
+    big = np.empty(n_fill * fill_len + len(codes), np.uint8)
+    big[:n_fill * fill_len] = 4
+    big[n_fill * fill_len:] = codes
+    off2 = np.concatenate([np.arange(n_fill, dtype=np.int64) * fill_len, off + n_fill * fill_len])
+    assert off2[n_fill] > 2 ** 32
+    b2 = copy.copy(b)
+    b2.tid = (b.tid + n_fill).astype(np.int32)
+    with sp.Secphase("hifi") as eng:
+        eng.set_reference_codes(big, off2)
+        del big
+        got = eng.run_debug(b2)
+        bad = compare_results(exp, got, label="cuda-6GB-replica")
+        assert not bad, "\n".join(bad)
+        assert got["hmm_instances"] == len(exp["hmm"]) > 0
+        eng.set_write_qual(True)
+        full = eng.run(b2)
+        assert np.array_equal(full["baq_qual"], exp["qual"])
+
+
 def test_reference_ascii_upload_matches_codes(sp, oracle):
     s, b, codes, off = make_case("hifi", 30, locus_len=200000, n_rate=1e-3)
     with sp.Secphase("hifi") as e1, sp.Secphase("hifi") as e2:
