@@ -164,7 +164,11 @@ int sp_run_resident(sp_ctx *ctx, int slot);
  *   2 consensus blocks     [n][SP_BLOCK_W],  off per alignment
  *   3 HMM instances        [n][SP_HMM_W],    off = NULL
  *   4 HMM marker rows      [n][4] = instance, row t, state, q ; off = NULL
- * Returns the number of rows, or a negative error.  Pointers are host memory owned by ctx. */
+ * Returns the number of rows, or a negative error.  Pointers are host memory owned by ctx.
+ * Test switches (rows/off ignored): what = -1 keeps the post-BAQ table of later batches; what = -2 returns
+ * how many batches were re-run with the provable table bounds so far (SP_ECAPACITY is only reported when
+ * that second run overflows too); what <= -100 clamps the FIRST plan's per-group block workspace to
+ * -(what+100) entries so that tests can force that retry. */
 int64_t sp_debug_table(sp_ctx *ctx, int slot, int what, const int32_t **rows, const int64_t **off);
 
 /* --- the HMM alone, batch form of probaln_glocal(ref,l_ref,query,l_query,iqual,&conf,state,q)

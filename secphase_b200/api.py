@@ -288,6 +288,14 @@ class Secphase:
     def enable_debug_tables(self):
         self._L.sp_debug_table(self._h, 0, -1, None, None)
 
+    def debug_force_block_cap(self, cap):
+        """Tests: clamp the first plan's per-group block workspace to `cap` entries (0 = off), which makes the
+        kernels flag SP_GERR_BLOCK_CAP and sp_wait re-run the batch with the provable bounds."""
+        self._L.sp_debug_table(self._h, 0, -100 - int(cap), None, None)
+
+    def cap_retries(self):
+        return int(self._L.sp_debug_table(self._h, 0, -2, None, None))
+
     def debug_table(self, what, slot=0):
         rows = C.POINTER(C.c_int32)()
         off = C.POINTER(C.c_int64)()

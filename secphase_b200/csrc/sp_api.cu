@@ -106,6 +106,7 @@ struct Slot {
     int n_copies = 0;
     SpPlan plan;
     bool safe_caps = false;
+    size_t off_gblk_cap = 0, off_gblk_off = 0, off_giv_off = 0;  // plan-derived sections inside h_in / d_in
     // device work tables
     DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, item_off, row_off, sdbl_off, score,
         fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out, set_base;
@@ -146,6 +147,8 @@ struct sp_ctx {
     Slot slot[SP_N_SLOTS];
     SpRng rng;
     bool debug_tables = false;
+    int test_block_cap = 0;  // tests: first plan clamps every group's block workspace to this (forces the retry)
+    int64_t cap_retries = 0;
     bool full_baq = false;  // sp_set_write_qual: --writeBam mode
     bool streams_ready = false;  // ensure_streams
     int sm_count = 0;
@@ -566,7 +569,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
         const unsigned hw = std::thread::hardware_concurrency();
         plan_threads = hw >= 16 ? 8 : hw >= 4 ? (int) hw / 2 : 1;
     }
-    int rc = sp_make_plan(b, c->par.indel_threshold, S.safe_caps, S.plan, plan_threads);
+    int rc = sp_make_plan(b, c->par.indel_threshold, S.safe_caps, S.plan, plan_threads, c->test_block_cap);
     if (rc != SP_OK) {
         set_err("malformed batch (code %d): groups need 1..%d alignments, CIGAR ops limited to MIDSH=X", rc,
                 SP_MAX_ALN_PER_GROUP);
@@ -580,6 +583,9 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
         }
     }
     InLayout L = make_layout(b, pl);
+    S.off_gblk_cap = L.gblk_cap.off;
+    S.off_gblk_off = L.gblk_off.off;
+    S.off_giv_off = L.giv_off.off;
     rc = S.h_in.ensure(L.total);
     if (rc) return rc;
     rc = S.d_in.ensure(L.total);
@@ -960,6 +966,42 @@ static int enqueue_results(Slot &S) {
     return SP_OK;
 }
 
+// A batch whose kernels flagged SP_GERR_BLOCK_CAP (the tight per-group bound on consensus blocks was not
+// enough, sp_plan.h) is laid out again with the provable bound and run once more from the walk.  The
+// pools are already on the device and the per-group counts are kept in the plan, so this needs neither
+// the caller's buffers nor another pass over the text: only the three plan-derived offset tables are
+// rewritten and the metadata section is copied again.  Blocking; called from sp_wait.
+static int rerun_with_safe_caps(sp_ctx *c, Slot &S) {
+    S.safe_caps = true;
+    uint8_t *h = S.h_in.as<uint8_t>();
+    int rc = sp_plan_block_caps(S.plan, reinterpret_cast<const int32_t *>(h), true);  // grp_aln_off is the first section
+    if (rc) {
+        set_err("block workspace of the safe plan does not fit");
+        return rc;
+    }
+    const SpPlan &pl = S.plan;
+    const size_t G = (size_t) pl.G;
+    memcpy(h + S.off_gblk_cap, pl.gblk_cap.data(), 4 * G);
+    memcpy(h + S.off_gblk_off, pl.gblk_off.data(), 8 * (G + 1));
+    memcpy(h + S.off_giv_off, pl.giv_off.data(), 8 * (G + 1));
+    if ((rc = S.blk.ensure(sizeof(SpBlock) * (size_t) (pl.total_blk + 1)))) return rc;
+    if ((rc = S.iv.ensure(sizeof(SpIv) * (size_t) (pl.total_iv + 1)))) return rc;
+    S.P.blk = S.blk.as<SpBlock>();
+    S.P.iv = S.iv.as<SpIv>();
+    CK(cudaMemcpyAsync(S.d_in.p, S.h_in.p, S.meta_bytes, cudaMemcpyHostToDevice, S.stream));
+    const int launches = S.launches;
+    if ((rc = run_phase_a(c, S))) return rc;
+    hand_to_launcher(c, (int) (&S - c->slot));
+    if ((rc = await_phase_b(c, S))) {
+        cudaStreamSynchronize(S.stream);
+        return rc;
+    }
+    CK(cudaStreamSynchronize(S.stream));
+    S.launches += launches;
+    c->cap_retries++;
+    return SP_OK;
+}
+
 extern "C" {
 
 int sp_submit(sp_ctx *c, const sp_flat_batch *b, int slot) {
@@ -1114,6 +1156,13 @@ int sp_wait(sp_ctx *c, int slot, sp_result *out) {
     }
     CK(cudaStreamSynchronize(S.stream));
     SpTotals T = *S.h_tot.as<SpTotals>();
+    if ((T.err & SP_GERR_BLOCK_CAP) && !(T.err & SP_GERR_BADOP) && !S.safe_caps) {
+        if (int rrc = rerun_with_safe_caps(c, S)) {
+            S.state = 3;
+            return rrc;
+        }
+        T = *S.h_tot.as<SpTotals>();
+    }
     // second, exact-size copy: the compact final-marker table
     int rc = S.h_fin.ensure(24 * (size_t) (T.fin_rows + 1));
     if (rc) return rc;
@@ -1200,6 +1249,11 @@ int64_t sp_debug_table(sp_ctx *c, int slot, int what, const int32_t **rows_out, 
         c->debug_tables = true;
         return 0;
     }
+    if (what <= -100) {  // tests: clamp the first plan's block workspaces to -(what+100) entries per list
+        c->test_block_cap = -(what + 100);
+        return 0;
+    }
+    if (what == -2) return c->cap_retries;  // batches re-run with the provable bounds so far
     if (!rows_out) return SP_EINVAL;
     if (cudaSetDevice(c->device) != cudaSuccess) return SP_ECUDA;
     Slot &S = c->slot[slot];

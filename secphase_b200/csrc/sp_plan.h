@@ -35,6 +35,7 @@ struct SpPlan {
     std::vector<int64_t> gblk_off;  // [G+1] SpBlock workspace: n lists of gblk_cap[g]
     std::vector<int64_t> giv_off;   // [G+1] SpIv workspace: 3 lists of gblk_cap[g]
     std::vector<int32_t> gblk_cap;  // [G]
+    std::vector<int64_t> g_msum, g_cbsum;  // [G] the bounds gblk_cap was derived from (sp_plan_block_caps)
     int64_t total_ops = 0, total_imk = 0, total_pos = 0, total_ent = 0, total_blk = 0, total_iv = 0;
 };
 
@@ -90,8 +91,32 @@ inline void sp_count_alignment(const sp_flat_batch *b, int a, int indel_threshol
     o.nmis = nmis;
 }
 
+// Block / interval workspaces of every group from the per-group bounds: the tight cap, or (safe) the
+// provable one.  Needs nothing but the counts, so a batch whose kernels flagged SP_GERR_BLOCK_CAP can
+// be laid out again without another pass over its text.
+inline int sp_plan_block_caps(SpPlan &pl, const int32_t *grp_aln_off, bool safe_caps, int test_cap = 0) {
+    int64_t blk = 0, iv = 0;
+    for (int g = 0; g < pl.G; g++) {
+        const int64_t n = grp_aln_off[g + 1] - grp_aln_off[g], P = pl.g_msum[(size_t) g], cbsum = pl.g_cbsum[(size_t) g];
+        int64_t cap = safe_caps ? n * P + cbsum + 2 * n + 8 : P + cbsum + 2 * n + 8;
+        if (test_cap > 0 && !safe_caps && cap > test_cap) cap = test_cap;  // tests: force the retry path
+        if (cap > 0x3fffffff) return SP_ENOMEM;
+        pl.gblk_cap[(size_t) g] = (int32_t) cap;
+        pl.gblk_off[(size_t) g] = blk;
+        blk += cap * n;
+        pl.giv_off[(size_t) g] = iv;
+        iv += cap * 3;
+    }
+    pl.gblk_off[(size_t) pl.G] = blk;
+    pl.giv_off[(size_t) pl.G] = iv;
+    pl.total_blk = blk;
+    pl.total_iv = iv;
+    return SP_OK;
+}
+
 // returns SP_OK or a negative error.  n_threads > 1: the per-alignment text scan runs on that many threads.
-inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_caps, SpPlan &pl, int n_threads = 1) {
+inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_caps, SpPlan &pl, int n_threads = 1,
+                        int test_cap = 0) {
     const int G = b->n_groups, A = b->n_alns;
     if (G < 0 || A < 0) return SP_EINVAL;
     pl.G = G;
@@ -105,6 +130,8 @@ inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_c
     pl.gblk_off.assign((size_t) G + 1, 0);
     pl.giv_off.assign((size_t) G + 1, 0);
     pl.gblk_cap.assign((size_t) G, 0);
+    pl.g_msum.assign((size_t) G, 0);
+    pl.g_cbsum.assign((size_t) G, 0);
     for (int g = 0; g < G; g++) {
         const int a0 = b->grp_aln_off[g], a1 = b->grp_aln_off[g + 1];
         const int n = a1 - a0;
@@ -125,7 +152,7 @@ inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_c
     } else {
         for (int a = 0; a < A; a++) sp_count_alignment(b, a, indel_threshold, cnt[(size_t) a]);
     }
-    int64_t ops = 0, imk = 0, pos = 0, ent = 0, blk = 0, iv = 0;
+    int64_t ops = 0, imk = 0, pos = 0, ent = 0;
     for (int g = 0; g < G; g++) {
         const int a0 = b->grp_aln_off[g], a1 = b->grp_aln_off[g + 1];
         const int n = a1 - a0;
@@ -143,31 +170,22 @@ inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_c
             cbsum += c.cb;
         }
         const int64_t P = msum;
-        int64_t cap = safe_caps ? (int64_t) n * P + cbsum + 2 * n + 8 : P + cbsum + 2 * n + 8;
-        if (cap > 0x3fffffff) return SP_ENOMEM;
-        pl.gblk_cap[(size_t) g] = (int32_t) cap;
+        pl.g_msum[(size_t) g] = msum;
+        pl.g_cbsum[(size_t) g] = cbsum;
         pl.gpos_off[(size_t) g] = pos;
         pos += P;
         pl.gent_off[(size_t) g] = ent;
         ent += P * n;
-        pl.gblk_off[(size_t) g] = blk;
-        blk += cap * n;
-        pl.giv_off[(size_t) g] = iv;
-        iv += cap * 3;
     }
     pl.ops_off[(size_t) A] = ops;
     pl.imk_off[(size_t) A] = imk;
     pl.gpos_off[(size_t) G] = pos;
     pl.gent_off[(size_t) G] = ent;
-    pl.gblk_off[(size_t) G] = blk;
-    pl.giv_off[(size_t) G] = iv;
     pl.total_ops = ops;
     pl.total_imk = imk;
     pl.total_pos = pos;
     pl.total_ent = ent;
-    pl.total_blk = blk;
-    pl.total_iv = iv;
-    return SP_OK;
+    return sp_plan_block_caps(pl, b->grp_aln_off, safe_caps, test_cap);
 }
 
 // ---- constants the device must not derive itself (host libm / C float semantics) ------------

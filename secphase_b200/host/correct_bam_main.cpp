@@ -314,7 +314,10 @@ int main(int argc, char *argv[]) {
             if (!in.need(o + 4)) { fprintf(stderr, "Error: truncated BAM header\n"); return 1; }
             const uint32_t l_name = le32(in.buf.data() + in.pos + o);
             if (!in.need(o + 4 + l_name + 4)) { fprintf(stderr, "Error: truncated BAM header\n"); return 1; }
-            names.emplace_back((const char *) in.buf.data() + in.pos + o + 4);
+            {  // the name is NUL-terminated inside l_name bytes in a well-formed file; never read past them
+                const char *nm = (const char *) in.buf.data() + in.pos + o + 4;
+                names.emplace_back(nm, l_name ? strnlen(nm, l_name) : 0);
+            }
             o += 4 + (size_t) l_name + 4;
         }
         header.assign(in.buf.begin() + (ptrdiff_t) in.pos, in.buf.begin() + (ptrdiff_t) (in.pos + o));

@@ -35,6 +35,7 @@
 #include <cstring>
 #include <ctime>
 #include <deque>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -196,12 +197,17 @@ struct Shared {
     std::mutex mu;
     std::string error;  // first fatal error
     bool failed = false;
+    // called once, by the first failing thread: closes the pipeline's queues so that every thread blocked
+    // on one of them (reader on free_q, an idle GPU thread on work_q) wakes up and winds down
+    std::function<void()> on_fail;
     void fail(const std::string &msg) {
-        std::lock_guard<std::mutex> g(mu);
-        if (!failed) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (failed) return;
             failed = true;
             error = msg;
         }
+        if (on_fail) on_fail();
     }
     bool is_failed() {
         std::lock_guard<std::mutex> g(mu);
@@ -403,10 +409,26 @@ int main(int argc, char *argv[]) {
         sph_bam_set_contig_limits(bam, lim.data());
     }
 
-    // one context per device (there is no CPU path: sp_create fails without a GPU)
+    // one context per device (there is no CPU path: sp_create fails without a GPU).  SECPHASE_B200_DEVICES
+    // ("0,0", "2,3", ...) maps context k to a CUDA device: lets --gpus N be exercised on fewer physical GPUs
+    // (two contexts on one device behave exactly like two devices to everything above the C ABI).
+    std::vector<int> dev_of((size_t) n_gpus);
+    for (int d = 0; d < n_gpus; d++) dev_of[(size_t) d] = d;
+    if (const char *e = getenv("SECPHASE_B200_DEVICES")) {
+        int k = 0;
+        for (const char *q = e; *q && k < n_gpus;) {
+            dev_of[(size_t) k++] = atoi(q);
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+    }
+    // test hook: SECPHASE_B200_FAIL_AT="<ctx>,<n>" makes GPU thread <ctx> report a failure instead of
+    // submitting its n-th batch (the error path of a multi-device run must end with exit code 1, not hang)
+    int fail_ctx = -1, fail_at = -1;
+    if (const char *e = getenv("SECPHASE_B200_FAIL_AT")) sscanf(e, "%d,%d", &fail_ctx, &fail_at);
     std::vector<sp_ctx *> ctx((size_t) n_gpus, nullptr);
     for (int d = 0; d < n_gpus; d++) {
-        ctx[(size_t) d] = sp_create(&par, d);
+        ctx[(size_t) d] = sp_create(&par, dev_of[(size_t) d]);
         if (!ctx[(size_t) d]) {
             fprintf(stderr, "[%s] Error: cannot initialise GPU %d: %s\n", get_timestamp(), d, sp_last_error());
             return 1;
@@ -437,6 +459,10 @@ int main(int argc, char *argv[]) {
     Queue<sph_batch *> free_q;
     Queue<Work> work_q;
     Queue<Done *> done_q;
+    shared.on_fail = [&] {
+        work_q.close();
+        free_q.close();
+    };
     const int n_batches = n_gpus * (SP_N_SLOTS + 1) + 2;
     std::vector<sph_batch *> all_batches;
     for (int i = 0; i < n_batches; i++) {
@@ -521,6 +547,7 @@ int main(int argc, char *argv[]) {
             };
             Work w;
             bool ok = true;
+            int n_submitted = 0;
             for (;;) {
                 if (shared.is_failed()) break;
                 // with batches in flight never block on the reader: retire finished ones meanwhile
@@ -543,6 +570,11 @@ int main(int argc, char *argv[]) {
                     continue;
                 }
                 if ((int) inflight.size() == SP_N_SLOTS && !(ok = collect())) break;
+                if (d == fail_ctx && n_submitted++ == fail_at) {
+                    shared.fail(std::string("GPU ") + std::to_string(d) + ": injected failure (SECPHASE_B200_FAIL_AT)");
+                    ok = false;
+                    break;
+                }
                 int64_t t0 = now_us();
                 int src = sp_submit(cx, sph_batch_view(w.hb), next_slot);
                 submit_us += now_us() - t0;
@@ -618,7 +650,9 @@ int main(int argc, char *argv[]) {
     Done *dn = nullptr;
     while (done_q.pop(dn)) {
         parked[dn->seq] = dn;
-        while (!parked.empty() && parked.begin()->first == next_seq) {
+        // after a failure the batch a dead GPU thread held never arrives: nothing more is emitted, later
+        // batches are dropped as they come (their buffers are freed with all_batches below)
+        while (!parked.empty() && (parked.begin()->first == next_seq || shared.is_failed())) {
             Done *d2 = parked.begin()->second;
             parked.erase(parked.begin());
             if (!shared.is_failed()) emit(d2);

@@ -136,10 +136,35 @@ def test_cli_contig_order_and_extra_contigs(tmp_path, oracle):
 
 
 @pytest.mark.gpu
-def test_cli_two_gpus_same_output(tmp_path, oracle):
+def _two_contexts_env():
+    """--gpus 2 on this box: two physical devices when present, else two contexts on device 0
+    (SECPHASE_B200_DEVICES; above the C ABI the two cases are the same code path)."""
     import torch
+    env = dict(os.environ)
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+        env["SECPHASE_B200_DEVICES"] = "0,0"
+    return env
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_failure_exits_instead_of_hanging(tmp_path):
+    """A GPU thread that fails must not leave the reader, the other GPU thread and the ordered output
+    waiting on each other: the run ends with the error on stderr and exit code 1."""
+    s, b, _, _ = make_case("hifi", 200, locus_len=300000)
+    bam, fa = str(tmp_path / "in.bam"), str(tmp_path / "asm.fa")
+    hostlib.write_bam(bam, s.names, s.lens, b)
+    hostlib.write_fasta(fa, s.names, [s.contig_ptr(i) for i in range(s.n_contigs)], s.lens)
+    for where in ("0,1", "1,0", "1,3"):
+        env = dict(_two_contexts_env(), SECPHASE_B200_FAIL_AT=where)
+        r = subprocess.run([CLI, "-i", bam, "-f", fa, "-o", str(tmp_path / ("f" + where.replace(",", "_"))), "--hifi",
+                            "--gpus", "2", "--batchGroups", "16"], capture_output=True, text=True, timeout=120, env=env)
+        assert r.returncode == 1, (where, r.stderr[-500:])
+        assert "injected failure" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_same_output(tmp_path, oracle):
+    env2 = _two_contexts_env()
     s, b, _, _ = make_case("hifi", 200, locus_len=300000)
     bam, fa = str(tmp_path / "in.bam"), str(tmp_path / "asm.fa")
     hostlib.write_bam(bam, s.names, s.lens, b)
@@ -147,10 +172,12 @@ def test_cli_two_gpus_same_output(tmp_path, oracle):
     outs = []
     for n in (1, 2):
         d = tmp_path / f"g{n}"
-        r = run_cli(["-i", bam, "-f", fa, "-o", str(d), "--hifi", "--gpus", str(n), "--batchGroups", "16"])
+        r = run_cli(["-i", bam, "-f", fa, "-o", str(d), "--hifi", "--gpus", str(n), "--batchGroups", "16"], env=env2)
         assert r.returncode == 0, r.stderr
         outs.append([(d / f"secphase.{f}").read_bytes() for f in OUT_FILES])
+        assert f'"gpus": {n}' in r.stderr
     assert outs[0] == outs[1]
+    assert len(outs[0][0]) > 0  # out.log is not empty: secondaries were selected
 
 
 @pytest.mark.gpu

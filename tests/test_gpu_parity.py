@@ -122,6 +122,36 @@ def test_write_qual_without_consensus_long_windows(sp, oracle):
     assert int(exp["hmm"][:, 2].max()) > 2046 or len(exp["hmm"]) == 0
 
 
+@pytest.mark.parametrize("name", ["hifi", "stress"])
+def test_block_capacity_retry(sp, oracle, name):
+    """A batch whose kernels overflow the tight per-group bound on consensus blocks is re-run inside sp_wait
+    with the provable bound (sp_plan.h); the caller sees the same results, not SP_ECAPACITY.  The overflow is
+    forced by clamping the first plan's workspaces; submit and resident paths, and a second batch after it."""
+    _, spreset, ppreset, ng, over = [c for c in CASES if c[0] == name][0]
+    s, b, codes, off = make_case(spreset, ng, **over)
+    exp = oracle.run(b, oracle.preset_params(ppreset), oracle_refseq(oracle, s), keep_hmm=False)
+    with sp.Secphase(ppreset) as eng:
+        eng.set_reference_codes(codes, off)
+        eng.debug_force_block_cap(2)
+        got = eng.run_debug(b)
+        assert eng.cap_retries() == 1
+        bad = compare_results(exp, got, label="cuda-after-retry")
+        assert not bad, "\n".join(bad)
+        eng.upload(b, slot=1)
+        eng.run_resident(1)
+        r2 = eng.wait(1)
+        assert eng.cap_retries() == 2
+        assert np.array_equal(r2["scores"].view(np.int64), exp["scores"].view(np.int64))
+        eng.run_resident(1)  # the slot now holds the safe plan: no further retry
+        r3 = eng.wait(1)
+        assert eng.cap_retries() == 2
+        assert np.array_equal(r3["scores"].view(np.int64), exp["scores"].view(np.int64))
+        eng.debug_force_block_cap(0)
+        r4 = eng.run(b, slot=2)
+        assert eng.cap_retries() == 2
+        assert np.array_equal(r4["scores"].view(np.int64), exp["scores"].view(np.int64))
+
+
 def test_reference_windows_beyond_2_32(sp, oracle):
     """BASELINE configs[3] addressing (a 2 x 3.1 Gb assembly is a 6.2 GB replica per GPU): with 18 filler
     contigs of N (4.32e9 codes > 2^32) ahead of the real ones, every window the kernels fetch -- contig_off,

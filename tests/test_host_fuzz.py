@@ -107,3 +107,32 @@ def test_tools_survive_malformed_records(tmp_path):
         assert r.returncode in (0, 1), (p, r.returncode, r.stderr[-300:])      # a signal would be negative
         r = subprocess.run([INDEX_TOOL, "-i", p, "--stepSize", "2"], capture_output=True, text=True, timeout=60)
         assert r.returncode in (0, 1), (p, r.returncode, r.stderr[-300:])
+
+
+def test_header_name_without_terminator(tmp_path):
+    """A reference name with no NUL inside its l_name bytes (malformed header): correct_bam and the reader take
+    exactly l_name bytes instead of reading on through l_ref and the records (run under ASan in a debug build;
+    here: no crash, and the records still come out)."""
+    import gzip
+    s, b, _, _ = make_case("hifi", 4, locus_len=100000, len_mean=3000, len_sd=500, len_min=1500)
+    src = str(tmp_path / "src.bam")
+    hostlib.write_bam(src, s.names, s.lens, b)
+    raw = bytearray(gzip.open(src, "rb").read())
+    o = 8 + struct.unpack_from("<i", raw, 4)[0]
+    n_ref = struct.unpack_from("<i", raw, o)[0]
+    o += 4
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", raw, o)[0]
+        assert raw[o + 4 + l_name - 1] == 0
+        raw[o + 4 + l_name - 1] = ord("X")   # the terminator becomes part of the name
+        o += 4 + l_name + 4
+    p = str(tmp_path / "noterm.bam")
+    bgzf_write(p, bytes(raw))
+    if not os.path.exists(CORRECT_BAM):
+        from secphase_b200.build import build_host
+        build_host()
+    r = subprocess.run([CORRECT_BAM, "-i", p, "-o", str(tmp_path / "o.bam"), "-m", "0", "-a", "0"],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode in (0, 1), (r.returncode, r.stderr[-300:])
+    with hostlib.BamReader(p, threads=1) as rd:
+        assert all(n.endswith("X") and "\0" not in n for n in rd.names)
