@@ -1,0 +1,65 @@
+#!/bin/bash
+# One GPU-box visit: `gpurun --timeout T -- 'bash tools/gpu_visit.sh <tag> <step>...'`
+# steps: test smoke bench ref ncu_launch ncu_hmm cli cli2 stage
+tag=$1; shift
+out=gpurun_out
+mkdir -p $out
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_smi.txt 2>&1
+nproc >> $out/${tag}_smi.txt
+for step in "$@"; do
+case $step in
+test)
+  ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $out/${tag}_pytest_gpu.log 2>&1
+  tail -5 $out/${tag}_pytest_gpu.log ;;
+smoke)
+  ( timeout 300 python __graft_entry__.py smoke ) > $out/${tag}_smoke.log 2>&1
+  tail -2 $out/${tag}_smoke.log ;;
+bench)
+  ( time timeout 900 python bench.py ) > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+  tail -3 $out/${tag}_bench.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("$out/${tag}_bench.json"))
+    r = d["roofline"]
+    print("value %.0f e2e %.0f kernel_ms %.2f frac %.3f mode %s rerun %s" % (d["value"], d["e2e"]["value"], r["kernel_ms_per_step"], r["frac"], r.get("hmm_mode"), r.get("strict_rerun_instances_per_step")))
+    print("parity", d.get("parity_vs_cpu_reference"))
+    for k, v in d.get("per_config", {}).items():
+        if "error" in v: print(k, v); continue
+        p = v.get("parity_vs_cpu_reference") or {}
+        print(k, "value %.0f e2e %.0f frac %.3f kernel_ms %.2f wall %.0fs" % (v["value"], v["e2e"]["value"], v["roofline"]["frac"], v["roofline"]["kernel_ms_per_step"], v["wall_s"]), v["stage_ms_isolated"], "all_equal", p.get("all_equal"), "ties", p.get("groups_with_tied_top_secondaries"), p.get("mismatches"))
+except Exception as e:
+    print("bench parse failed", e)
+PY
+  ;;
+benchq)  # the bench line only (no CPU legs)
+  ( timeout 600 python bench.py --no-cpu-baseline ) > $out/${tag}_benchq.json 2> $out/${tag}_benchq.err
+  tail -c 900 $out/${tag}_benchq.json ;;
+ref)
+  ( timeout 400 python bench.py --impl reference --steps 3 --warmup 1 ) > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
+  cat $out/${tag}_bench_ref.json ;;
+stage)
+  for p in hifi ont stress; do
+    timeout 300 python tools/stage_bench.py --preset $p --groups 2048 >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
+  done
+  timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
+  cat $out/${tag}_stage.json ;;
+cli)
+  ( timeout 500 python tools/cli_bench.py --groups 32768 ) > $out/${tag}_cli.json 2> $out/${tag}_cli.err
+  tail -c 1200 $out/${tag}_cli.json ;;
+ncu_launch)
+  timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/${tag}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_launch.log 2>&1 ;;
+ncu_hmm)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_hmm -s 8 -c 16 -f -o $out/${tag}_k_hmm \
+    python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --iters 1 > $out/${tag}_ncu_full.log 2>&1 ;;
+ncu_int)
+  for p in ont stress; do
+    timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_walk|k_group|k_emit' -s 3 -c 3 -f -o $out/${tag}_int_$p \
+      python tools/stage_bench.py --preset $p --groups 2048 --iters 1 > $out/${tag}_ncu_int_$p.log 2>&1
+  done ;;
+*) echo "unknown step $step" ;;
+esac
+done
+ls -la $out | grep ${tag}_ | tail -20
