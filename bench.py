@@ -106,7 +106,11 @@ SPECS = {
                        reads="HiFi reads on the last two contigs of a 6.2 Gb replica (25 filler contigs of N first: every "
                              "reference window lies beyond 2^32), --hifi preset"),
     "stress": dict(config="configs[4]", title="stress", synth="stress", params="hifi", locus_len=2_000_000,
-                   groups=8192, pool=2, reads="9 near-identical repeat copies, up to 8 secondaries per read, homopolymer-rich (30 %), --hifi preset"),
+                   groups=8192, pool=2,
+                   # a second parity sample from even more similar copies: there several secondaries share the top
+                   # score, so the reference's rand() tie-break (ptAlignment.c:156-170) is compared at size too
+                   tie_parity=dict(groups=1024, synth_over=dict(snv_rate=2e-4, indel_rate=4e-5, long_indel_rate=4e-6)),
+                   reads="9 near-identical repeat copies, up to 8 secondaries per read, homopolymer-rich (30 %), --hifi preset"),
 }
 
 
@@ -139,7 +143,7 @@ class Workload:
         from tools.parity import encode_reference
         from tools.synth.pysynth import Synth, default_cfg
         self.sp = sp
-        self.synth = Synth(default_cfg(sp["synth"], locus_len=sp["locus_len"], seed=20240603))
+        self.synth = Synth(default_cfg(sp["synth"], locus_len=sp["locus_len"], seed=20240603, **sp.get("synth_over", {})))
         codes, off = encode_reference(self.synth)
         self.tid_shift = 0
         self.names = list(self.synth.names)
@@ -526,6 +530,17 @@ def measure_config(sp, args, steps, warmup, local, rank, world, barrier, allredu
             m["cpu_baseline"], m["parity"] = cpu, parity
         except RuntimeError as e:
             m["cpu_baseline"], m["parity"] = {"unavailable": str(e)}, None
+        if sp.get("tie_parity") and m.get("parity") is not None:
+            eng.close()
+            tp = sp["tie_parity"]
+            wl2 = Workload(dict(sp, synth_over=tp["synth_over"]))
+            eng = secphase_b200.Secphase(sp["params"], device=local)
+            if args.hmm and hasattr(eng, "set_hmm_mode"):
+                eng.set_hmm_mode(args.hmm)
+            eng.set_reference_codes(wl2.codes, wl2.off)
+            _, ptie = parity_at_size(eng, wl2, wl2.generate(0, tp["groups"]), sp["params"], threads)
+            ptie["workload"] = "same generator with " + ", ".join(f"{k}={v:g}" for k, v in tp["synth_over"].items())
+            m["parity"]["tie_sample"] = ptie
     eng.close()
     return m
 

@@ -33,6 +33,7 @@ struct HsOut {
     std::vector<int64_t> block_off;
     std::vector<int32_t> items;  // [.][SP_HMM_W]
     std::vector<int32_t> rows;   // [.][4] item, t, state, q
+    std::vector<double> rows_pmax;  // [.] normalised max posterior of each row
     std::vector<uint8_t> qual;   // full_baq mode: quality pool after the write-back (k_baq_rows, k_baq_zero)
     int64_t cells = 0;
     int32_t err = 0;
@@ -99,6 +100,7 @@ HS_GET(hs_block_off, block_off, int64_t)
 HS_GET(hs_items, items, int32_t)
 HS_GET(hs_rows, rows, int32_t)
 HS_GET(hs_qual, qual, uint8_t)
+HS_GET(hs_rows_pmax, rows_pmax, double)
 const int32_t *hs_markers(const HsOut *o, int st, int64_t *n) { *n = (int64_t) o->mk[st].size(); return o->mk[st].data(); }
 const int64_t *hs_marker_off(const HsOut *o, int st, int64_t *n) { *n = (int64_t) o->mk_off[st].size(); return o->mk_off[st].data(); }
 int64_t hs_cells(const HsOut *o) { return o->cells; }
@@ -421,6 +423,7 @@ int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
     for (int r = 0; r < row_off[G]; r++) {
         int32_t rr[4] = {rows[r].item, rows[r].t, rows[r].state, rows[r].q};
         out->rows.insert(out->rows.end(), rr, rr + 4);
+        out->rows_pmax.push_back(rows[r].pmax);
     }
     if (full_baq) {  // run_phase_b: D2D copy of the raw pool, k_baq_rows, k_baq_zero
         out->qual.assign(b->qual_pool, b->qual_pool + b->qual_off[A]);

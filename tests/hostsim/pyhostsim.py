@@ -52,7 +52,8 @@ def lib():
         L.hs_qual.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.hs_qual.restype = C.POINTER(C.c_uint8)
         for name, rt in [("group", C.c_int32), ("score", C.c_double), ("extent", C.c_int32),
-                         ("blocks", C.c_int32), ("block_off", C.c_int64), ("items", C.c_int32), ("rows", C.c_int32)]:
+                         ("blocks", C.c_int32), ("block_off", C.c_int64), ("items", C.c_int32), ("rows", C.c_int32),
+                         ("rows_pmax", C.c_double)]:
             f = getattr(L, "hs_" + name)
             f.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
             f.restype = C.POINTER(rt)
@@ -110,6 +111,7 @@ def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1, full_baq=
         r["block_off"] = _take(L.hs_block_off(out, C.byref(n)), n.value, 1, np.int64)
         r["items"] = _take(L.hs_items(out, C.byref(n)), n.value, 8, np.int32)
         r["rows"] = _take(L.hs_rows(out, C.byref(n)), n.value, 4, np.int32)
+        r["rows_pmax"] = _take(L.hs_rows_pmax(out, C.byref(n)), n.value, 1, np.float64)
         for st, nm in enumerate(("markers_pre", "markers_baq", "markers_final")):
             r[nm] = _take(L.hs_markers(out, st, C.byref(n)), n.value, 6, np.int32)
             r[nm + "_off"] = _take(L.hs_marker_off(out, st, C.byref(n)), n.value, 1, np.int64)

@@ -73,11 +73,14 @@ def test_cuda_reproduces_golden(path):
         bad = compare_results(exp, got, label="cuda")
         assert not bad, "\n".join(bad)
         # same answer with the pools in page-locked memory (zero-copy H2D path)
+        eng.rng_seed(1)  # the tie-break stream continues across batches of a context: rewind it for the repeat
         again = eng.run(secphase_b200.pin_batch(batch))
         assert np.array_equal(again["scores"].view(np.int64), exp["scores"].view(np.int64))
         assert np.array_equal(again["groups"], exp["groups"])
         # -w/--writeBam mode: the records' quality arrays as the reference leaves them
         eng.set_write_qual(True)
+        eng.rng_seed(1)
         full = eng.run(batch)
+        assert np.array_equal(full["groups"], exp["groups"])
         assert np.array_equal(full["baq_qual"], exp["qual"])
         assert np.array_equal(full["scores"].view(np.int64), exp["scores"].view(np.int64))
