@@ -104,6 +104,11 @@ typedef struct sp_result {
      * batch's qual_pool / qual_off -- what sam_write1 emits at secphase.c:182-189. */
     const uint8_t *baq_qual;
     int64_t baq_qual_bytes;
+    /* BAQ-HMM arithmetic this batch ran with (sp_set_hmm_mode) and, in fast mode, how many HMM instances its
+     * guard band sent to the strict kernel */
+    int32_t hmm_mode;
+    int32_t pad0;
+    int64_t hmm_strict_reruns;
 } sp_result;
 
 /* Page-locked host memory for the pools of an sp_flat_batch (cigar_pool, tag_pool, seq_pool,
@@ -139,6 +144,20 @@ int sp_poll(sp_ctx *ctx, int slot);
  * Must be called with no batch in flight; batches uploaded with sp_upload before the switch have to
  * be uploaded again, and results of completed batches must have been read. */
 int sp_set_write_qual(sp_ctx *ctx, int on);
+
+/* BAQ-HMM arithmetic (the replacement of htslib's probaln_glocal, call site ptMarker.c:754-757).
+ *   0 "strict": every double operation in the reference's order, no FMA contraction -- the bits of every
+ *      intermediate posterior equal the reference's.
+ *   1 "fast" (default): FMA-contracted, scale-free evaluation (csrc/sp_hmmf.cuh) -- about half the FP64
+ *      instructions.  Intermediate posteriors drift (measured <= 1e-11 relative on 1 - pmax, <= 11 units of
+ *      2^-53 absolute); the integers that are consumed (MAP state, q) are protected by a guard band of
+ *      1e-9 relative + 2^-47 absolute around every decision threshold and 1e-9 relative between the two best
+ *      posteriors: an instance with a consumed row inside a band is recomputed by the strict kernel, so
+ *      BAQ values, markers, scores and the selected alignment are the reference's in both modes.
+ * --writeBam batches (sp_set_write_qual) always run strict.  SECPHASE_B200_HMM=strict|fast in the environment
+ * of sp_create sets the initial mode.  Must be called with no batch in flight. */
+int sp_set_hmm_mode(sp_ctx *ctx, int mode);
+int sp_get_hmm_mode(sp_ctx *ctx);
 
 /* Device-side stopwatch over several batches (bench.py): sp_mark records a CUDA event on slot 0's
  * stream (call it when the device is idle); sp_elapsed_since_mark gives the CUDA-event time from

@@ -51,6 +51,7 @@ class _CResult(C.Structure):
         ("hmm_instances", C.c_int64), ("hmm_cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ms_total", C.c_float), ("ms_hmm", C.c_float), ("ms_stage", C.c_float * 8), ("gpu_launches", C.c_int32),
         ("baq_qual", C.POINTER(C.c_uint8)), ("baq_qual_bytes", C.c_int64),
+        ("hmm_mode", C.c_int32), ("pad0", C.c_int32), ("hmm_strict_reruns", C.c_int64),
     ]
 
 
@@ -102,6 +103,10 @@ def load_library(path=None):
     L.sp_sm_partition.restype = C.c_int
     L.sp_set_write_qual.argtypes = [C.c_void_p, C.c_int]
     L.sp_set_write_qual.restype = C.c_int
+    L.sp_set_hmm_mode.argtypes = [C.c_void_p, C.c_int]
+    L.sp_set_hmm_mode.restype = C.c_int
+    L.sp_get_hmm_mode.argtypes = [C.c_void_p]
+    L.sp_get_hmm_mode.restype = C.c_int
     L.sp_poll.argtypes = [C.c_void_p, C.c_int]
     L.sp_poll.restype = C.c_int
     L.sp_mark.argtypes = [C.c_void_p]
@@ -118,7 +123,7 @@ def load_library(path=None):
 EXPORTED_SYMBOLS = [
     "sp_params_default", "sp_params_preset", "sp_create", "sp_destroy", "sp_last_error", "sp_version",
     "sp_set_reference_ascii", "sp_set_reference_codes", "sp_submit", "sp_wait", "sp_poll", "sp_sm_partition", "sp_mark", "sp_elapsed_since_mark", "sp_upload", "sp_run_resident",
-    "sp_set_write_qual", "sp_debug_table", "sp_hmm_batch", "sp_fp64_peak", "sp_rng_seed", "sp_rng_next", "sp_host_alloc", "sp_host_free",
+    "sp_set_write_qual", "sp_set_hmm_mode", "sp_get_hmm_mode", "sp_debug_table", "sp_hmm_batch", "sp_fp64_peak", "sp_rng_seed", "sp_rng_next", "sp_host_alloc", "sp_host_free",
 ]
 
 
@@ -263,6 +268,7 @@ class Secphase:
             "h2d_bytes": r.h2d_bytes, "d2h_bytes": r.d2h_bytes,
             "ms_total": r.ms_total, "ms_hmm": r.ms_hmm, "ms_stage": list(r.ms_stage),
             "gpu_launches": r.gpu_launches,
+            "hmm_mode": "fast" if r.hmm_mode == 1 else "strict", "hmm_rerun": int(r.hmm_strict_reruns),
         }
         if copy:
             out["groups"] = _take(r.group, r.n_groups, GROUP_W, np.int32)
@@ -284,6 +290,14 @@ class Secphase:
         """-w/--writeBam mode (secphase.c:182-189): wait() then also returns `baq_qual`, the records'
         quality arrays after calc_update_baq_all, laid out like the batch's qual_pool."""
         self._ck(self._L.sp_set_write_qual(self._h, 1 if on else 0))
+
+    def set_hmm_mode(self, mode):
+        """"strict": the reference's rounding order; "fast" (default): FMA / scale-free arithmetic with a guard
+        band and a strict re-run of the flagged instances (include/secphase_b200.h, sp_set_hmm_mode)."""
+        self._ck(self._L.sp_set_hmm_mode(self._h, {"strict": 0, "fast": 1}[mode]))
+
+    def hmm_mode(self):
+        return "fast" if self._L.sp_get_hmm_mode(self._h) == 1 else "strict"
 
     def enable_debug_tables(self):
         self._L.sp_debug_table(self._h, 0, -1, None, None)

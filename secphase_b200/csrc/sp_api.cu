@@ -109,9 +109,11 @@ struct Slot {
     size_t off_gblk_cap = 0, off_gblk_off = 0, off_giv_off = 0;  // plan-derived sections inside h_in / d_in
     // device work tables
     DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, item_off, row_off, sdbl_off, score,
-        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out, set_base;
+        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out, set_base,
+        rerun_list;
     // host results
-    PinBuf h_tot, h_gout, h_score, h_info, h_fin, h_qual;
+    PinBuf h_tot, h_gout, h_score, h_info, h_fin, h_qual, h_rerun;
+    bool fast_hmm = false;  // this batch's HMM launches used the fast kernel (+ strict re-run of flagged instances)
     size_t qual_bytes = 0;  // size of the batch's quality pool (== of qual_out in full_baq mode)
     bool full_baq = false;  // this batch was planned with SpConst::full_baq set
     SpBatchPtrs P;
@@ -150,6 +152,7 @@ struct sp_ctx {
     int test_block_cap = 0;  // tests: first plan clamps every group's block workspace to this (forces the retry)
     int64_t cap_retries = 0;
     bool full_baq = false;  // sp_set_write_qual: --writeBam mode
+    int hmm_mode = 1;       // sp_set_hmm_mode: 0 strict (the reference's rounding order), 1 fast + guard band + strict re-run
     bool streams_ready = false;  // ensure_streams
     int sm_count = 0;
     size_t max_smem = 0;
@@ -381,6 +384,10 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
     SP_ATTR(1, 47); SP_ATTR(1, 49); SP_ATTR(1, 51);
 #endif
 #undef SP_ATTR
+#define SP_ATTRF(NC) attr_ok = attr_ok && cudaFuncSetAttribute(k_hmmf<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) == cudaSuccess
+    SP_ATTRF(41); SP_ATTRF(43); SP_ATTRF(45); SP_ATTRF(55);
+#undef SP_ATTRF
+    if (const char *e = getenv("SECPHASE_B200_HMM")) c->hmm_mode = strcmp(e, "strict") == 0 ? 0 : 1;
     if (!attr_ok) {
         set_err("sp_create: cudaFuncSetAttribute(k_hmm) failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -430,9 +437,9 @@ void sp_destroy(sp_ctx *c) {
         DevBuf *bufs[] = {&S.d_in, &S.ops, &S.imk, &S.info, &S.blk, &S.iv, &S.nb, &S.gpos, &S.ent, &S.res, &S.baq,
                           &S.gP, &S.gout, &S.gcnt, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
                           &S.fin, &S.items, &S.rows, &S.order, &S.bins, &S.class_start, &S.s_pool, &S.fsave,
-                          &S.gband, &S.totals, &S.work_counter, &S.qual_out, &S.set_base};
+                          &S.gband, &S.totals, &S.work_counter, &S.qual_out, &S.set_base, &S.rerun_list};
         for (DevBuf *b : bufs) b->release();
-        PinBuf *pins[] = {&S.h_in, &S.h_tot, &S.h_gout, &S.h_score, &S.h_info, &S.h_fin, &S.h_qual};
+        PinBuf *pins[] = {&S.h_in, &S.h_tot, &S.h_gout, &S.h_score, &S.h_info, &S.h_fin, &S.h_qual, &S.h_rerun};
         for (PinBuf *b : pins) b->release();
         for (int k = 0; k < EV_N; k++)
             if (S.ev[k]) cudaEventDestroy(S.ev[k]);
@@ -658,6 +665,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
     if ((rc = S.h_gout.ensure(sizeof(SpGroupOut) * (G + 1)))) return rc;
     if ((rc = S.h_score.ensure(8 * (A + 1)))) return rc;
     if ((rc = S.h_info.ensure(sizeof(SpAlnInfo) * (A + 1)))) return rc;
+    if ((rc = S.h_rerun.ensure(sizeof(int) * SP_N_CLASSES))) return rc;
 
     uint8_t *d = S.d_in.as<uint8_t>();
     SpBatchPtrs &P = S.P;
@@ -693,7 +701,13 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
 template <int NW, int NC, bool IL>
 static void launch_hmm2(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first, int cnt, const uint8_t *ref,
                         const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride,
-                        const int64_t *set_base, int set_first) {
+                        const int64_t *set_base, int set_first, const int32_t *order = nullptr, const int *count_ptr = nullptr,
+                        int *counter = nullptr) {
+    // count_ptr != nullptr: strict re-run of the instances the fast kernel flagged -- their number is only known
+    // on the device; cnt is then the upper bound (the class size) and a small grid is enough
+    if (!order) order = S.order.as<int32_t>();
+    if (!counter) counter = S.work_counter.as<int>() + cls;
+    if (count_ptr && cnt > 32 * 64) cnt = 32 * 64;
     const int nblk = (cnt + 31) / 32;
     const int ncell = sp_h2_cells(sp_class_bw(cls));
     const size_t slab = (size_t) ncell * 32 * 24;
@@ -702,21 +716,40 @@ static void launch_hmm2(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first,
     if (wpc > nblk) wpc = nblk;
     int grid = (nblk + wpc - 1) / wpc;
     if (grid > c->hmm_sms) grid = c->hmm_sms;
-    k_hmm2<NW, NC, IL><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(),
+    k_hmm2<NW, NC, IL><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), order,
                                                    first, cnt, ncell, ref, qbytes, seq_pool, seq_off,
                                                    S.s_pool.as<double>(), S.fsave.as<double>(),
                                                    set_base ? (int64_t) (2 * sp_class_bw(cls) + 1) * 64 : fs_stride,
-                                                   S.rows.as<SpRow>(), S.work_counter.as<int>() + cls, set_base, set_first);
+                                                   S.rows.as<SpRow>(), counter, set_base, set_first, count_ptr);
+}
+
+template <int NC>
+static void launch_hmmf(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first, int cnt, const uint8_t *ref,
+                        const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride,
+                        bool guard_all) {
+    const int nblk = (cnt + 31) / 32;
+    const size_t slab = (size_t) (NC + 2) * 32 * 16;
+    int wpc = (int) (c->max_smem / slab);
+    if (wpc > 8) wpc = 8;  // k_hmmf is compiled for at most 256 threads per CTA (255 registers each)
+    if (wpc > nblk) wpc = nblk;
+    int grid = (nblk + wpc - 1) / wpc;
+    if (grid > c->hmm_sms) grid = c->hmm_sms;
+    k_hmmf<NC><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(), first, cnt,
+                                                  ref, qbytes, seq_pool, seq_off, S.fsave.as<double>(), fs_stride,
+                                                  S.rows.as<SpRow>(), S.work_counter.as<int>() + cls, S.rerun_list.as<int32_t>(),
+                                                  S.work_counter.as<int>() + 2 * SP_N_CLASSES + cls, guard_all ? 1 : 0);
 }
 
 // `interleaved`: the -w mode's lane-interleaved forward-row pool (set bases from k_fs_sets), else
 // every instance keeps its rows to itself at row0 * fs_stride
 static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_count, int max_bw, const uint8_t *ref,
                       const uint8_t *qbytes, const uint8_t *seq_pool, const int64_t *seq_off, int64_t fs_stride,
-                      bool interleaved = false) {
+                      bool interleaved = false, bool fast = false, bool guard_all = true) {
     int rc;
-    if ((rc = S.work_counter.ensure(sizeof(int) * SP_N_CLASSES))) return rc;
-    CK(cudaMemsetAsync(S.work_counter.p, 0, sizeof(int) * SP_N_CLASSES, st));
+    // per class: work-queue head of the main launch, of the strict re-run launch, and the re-run count
+    if ((rc = S.work_counter.ensure(sizeof(int) * 3 * SP_N_CLASSES))) return rc;
+    CK(cudaMemsetAsync(S.work_counter.p, 0, sizeof(int) * 3 * SP_N_CLASSES, st));
+    S.fast_hmm = fast;
     int first[SP_N_CLASSES + 1];
     first[0] = 0;
     for (int cls = 0; cls < SP_N_CLASSES; cls++) first[cls + 1] = first[cls] + class_count[cls];
@@ -743,7 +776,21 @@ static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_
         if (used < SP_N_AUX) CK(cudaStreamWaitEvent(as, S.ev_fork, 0));
         used++;
         const int bwc = sp_class_bw(cls);
-        if (bwc != 0) {
+        const int fcells = fast ? sp_hmmf_class_cells(cls) : 0;
+        if (fcells != 0) {
+            switch (fcells) {
+                case 41: launch_hmmf<41>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                case 43: launch_hmmf<43>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                case 45: launch_hmmf<45>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                default: launch_hmmf<55>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+            }
+            S.launches++;
+            // the instances its guard band flagged, recomputed in the reference's rounding order (generic strict body:
+            // their number is tiny and only known on the device)
+            launch_hmm2<1, 0, false>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, nullptr, 0,
+                                     S.rerun_list.as<int32_t>(), S.work_counter.as<int>() + 2 * SP_N_CLASSES + cls,
+                                     S.work_counter.as<int>() + SP_N_CLASSES + cls);
+        } else if (bwc != 0) {
             const int nw = sp_h2_words(bwc);
 #define SP_LAUNCH(NW, NC)                                                                                          \
     do {                                                                                                           \
@@ -835,7 +882,13 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
     if ((rc = S.rows.ensure(sizeof(SpRow) * (size_t) (T.n_rows + 1)))) return rc;
     if ((rc = S.order.ensure(4 * (size_t) (T.n_items + 1)))) return rc;
     if ((rc = S.s_pool.ensure(8 * (size_t) (T.s_doubles + 2)))) return rc;
-    const int64_t fs_stride = 2 * (2 * (int64_t) T.max_bw + 1);
+    const bool fast = c->hmm_mode == 1 && !S.full_baq;
+    if ((rc = S.rerun_list.ensure(4 * (size_t) (T.n_items + 1)))) return rc;
+    // doubles per saved forward row: the widest band of the batch -- or, wider still, the cells of the fast
+    // kernel's class that band falls in (its virtual band always has the class's full width)
+    int64_t fs_cells = 2 * (int64_t) T.max_bw + 1;
+    if (fast && sp_hmmf_class_cells(sp_band_class(T.max_bw)) > fs_cells) fs_cells = sp_hmmf_class_cells(sp_band_class(T.max_bw));
+    const int64_t fs_stride = 2 * fs_cells;
     // -w mode: every lane of a warp saves and re-reads every row in lock step, so the forward rows of a
     // 32-instance set are interleaved lane by lane (coalesced 512-byte accesses) instead of each
     // instance keeping ~650-byte rows to itself.  Needs the shared-memory-band kernel for every
@@ -868,8 +921,10 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
     CK(cudaEventRecord(S.ev[EV_EMIT], st));
     if (T.n_items > 0) {
         if ((rc = launch_hmm(c, S, st, T.class_count, T.max_bw, P.ref, nullptr, P.seq_pool, P.seq_off, fs_stride,
-                             interleaved)))
+                             interleaved, fast, /*guard_all=*/false)))
             return rc;
+    } else {
+        S.fast_hmm = false;
     }
     CK(cudaEventRecord(S.ev[EV_HMM], st));
     if (S.full_baq && S.qual_bytes > 0) {
@@ -959,6 +1014,11 @@ static int enqueue_results(Slot &S) {
     CK(cudaMemcpyAsync(S.h_score.p, S.score.p, 8 * A, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(S.h_info.p, S.info.p, sizeof(SpAlnInfo) * A, cudaMemcpyDeviceToHost, st));
     S.d2h_bytes = (int64_t) (sizeof(SpTotals) + sizeof(SpGroupOut) * G + 8 * A + sizeof(SpAlnInfo) * A);
+    if (S.fast_hmm) {  // how many instances the fast kernel's guard band handed to the strict kernel, per class
+        CK(cudaMemcpyAsync(S.h_rerun.p, S.work_counter.as<int>() + 2 * SP_N_CLASSES, sizeof(int) * SP_N_CLASSES,
+                           cudaMemcpyDeviceToHost, st));
+        S.d2h_bytes += (int64_t) sizeof(int) * SP_N_CLASSES;
+    }
     if (S.full_baq && S.qual_bytes > 0) {
         CK(cudaMemcpyAsync(S.h_qual.p, S.qual_out.p, S.qual_bytes, cudaMemcpyDeviceToHost, st));
         S.d2h_bytes += (int64_t) S.qual_bytes;
@@ -1086,6 +1146,18 @@ int sp_set_write_qual(sp_ctx *c, int on) {
         if (c->slot[s].state == 1 || c->slot[s].state == 3) c->slot[s].state = 0;
     return SP_OK;
 }
+
+int sp_set_hmm_mode(sp_ctx *c, int mode) {
+    if (!c || (mode != 0 && mode != 1)) return SP_EINVAL;
+    for (int s = 0; s < SP_N_SLOTS; s++)
+        if (c->slot[s].state == 2) {
+            set_err("sp_set_hmm_mode: slot %d still has a batch in flight", s);
+            return SP_ESTATE;
+        }
+    c->hmm_mode = mode;
+    return SP_OK;
+}
+int sp_get_hmm_mode(sp_ctx *c) { return c ? c->hmm_mode : SP_EINVAL; }
 
 int sp_mark(sp_ctx *c) {
     if (!c) return SP_EINVAL;
@@ -1227,6 +1299,10 @@ int sp_wait(sp_ctx *c, int slot, sp_result *out) {
     out->h2d_bytes = S.h2d_bytes;
     out->d2h_bytes = S.d2h_bytes;
     out->gpu_launches = S.launches;
+    out->hmm_mode = S.fast_hmm ? 1 : 0;
+    out->hmm_strict_reruns = 0;
+    if (S.fast_hmm && T.n_items > 0)
+        for (int k = 0; k < SP_N_CLASSES; k++) out->hmm_strict_reruns += S.h_rerun.as<int>()[k];
     out->baq_qual = S.full_baq ? S.h_qual.as<uint8_t>() : nullptr;
     out->baq_qual_bytes = S.full_baq ? (int64_t) S.qual_bytes : 0;
     float ms = 0;
@@ -1416,7 +1492,11 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
     if ((rc = S.rows.ensure(sizeof(SpRow) * (size_t) (n_rows + 1)))) return rc;
     if ((rc = S.order.ensure(4 * (size_t) n))) return rc;
     if ((rc = S.s_pool.ensure(8 * (size_t) (s_total + 2)))) return rc;
-    const int64_t fs_stride = 2 * (2 * (int64_t) max_bw + 1);
+    const bool fast = c->hmm_mode == 1;
+    if ((rc = S.rerun_list.ensure(4 * (size_t) (n + 1)))) return rc;
+    int64_t fs_cells = 2 * (int64_t) max_bw + 1;
+    if (fast && sp_hmmf_class_cells(sp_band_class(max_bw)) > fs_cells) fs_cells = sp_hmmf_class_cells(sp_band_class(max_bw));
+    const int64_t fs_stride = 2 * fs_cells;
     if ((rc = S.fsave.ensure(8 * (size_t) (n_rows * fs_stride + 2)))) return rc;
     if ((rc = S.bins.ensure(4 * (size_t) ((SP_N_CLASSES + 1) * SP_SORT_LBINS)))) return rc;
     if ((rc = S.class_start.ensure(4 * (SP_N_CLASSES + 3)))) return rc;
@@ -1435,7 +1515,7 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
     CK(cudaEventRecord(e0, st));
     const int launches_before = S.launches;
     if ((rc = launch_hmm(c, S, st, cls_count, max_bw, d_ref.as<uint8_t>(), d_q.as<uint8_t>(), nullptr, nullptr,
-                         fs_stride)))
+                         fs_stride, false, fast, /*guard_all=*/true)))
         return rc;
     S.launches = launches_before;
     CK(cudaEventRecord(e1, st));

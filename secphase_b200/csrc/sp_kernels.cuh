@@ -15,6 +15,7 @@
 #include "sp_common.h"
 #include "sp_hmm.cuh"
 #include "sp_hmm2.cuh"
+#include "sp_hmmf.cuh"
 #include "sp_markers.cuh"
 #include "sp_score.cuh"
 #include "sp_walk.cuh"
@@ -366,8 +367,9 @@ __global__ void __launch_bounds__(224, 1) k_hmm2(const SpConst *__restrict__ Cp,
                                               const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,
                                               double *__restrict__ s_pool, double *__restrict__ fsave, int64_t fs_stride,
                                               SpRow *rows, int *work_counter, const int64_t *__restrict__ set_base,
-                                              int set_first) {
+                                              int set_first, const int *__restrict__ count_ptr) {
     extern __shared__ double2 smem2[];
+    if (count_ptr) count = *count_ptr;  // strict re-run of the instances the fast kernel's guard band flagged
     const int lane = threadIdx.x & 31;
     double2 *slab = smem2 + (size_t) (threadIdx.x >> 5) * ncell * 48;  // ncell*32*(16+8) bytes per warp
     double2 *mi = slab + lane;
@@ -409,6 +411,52 @@ __global__ void __launch_bounds__(224, 1) k_hmm2(const SpConst *__restrict__ Cp,
                 sp_hmm2_instance<32, NW, NC>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride,
                                              fs_stride, rows + it.row0, it.n_rows, w * 32 + 32 <= count);
         }
+        __syncwarp();
+    }
+}
+
+// Fast-arithmetic K4 kernel (sp_hmmf.cuh) for the band classes that have a fully unrolled body: persistent
+// CTAs, one instance per lane, per-warp slab of (NC+2) x 32 double2 (M,I) cells -- the forward D state
+// lives in registers, so eight warps fit an SM.  Every lane of a warp runs an instance (the last,
+// partial set repeats its last instance with no rows) because the row bodies are chosen by warp votes.
+// Instances whose guard band fired are appended to rerun_list[first ...] for the strict kernel.
+template <int NC>
+__global__ void __launch_bounds__(256, 1) k_hmmf(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
+                                                 const int32_t *__restrict__ order, int first, int count,
+                                                 const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qbytes,
+                                                 const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,
+                                                 double *__restrict__ fsave, int64_t fs_stride, SpRow *rows,
+                                                 int *work_counter, int32_t *rerun_list, int *rerun_count, int guard_all) {
+    extern __shared__ double2 smem2[];
+    const int lane = threadIdx.x & 31;
+    double2 *mi = smem2 + (size_t) (threadIdx.x >> 5) * (NC + 2) * 32 + 32 + lane;  // cell -1 sits one row below
+    const int nwork = (count + 31) >> 5;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nwork) break;
+        const int slot = w * 32 + lane;
+        const bool dup = slot >= count;
+        const int idx = order ? order[first + (dup ? count - 1 : slot)] : first + (dup ? count - 1 : slot);
+        const SpItem it = items[idx];
+        SpHmmIn in;
+        in.ref = ref + it.ref_off;
+        if (it.query_off >= 0) {
+            in.qbytes = qbytes;
+            in.qseq4 = nullptr;
+            in.q0 = it.query_off;
+        } else {
+            in.qbytes = nullptr;
+            in.qseq4 = seq_pool + seq_off[it.aln];
+            in.q0 = it.q_sqs;
+        }
+        in.l_ref = it.l_ref;
+        in.l_query = it.l_query;
+        in.par_bw = it.par_bw;
+        const int flag = sp_hmmf_instance<32, NC>(*Cp, in, mi, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
+                                                  rows + it.row0, dup ? 0 : it.n_rows, guard_all != 0);
+        if (!dup && flag) rerun_list[first + atomicAdd(rerun_count, 1)] = idx;
         __syncwarp();
     }
 }

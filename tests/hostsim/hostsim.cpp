@@ -18,6 +18,7 @@
 #include "../../secphase_b200/csrc/sp_common.h"
 #include "../../secphase_b200/csrc/sp_hmm.cuh"
 #include "../../secphase_b200/csrc/sp_hmm2.cuh"
+#include "../../secphase_b200/csrc/sp_hmmf.cuh"
 #include "../../secphase_b200/csrc/sp_markers.cuh"
 #include "../../secphase_b200/csrc/sp_plan.h"
 #include "../../secphase_b200/csrc/sp_score.cuh"
@@ -37,7 +38,30 @@ struct HsOut {
     std::vector<uint8_t> qual;   // full_baq mode: quality pool after the write-back (k_baq_rows, k_baq_zero)
     int64_t cells = 0;
     int32_t err = 0;
+    // fast HMM arithmetic (hs_run3, hmm_mode 1): instances the guard band sent to the strict kernel
+    int64_t fast_instances = 0, rerun_instances = 0, rerun_threshold = 0, rerun_tie = 0, rerun_numeric = 0;
+    // hmm_mode 2, over the consumed rows of un-flagged instances, t = 1 - pmax: largest |t_fast - t_strict| in units
+    // of 2^-53 (the grid the reference's own 1 - max/sum lives on) and largest relative difference among rows
+    // with t >= 1e-4 (where that grid is finer than 1e-12 relative)
+    double max_abs_drift_ulp = 0, max_rel_drift = 0;
 };
+
+// the fast kernel body (sp_hmmf.cuh) for the band class of `bw`; returns the guard flags, or -1 when the
+// class has no fast body (the launcher then runs the strict kernel)
+static int hs_hmmf_dispatch(const SpConst &C, const SpHmmIn &in, int bw, double *fsave, int64_t fss, SpRow *rows, int n_rows,
+                            bool guard_all) {
+    const int cls = sp_band_class(bw);
+    const int nc = sp_hmmf_class_cells(cls);
+    if (nc == 0) return -1;
+    std::vector<SpD2> mi((size_t) nc + 2);
+    switch (nc) {
+        case 41: return sp_hmmf_instance<1, 41>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
+        case 43: return sp_hmmf_instance<1, 43>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
+        case 45: return sp_hmmf_instance<1, 45>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
+        case 55: return sp_hmmf_instance<1, 55>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
+        default: return -1;
+    }
+}
 
 // the instantiation launch_hmm() (sp_api.cu) picks for a band half-width; `unrolled` = what a full
 // warp of that class runs, otherwise what a partial last warp runs
@@ -104,6 +128,12 @@ HS_GET(hs_rows_pmax, rows_pmax, double)
 const int32_t *hs_markers(const HsOut *o, int st, int64_t *n) { *n = (int64_t) o->mk[st].size(); return o->mk[st].data(); }
 const int64_t *hs_marker_off(const HsOut *o, int st, int64_t *n) { *n = (int64_t) o->mk_off[st].size(); return o->mk_off[st].data(); }
 int64_t hs_cells(const HsOut *o) { return o->cells; }
+void hs_fast_stats(const HsOut *o, int64_t *st5, double *drift) {
+    drift[1] = o->max_abs_drift_ulp;
+    st5[0] = o->fast_instances; st5[1] = o->rerun_instances; st5[2] = o->rerun_threshold; st5[3] = o->rerun_tie;
+    st5[4] = o->rerun_numeric;
+    drift[0] = o->max_rel_drift;
+}
 int32_t hs_err(const HsOut *o) { return o->err; }
 
 void hs_fill_const(const sp_params *p, SpConst *C) { sp_fill_const(*p, *C); }
@@ -177,6 +207,32 @@ int hs_hmm2(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *qu
     return 0;
 }
 
+// The fast-arithmetic body (sp_hmmf.cuh) alone; returns the guard flags (>= 0) or -1 when the band class has none.
+int hs_hmmf(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *query, int l_query, int par_bw,
+            const int32_t *rows_t, int n_rows, int32_t *state, uint8_t *q, double *pmax) {
+    SpConst C;
+    sp_fill_const(*p, C);
+    const int bw = sp_hmm_bw(l_ref, l_query, par_bw);
+    const int nc = sp_hmmf_class_cells(sp_band_class(bw));
+    if (nc == 0) return -1;
+    std::vector<double> fsave((size_t) n_rows * 2 * nc + 2, 0.0);
+    std::vector<SpRow> rows((size_t) (n_rows > 0 ? n_rows : 1));
+    for (int i = 0; i < n_rows; i++) {
+        rows[i].item = 0; rows[i].t = rows_t[i]; rows[i].entry = -1; rows[i].expected = 0;
+        rows[i].state = 0; rows[i].q = 0; rows[i].pmax = 0;
+    }
+    SpHmmIn in;
+    in.ref = ref; in.qbytes = query; in.qseq4 = nullptr; in.q0 = 0;
+    in.l_ref = l_ref; in.l_query = l_query; in.par_bw = par_bw;
+    const int flag = hs_hmmf_dispatch(C, in, bw, fsave.data(), 2 * nc, rows.data(), n_rows, true);
+    for (int i = 0; i < n_rows; i++) {
+        state[i] = rows[i].state;
+        q[i] = (uint8_t) rows[i].q;
+        if (pmax) pmax[i] = rows[i].pmax;
+    }
+    return flag;
+}
+
 // Signature of the batch plan (every table offset) computed with n_threads text-scan threads: the plan must
 // not depend on the thread count.
 uint64_t hs_plan_sig(const sp_flat_batch *b, int indel_threshold, int safe_caps, int n_threads, int *rc_out) {
@@ -228,6 +284,8 @@ int hs_walk_stats(const sp_flat_batch *b, const sp_params *p, int32_t *out /* [A
 // Whole marker path for a batch; ref_codes: concatenated contigs (codes 0..4), contig_off[n+1].
 int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
             int n_contigs, int safe_caps, unsigned rng_seed, int full_baq, HsOut *out);
+int hs_run3(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
+            int n_contigs, int safe_caps, unsigned rng_seed, int full_baq, int hmm_mode, HsOut *out);
 int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
            int n_contigs, int safe_caps, unsigned rng_seed, HsOut *out) {
     return hs_run2(b, p, ref_codes, contig_off, n_contigs, safe_caps, rng_seed, 0, out);
@@ -235,6 +293,14 @@ int hs_run(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes,
 // full_baq != 0: the --writeBam mode of sp_set_write_qual (rows for every base of the write-back range)
 int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
             int n_contigs, int safe_caps, unsigned rng_seed, int full_baq, HsOut *out) {
+    return hs_run3(b, p, ref_codes, contig_off, n_contigs, safe_caps, rng_seed, full_baq, 0, out);
+}
+// hmm_mode: 0 strict kernels only; 1 the product's default: fast kernel where the band class has one (never in
+// -w mode), instances flagged by its guard band re-run by the strict kernel; 2 = 1 plus statistics: every fast
+// instance is ALSO run strictly and the integers / drift of the un-flagged ones compared (out->err bit 0x200 on
+// a difference the guard band missed)
+int hs_run3(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes, const int64_t *contig_off,
+            int n_contigs, int safe_caps, unsigned rng_seed, int full_baq, int hmm_mode, HsOut *out) {
     (void) n_contigs;
     SpConst C;
     sp_fill_const(*p, C);
@@ -404,7 +470,26 @@ int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         in.qseq4 = b->seq_pool + b->seq_off[I.aln];
         in.q0 = I.q_sqs;
         in.l_ref = I.l_ref; in.l_query = I.l_query; in.par_bw = I.par_bw;
-        if (bw <= SP_H2_MAXBW) {  // same dispatch as launch_hmm() in sp_api.cu
+        bool strict = true;
+        std::vector<SpRow> fast_rows;
+        if (hmm_mode != 0 && !full_baq && sp_hmmf_class_cells(sp_band_class(bw)) != 0 && I.n_rows > 0) {
+            const int nc = sp_hmmf_class_cells(sp_band_class(bw));
+            std::vector<double> ff((size_t) I.n_rows * 2 * nc + 2, 0.0);
+            const int fl = hs_hmmf_dispatch(C, in, bw, ff.data(), 2 * nc, rows.data() + I.row0, I.n_rows, false);  // as k_hmmf does
+            out->fast_instances++;
+            strict = fl != 0;
+            if (fl) {
+                out->rerun_instances++;
+                if (fl & SP_HMMF_NEAR_THRESHOLD) out->rerun_threshold++;
+                if (fl & SP_HMMF_NEAR_TIE) out->rerun_tie++;
+                if (fl & SP_HMMF_NUMERIC) out->rerun_numeric++;
+            } else if (hmm_mode == 2) {
+                fast_rows.assign(rows.begin() + I.row0, rows.begin() + I.row0 + I.n_rows);
+                strict = true;
+            }
+        }
+        if (!strict) {
+        } else if (bw <= SP_H2_MAXBW) {  // same dispatch as launch_hmm() in sp_api.cu
             const int ncell = sp_h2_cells(bw);
             std::vector<SpD2> mi((size_t) ncell);
             std::vector<double> dd((size_t) ncell, 0.0);
@@ -416,6 +501,14 @@ int hs_run2(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
             SpBand<1> B;
             B.row = band.data(); B.code = code.data(); B.W = W;
             sp_hmm_instance<1, 1>(C, in, B, s.data(), fsave.data(), 2 * (2 * bw + 1), rows.data() + I.row0, I.n_rows);
+        }
+        for (size_t k = 0; k < fast_rows.size(); k++) {  // hmm_mode 2: what the guard band let through must be exact
+            const SpRow &S = rows[I.row0 + k], &F = fast_rows[k];
+            if (S.state != F.state || (S.q < 93 ? S.q : 93) != (F.q < 93 ? F.q : 93)) out->err |= 0x200;  // min(q,93) is what is consumed
+            const double ts = 1. - S.pmax, tf = 1. - F.pmax;
+            const double ad = tf > ts ? tf - ts : ts - tf;
+            if (ad * 9007199254740992. > out->max_abs_drift_ulp) out->max_abs_drift_ulp = ad * 9007199254740992.;
+            if (ts >= 1e-4 && ad / ts > out->max_rel_drift) out->max_rel_drift = ad / ts;
         }
         int32_t irow[SP_HMM_W] = {I.aln, I.l_ref, I.l_query, I.par_bw, I.blk, I.row0, I.n_rows, 0};
         out->items.insert(out->items.end(), irow, irow + SP_HMM_W);

@@ -47,6 +47,13 @@ def lib():
         L.hs_run2.argtypes = [C.POINTER(CFlatBatch), C.POINTER(SpParams), C.c_void_p, C.c_void_p, C.c_int,
                               C.c_int, C.c_uint, C.c_int, C.c_void_p]
         L.hs_run2.restype = C.c_int
+        L.hs_run3.argtypes = [C.POINTER(CFlatBatch), C.POINTER(SpParams), C.c_void_p, C.c_void_p, C.c_int,
+                              C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p]
+        L.hs_run3.restype = C.c_int
+        L.hs_fast_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_hmmf.argtypes = [C.POINTER(SpParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_hmmf.restype = C.c_int
         L.hs_plan_sig.argtypes = [C.POINTER(CFlatBatch), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.hs_plan_sig.restype = C.c_uint64
         L.hs_qual.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -91,15 +98,17 @@ def params_from_oracle(op):
     return SpParams(**{k: getattr(op, k) for k, _ in SpParams._fields_})
 
 
-def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1, full_baq=False):
+def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1, full_baq=False, hmm_mode=0):
+    """hmm_mode: 0 strict kernels; 1 fast kernel + guard-band re-run (the product's default); 2 = 1 and every
+    fast instance cross-checked against the strict kernel (r["fast"] statistics, err bit 0x200 on a miss)."""
     L = lib()
     out = L.hs_out_create()
     try:
         cb = batch.as_c()
         ref_codes = np.ascontiguousarray(ref_codes, np.uint8)
         contig_off = np.ascontiguousarray(contig_off, np.int64)
-        rc = L.hs_run2(C.byref(cb), C.byref(params), ref_codes.ctypes.data, contig_off.ctypes.data,
-                       len(contig_off) - 1, 1 if safe_caps else 0, seed, 1 if full_baq else 0, out)
+        rc = L.hs_run3(C.byref(cb), C.byref(params), ref_codes.ctypes.data, contig_off.ctypes.data,
+                       len(contig_off) - 1, 1 if safe_caps else 0, seed, 1 if full_baq else 0, hmm_mode, out)
         if rc != 0:
             raise RuntimeError(f"hs_run failed: {rc}")
         n = C.c_int64()
@@ -117,6 +126,12 @@ def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1, full_baq=
             r[nm + "_off"] = _take(L.hs_marker_off(out, st, C.byref(n)), n.value, 1, np.int64)
         if full_baq:
             r["qual"] = _take(L.hs_qual(out, C.byref(n)), n.value, 1, np.uint8)
+        st = (C.c_int64 * 5)()
+        drift = (C.c_double * 2)()
+        L.hs_fast_stats(out, st, drift)
+        r["fast"] = dict(zip(("instances", "rerun", "near_threshold", "near_tie", "numeric"), [int(x) for x in st]))
+        r["fast"]["max_rel_drift"] = drift[0]
+        r["fast"]["max_abs_drift_ulp"] = drift[1]
         r["cells"] = int(L.hs_cells(out))
         r["err"] = int(L.hs_err(out))
         return r
@@ -140,6 +155,23 @@ def hmm2(params, ref, query, par_bw, rows_t, unrolled=True):
     if rc != 0:
         return None
     return dict(state=state, q=q, pmax=pmax)
+
+
+def hmmf(params, ref, query, par_bw, rows_t):
+    """The fast-arithmetic kernel body (sp_hmmf.cuh) on the host; None if the band class has no fast body."""
+    L = lib()
+    ref = np.ascontiguousarray(ref, np.uint8)
+    query = np.ascontiguousarray(query, np.uint8)
+    rows_t = np.ascontiguousarray(rows_t, np.int32)
+    n = len(rows_t)
+    state = np.zeros(n, np.int32)
+    q = np.zeros(n, np.uint8)
+    pmax = np.zeros(n, np.float64)
+    fl = L.hs_hmmf(C.byref(params), ref.ctypes.data, len(ref), query.ctypes.data, len(query), par_bw,
+                   rows_t.ctypes.data, n, state.ctypes.data, q.ctypes.data, pmax.ctypes.data)
+    if fl < 0:
+        return None
+    return dict(state=state, q=q, pmax=pmax, flags=fl)
 
 
 def hmm(params, ref, query, par_bw, rows_t, want_s=False):

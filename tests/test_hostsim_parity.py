@@ -138,3 +138,78 @@ def test_hmm_kernel_bodies_all_rows_bit_exact_vs_port(hostsim, oracle, preset):
                 assert np.array_equal(o["state"][sel], g2["state"])
                 assert np.array_equal(o["q"][sel], g2["q"])
     assert n2 > 250
+
+
+def _fast_rows_check(o, got, rows):
+    """Per consumed row: is it outside every guard band (recomputed here from the oracle's pmax)?  Returns the
+    rows on which the fast kernel's integers may be used without a strict re-run."""
+    t = 1.0 - o["pmax"][rows]
+    return t
+
+
+@pytest.mark.parametrize("preset", ["hifi", "ont"])
+def test_hmm_fast_body_guard_band(hostsim, oracle, preset):
+    """sp_hmmf.cuh (FMA, no per-row sum, power-of-two rescaling, virtual sliding band) against the restated
+    probaln_glocal.  Contract of the guard band: an instance that comes back UNFLAGGED has the reference's
+    state and q at every consumed row; 1 - pmax agrees within 16 units of 2^-53 + 1e-10 relative (the band
+    itself is 64 units + 1e-9).  Instances with random bands, N bases, short references, sparse and dense
+    rows; the flagged fraction stays small on sparse (marker-like) rows."""
+    rng = np.random.default_rng(17)
+    op = oracle.preset_params(preset)
+    hp = hostsim.params_from_oracle(op)
+    n_fast = n_flag_dense = n_sparse = n_flag_sparse = 0
+    worst_ulp = worst_rel = 0.0
+    for ref, query, bw in _random_instances(rng, 160):
+        iq = np.full(len(query), op.set_q, np.uint8)
+        o = oracle.probaln(ref, query, iq, np.float32(op.conf_d), np.float32(op.conf_e), bw)
+        dense = np.arange(len(query), dtype=np.int32)
+        picks = [dense]
+        if len(query) > 40:
+            picks += [np.sort(rng.choice(np.arange(10, len(query) - 11), size=3, replace=False)).astype(np.int32)
+                      for _ in range(3)]
+        for rows in picks:
+            got = hostsim.hmmf(hp, ref, query, bw, rows)
+            if got is None:   # band class without a fast body: the launcher uses the strict kernel
+                continue
+            n_fast += 1
+            sparse = len(rows) == 3
+            n_sparse += sparse
+            if got["flags"]:
+                n_flag_sparse += sparse
+                n_flag_dense += not sparse
+                continue
+            assert np.array_equal(o["state"][rows], got["state"]), (len(ref), len(query), bw)
+            assert np.array_equal(o["q"][rows], got["q"]), (len(ref), len(query), bw)
+            ts, tf = 1.0 - o["pmax"][rows], 1.0 - got["pmax"]
+            ad = np.abs(ts - tf)
+            assert np.all(ad <= 16 * 2.0 ** -53 + 1e-10 * ts)
+            worst_ulp = max(worst_ulp, float(ad.max() * 2.0 ** 53))
+            big = ts >= 1e-4
+            if big.any():
+                worst_rel = max(worst_rel, float((ad[big] / ts[big]).max()))
+    assert n_fast > 150 and n_sparse > 100
+    assert n_flag_sparse <= 0.05 * n_sparse, (n_flag_sparse, n_sparse)
+    print(f"fast instances {n_fast}, flagged dense {n_flag_dense}, flagged sparse {n_flag_sparse}/{n_sparse}, "
+          f"worst |dt| {worst_ulp:.1f} x 2^-53, worst relative {worst_rel:.2e}")
+
+
+@pytest.mark.parametrize("name,spreset,ppreset,ng,over", CASES, ids=[c[0] for c in CASES])
+def test_fast_hmm_pipeline_bit_exact_vs_oracle(hostsim, oracle, name, spreset, ppreset, ng, over):
+    """The product's default K4 arrangement -- fast kernel, guard band, strict re-run of the flagged instances --
+    gives the oracle's tables; in cross-check mode (every fast instance also run strictly) no integer
+    difference slipped through the band and the drift stays 10x inside it."""
+    s, b, codes, off = make_case(spreset, ng, **over)
+    ref = oracle_refseq(oracle, s)
+    op = oracle.preset_params(ppreset)
+    exp = oracle.run(b, op, ref, keep_hmm=False)
+    hp = hostsim.params_from_oracle(op)
+    got = hostsim.run(b, hp, codes, off, hmm_mode=1)
+    assert got["err"] == 0
+    bad = compare_results(exp, got, label="hostsim-fast")
+    assert not bad, "\n".join(bad)
+    x = hostsim.run(b, hp, codes, off, hmm_mode=2)
+    assert x["err"] == 0, "an unflagged fast instance differs from the strict kernel"
+    f = x["fast"]
+    assert f["instances"] > 0.5 * len(x["items"])
+    assert f["rerun"] <= 0.01 * f["instances"] + 2
+    assert f["max_abs_drift_ulp"] <= 16 and f["max_rel_drift"] <= 1e-10

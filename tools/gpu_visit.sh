@@ -40,10 +40,12 @@ ref)
   ( timeout 400 python bench.py --impl reference --steps 3 --warmup 1 ) > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
   cat $out/${tag}_bench_ref.json ;;
 stage)
-  for p in hifi ont stress; do
-    timeout 300 python tools/stage_bench.py --preset $p --groups 2048 >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
+  for m in fast strict; do
+    for p in ont stress; do
+      timeout 300 python tools/stage_bench.py --preset $p --groups 2048 --hmm $m >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
+    done
+    timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --hmm $m >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
   done
-  timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
   cat $out/${tag}_stage.json ;;
 cli)
   ( timeout 500 python tools/cli_bench.py --groups 32768 ) > $out/${tag}_cli.json 2> $out/${tag}_cli.err
