@@ -13,8 +13,14 @@
 //  * a virtual band of NC = 2*BW+1 cells that slides by exactly one column per row for every row
 //    (cell o of row i is column i-BW+o); columns outside [1, l_ref] or outside the instance's own
 //    band |k-i| <= bw are held at exact zeros -- which is what the reference's zero padding means --
-//    by an edge variant of the row body that runs only for rows that have such columns (or an N);
-//    every other row runs a fully unrolled body with the forward D state in registers:
+//    by an edge variant of the row body that runs only for rows that have such columns (or an N, or a
+//    lane that has to keep the row for the MAP step, or a pending rescale);
+//  * the forward sweep does not store the states (M,I,D) of a row but the two sums the next row
+//    needs from them, G = m0*M + m3*I + m6*D (what flows into M one column to the right) and
+//    H = EI*(m1*M + m4*I) (what flows into I of the same column): M[i,k] = e*G[i-1,k-1],
+//    I[i,k] = H[i-1,k], and D lives only as the running chain value inside the row.  One 16-byte
+//    word per cell, no D plane, no state registers between rows -- so the bodies are short loops over
+//    chunks of cells with compile-time offsets and ten warps fit an SM;
 //    8 FP64 instructions per cell forward, 8 backward (the strict kernel issues 18 + 14).
 //
 // What this costs: the bits of the intermediate posteriors differ from the reference's (relative
@@ -36,15 +42,17 @@
 #define SP_FMA(a, b, c) __builtin_fma((a), (b), (c))
 #endif
 
-#define SP_HMMF_RS 8                             // rows between two range checks
+#define SP_HMMF_RS 16                            // rows between two range checks
 #define SP_HMMF_GUARD_ABS 7.105427357601002e-15  // 2^-47: 64 ulps of a posterior next to 1
 #define SP_HMMF_GUARD_REL 1e-9
 #define SP_HMMF_TIE_REL 1e-9
 enum { SP_HMMF_NEAR_THRESHOLD = 1, SP_HMMF_NEAR_TIE = 2, SP_HMMF_NUMERIC = 4 };
 
-// band classes the fast kernel has bodies for (sp_common.h classes 0..3: bw 20, 21, 22, <= 27)
+// cells of the fast kernel's virtual band for a band class (sp_common.h): every class the shared-memory
+// kernels cover (bw <= SP_H2_MAXBW); 0 = no fast body (the generic class)
 SP_HD int sp_hmmf_class_cells(int cls) {
-    return cls < SP_N_EXACT_CLASSES ? 2 * sp_class_bw(cls) + 1 : (cls == SP_N_EXACT_CLASSES ? 2 * sp_class_bw(cls) + 1 : 0);
+    const int bw = sp_class_bw(cls);
+    return bw > 0 ? 2 * bw + 1 : 0;
 }
 
 SP_HD int sp_dbl_hi(double x) {
@@ -89,6 +97,10 @@ SP_HD bool sp_bits_all(const SpBits<NW> &b) {  // bits 0..NC-1 all set
     return ok;
 }
 #define SP_BIT(b, o) (((b).w[(o) >> 6] >> ((o) & 63)) & 1)
+template <int N>
+struct SpInt {
+    static constexpr int value = N;
+};
 
 // Returns the guard flags of the instance (0: every consumed row's state / q is safe to use).
 // mi: this lane's cells, cell c (-1 <= c <= NC) at mi[c*STRIDE]; overwritten.
@@ -103,6 +115,10 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
                            int n_rows, bool guard_all = true) {
     constexpr int NW = (NC + 63) / 64;
     constexpr int BW = (NC - 1) / 2;
+    constexpr int CH = 8;  // cells per chunk: mask bits of a chunk never straddle a 64-bit word
+    // the plain bodies of the narrow classes are unrolled completely (the chunks' independent parts overlap the
+    // serial D chain of their neighbours); wide bands keep a loop of two chunks so that the code stays small
+    constexpr int UF = NC <= 45 ? NC / CH : 2;
     const int Lr = in.l_ref, Lq = in.l_query;
     const int bw = sp_hmm_bw(Lr, Lq, in.par_bw);
     int flag = 0;
@@ -115,16 +131,13 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
     const double oms = 1. - sM;
     const double m0 = C.m0f * oms, m1 = C.d_d * oms, m2 = m1, m3 = C.ome_f * oms, m4 = C.e_d * oms;
     const double m6 = C.ome_f, m8 = C.e_d;
-    const double bM = (double) SP_FDIV(C.omd_ff, (float) Lr), bI = (double) SP_FDIV(C.d_f, (float) Lr);
     const double eim1 = SP_HMM_EI * m1, eim4 = SP_HMM_EI * m4;
     const double emA = C.em_match, emB = C.em_mis;
     const SpD2 zero2 = {0., 0.};
+    const bool narrow = bw < BW;  // the instance's own band is narrower than the class's: every row is an edge row
 
     SpBits<NW> p0, p1, p2;  // bit-planes of the reference codes under the band
     p0.clear(); p1.clear(); p2.clear();
-    double Dr[NC];  // forward D state of the last written row
-#pragma unroll
-    for (int o = 0; o < NC; o++) Dr[o] = 0.;
     for (int c = -1; c <= NC; c++) mi[c * STRIDE] = zero2;
 
     // valid cells of row i: columns 1..Lr inside the instance's own band
@@ -136,26 +149,31 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
     // ------------------------------------------------------------------ forward, row 1
     int nr = 0;
     {
+        const double bM = (double) SP_FDIV(C.omd_ff, (float) Lr), bI = (double) SP_FDIV(C.d_f, (float) Lr);
         const int qc = sp_query_code(in, 0);
         const int kend = Lr < bw + 1 ? Lr : bw + 1;
         const int kpl = Lr < BW + 1 ? Lr : BW + 1;  // columns under the virtual band of row 1
+        double *fs = (nr < n_rows && rows[nr].t == 0) ? fsave : nullptr;  // only the stand-alone API asks for row 1
+        if (fs)
+            for (int o = 0; o < NC; o++) *reinterpret_cast<SpD2 *>(fs + 2 * o) = zero2;
         for (int k = 1; k <= kpl; k++) {
             const int rc = in.ref[k - 1], o = k + BW - 1;
             p0.or_bit(o, (uint64_t) (rc & 1));
             p1.or_bit(o, (uint64_t) ((rc >> 1) & 1));
             p2.or_bit(o, (uint64_t) ((rc >> 2) & 1));
             if (k <= kend) {
+                const double M = sp_emis(C, rc, qc) * bM, I = SP_HMM_EI * bI;  // D[1,k] = 0
                 SpD2 v;
-                v.x = sp_emis(C, rc, qc) * bM;
-                v.y = SP_HMM_EI * bI;
+                v.x = SP_FMA(m3, I, m0 * M);
+                v.y = SP_FMA(eim4, I, eim1 * M);
                 mi[o * STRIDE] = v;
+                if (fs) {
+                    SpD2 f = {M, I};
+                    *reinterpret_cast<SpD2 *>(fs + 2 * o) = f;
+                }
             }
         }
-        if (nr < n_rows && rows[nr].t == 0) {  // only the stand-alone API asks for row 1
-            double *fs = fsave + (int64_t) nr * fs_stride;
-            for (int o = 0; o < NC; o++) *reinterpret_cast<SpD2 *>(fs + 2 * o) = mi[o * STRIDE];
-            nr++;
-        }
+        if (fs) nr++;
     }
     // ------------------------------------------------------------------ forward, rows 2..Lq
     // All lanes of the warp walk the rows together up to the longest instance; a lane past its own last
@@ -164,7 +182,7 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
     int t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
     uint32_t qraw_next = Lq >= 2 ? sp_query_raw(in, 1) : 0;
     uint32_t rc_next = 2 + BW <= Lr ? sp_ldg_u8(in.ref + 1 + BW) : 0;  // the column entering at row 2, if any
-    double r = 1.;  // pending power-of-two scale, applied through the coefficients of the row after a check
+    double r = 1.;  // pending power-of-two scale, applied by the (edge) body of the row after a range check
     for (int i = 2; i <= LqW; i++) {
         const bool live = i <= Lq;
         int qc = 0;
@@ -180,71 +198,77 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
                 p2.or_bit(NC - 1, (uint64_t) ((rc_in >> 2) & 1));
             }
         }
-        SpBits<NW> mm, nn, vm;
+        SpBits<NW> mm, nn;
         sp_h2_row_masks(p0, p1, p2, qc, mm, nn);
-        int lo, hi;
-        valid_range(i, lo, hi);
-        sp_bits_range(vm, lo, hi);
-        const bool plain = SP_WARP_ALL(!live || (lo <= 0 && hi >= NC - 1 && !nn.any_below(NC)));
-        const double c0 = m0 * r, c3 = m3 * r, c6 = m6 * r, c1 = eim1 * r, c4 = eim4 * r;
-        r = 1.;
-        {
-            SpD2 a = mi[0];
-            double pM = a.x, pI = a.y, pD = Dr[0];
-            double Mlast = 0., cD = 0.;
-            if (plain) {
+        const bool save = live && t_next + 1 == i;
+        const bool rescale = i % SP_HMMF_RS == 1;  // (warp-uniform) r was derived from the row before
+        // rows whose every cell is a valid column and that need nothing special run the plain body
+        const bool plain = !rescale && SP_WARP_ALL(!live || (!narrow && !save && i > BW && i + BW <= Lr && !nn.any_below(NC)));
+        // cell o: M = e * G_old[o], I = H_old[o+1], D = m8*D[o-1] + m2*M[o-1]; stores G, H of the new row
+        double Gcur = mi[0].x, Mlast = 0., cD = 0.;
+        if (plain) {
+            auto chunk = [&](int o0, auto nc_tag) {
+                constexpr int N = decltype(nc_tag)::value;
+                const uint32_t mb = mm.from(o0);
 #pragma unroll
-                for (int o = 0; o < NC; o++) {
-                    double qM = 0., qI = 0., qD = 0.;
-                    SpD2 v;
-                    if (o + 1 < NC) {
-                        a = mi[(o + 1 < NC ? o + 1 : 0) * STRIDE];
-                        qM = a.x; qI = a.y; qD = Dr[o + 1 < NC ? o + 1 : 0];
-                        v.y = SP_FMA(c1, qM, c4 * qI);
-                    } else {
-                        v.y = 0.;  // old cell NC: the column that just entered, zeros in row i-1
-                    }
-                    const double e = SP_BIT(mm, o) ? emA : emB;
-                    v.x = e * SP_FMA(c0, pM, SP_FMA(c3, pI, c6 * pD));
+                for (int j = 0; j < N; j++) {
+                    const SpD2 a = mi[(o0 + j + 1) * STRIDE];  // (cell NC holds zeros)
+                    const double M = ((mb >> j) & 1 ? emA : emB) * Gcur;
+                    const double I = a.y;
                     cD = SP_FMA(m8, cD, m2 * Mlast);
-                    mi[o * STRIDE] = v;
-                    Dr[o] = cD;
-                    Mlast = v.x;
-                    pM = qM; pI = qI; pD = qD;
+                    SpD2 v;
+                    v.x = SP_FMA(m6, cD, SP_FMA(m3, I, m0 * M));
+                    v.y = SP_FMA(eim4, I, eim1 * M);
+                    mi[(o0 + j) * STRIDE] = v;
+                    Mlast = M;
+                    Gcur = a.x;
                 }
-            } else {
+            };
+#pragma unroll UF
+            for (int o0 = 0; o0 + CH <= NC; o0 += CH) chunk(o0, SpInt<CH>());
+            if constexpr (NC % CH != 0) chunk(NC - NC % CH, SpInt<NC % CH>());
+        } else {
+            SpBits<NW> vm;
+            int lo, hi;
+            valid_range(i, lo, hi);
+            sp_bits_range(vm, lo, hi);
+            const double eA = emA * r, eB = emB * r, eN = r;
+            double *fs = save ? fsave + (int64_t) nr * fs_stride : nullptr;
+            auto chunk = [&](int o0, auto nc_tag) {
+                constexpr int N = decltype(nc_tag)::value;
+                const uint32_t mb = mm.from(o0), nb = nn.from(o0), vb = vm.from(o0);
 #pragma unroll
-                for (int o = 0; o < NC; o++) {
-                    double qM = 0., qI = 0., qD = 0.;
+                for (int j = 0; j < N; j++) {
+                    const SpD2 a = mi[(o0 + j + 1) * STRIDE];
+                    const bool ok = (vb >> j) & 1;
+                    const double e = (nb >> j) & 1 ? eN : ((mb >> j) & 1 ? eA : eB);
+                    const double M = ok ? e * Gcur : 0.;
+                    const double I = ok ? r * a.y : 0.;
+                    cD = ok ? SP_FMA(m8, cD, m2 * Mlast) : 0.;
                     SpD2 v;
-                    if (o + 1 < NC) {
-                        a = mi[(o + 1 < NC ? o + 1 : 0) * STRIDE];
-                        qM = a.x; qI = a.y; qD = Dr[o + 1 < NC ? o + 1 : 0];
-                        v.y = SP_FMA(c1, qM, c4 * qI);
-                    } else {
-                        v.y = 0.;
+                    v.x = SP_FMA(m6, cD, SP_FMA(m3, I, m0 * M));
+                    v.y = SP_FMA(eim4, I, eim1 * M);
+                    mi[(o0 + j) * STRIDE] = v;
+                    if (fs) {
+                        SpD2 f = {M, I};
+                        *reinterpret_cast<SpD2 *>(fs + 2 * (o0 + j)) = f;
                     }
-                    const double e = SP_BIT(nn, o) ? 1. : (SP_BIT(mm, o) ? emA : emB);
-                    v.x = e * SP_FMA(c0, pM, SP_FMA(c3, pI, c6 * pD));
-                    cD = SP_FMA(m8, cD, m2 * Mlast);
-                    if (!SP_BIT(vm, o)) { v.x = 0.; v.y = 0.; cD = 0.; }
-                    mi[o * STRIDE] = v;
-                    Dr[o] = cD;
-                    Mlast = v.x;
-                    pM = qM; pI = qI; pD = qD;
+                    Mlast = M;
+                    Gcur = a.x;
                 }
+            };
+#pragma unroll 2
+            for (int o0 = 0; o0 + CH <= NC; o0 += CH) chunk(o0, SpInt<CH>());
+            if constexpr (NC % CH != 0) chunk(NC - NC % CH, SpInt<NC % CH>());
+            r = 1.;
+            if (save) {
+                nr++;
+                t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
             }
-        }
-        if (live && t_next + 1 == i) {  // consumed row: keep the raw forward M,I
-            double *fs = fsave + (int64_t) nr * fs_stride;
-#pragma unroll 4
-            for (int o = 0; o < NC; o++) *reinterpret_cast<SpD2 *>(fs + 2 * o) = mi[o * STRIDE];
-            nr++;
-            t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
         }
         if (i % SP_HMMF_RS == 0) {  // range check: largest exponent of the row -> exact power-of-two scale
             int mh = 0;
-#pragma unroll
+#pragma unroll 8
             for (int o = 0; o < NC; o++) {
                 const SpD2 a = mi[o * STRIDE];
                 const int hx = sp_dbl_hi(a.x), hy = sp_dbl_hi(a.y);
@@ -254,6 +278,7 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
             const int ex = (mh >> 20) & 0x7ff;
             if (ex == 0 || ex == 0x7ff || mh < 0) {
                 if (live) flag |= SP_HMMF_NUMERIC;
+                r = 1.;
             } else {
                 r = sp_dbl_from_hi((2046 - ex) << 20);  // 2^(1023-ex)
             }
@@ -299,11 +324,12 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
         rows[ri].pmax = pm;
         rows[ri].q = !(t > 0.) ? 0 : (lo > 100 ? 99 : lo);
     };
+    for (int c = -1; c <= NC; c++) mi[c * STRIDE] = zero2;
     if (n_rows > 0) {  // row Lq: constant inside the band (any constant: the posterior is scale-free)
         int lo, hi;
         valid_range(Lq, lo, hi);
         const SpD2 one2 = {1., 1.};
-        for (int o = 0; o < NC; o++) mi[o * STRIDE] = (o >= lo && o <= hi) ? one2 : zero2;
+        for (int o = lo < 0 ? 0 : lo; o <= hi && o < NC; o++) mi[o * STRIDE] = one2;
     }
     nr = n_rows - 1;
     if (nr >= 0 && rows[nr].t + 1 == Lq) {  // stand-alone API only (pipeline rows satisfy t <= Lq-12)
@@ -340,46 +366,62 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
                 p2.shl1_in((uint64_t) ((rc >> 2) & 1));
             }
         }
-        SpBits<NW> mm, nn, vm;
+        SpBits<NW> mm, nn;
         sp_h2_row_masks(p0, p1, p2, qc, mm, nn);
-        int lo, hi;
-        valid_range(i, lo, hi);
-        sp_bits_range(vm, lo, hi);
-        const bool plain = SP_WARP_ALL(!live || (lo <= 0 && hi >= NC - 1 && !nn.any_below(NC)));
-        const double eA = emA * r1, eB = emB * r1, c1 = eim1 * r1, c4 = eim4 * r1;
-        const double eN = r1;
-        r1 = 1.;
+        const bool rescale = j % SP_HMMF_RS == 0 && j > 0;  // (warp-uniform) r1 was derived at the step before
+        // Cells left of column 1 or right of l_ref need no mask here: with row i+1 zero outside its valid cells
+        // the right side stays zero by itself and what appears left of column 1 never flows back into a valid
+        // cell (dependencies only run towards smaller columns) nor into the MAP (f is zero there).  Only an
+        // instance narrower than its class, or an N, takes the edge body.
+        const bool plain = !rescale && SP_WARP_ALL(!live || (!narrow && !nn.any_below(NC)));
         const double m6e = i > 1 ? m6 : 0., m8e = i > 1 ? m8 : 0.;
-        {
-            // cell o needs bM of old cell o (column k+1 of row i+1) and bI of old cell o-1 (column k)
-            double cD = 0.;
-            double bMo = mi[(NC - 1) * STRIDE].x;
-            if (plain) {
+        // cell o needs bM of old cell o (column k+1 of row i+1) and bI of old cell o-1 (column k)
+        double cD = 0., bMo = mi[(NC - 1) * STRIDE].x;
+        if (plain) {
+            auto chunk = [&](int o0, auto nc_tag) {
+                constexpr int N = decltype(nc_tag)::value;
+                const uint32_t mb = mm.from(o0);
 #pragma unroll
-                for (int o = NC - 1; o >= 0; o--) {
-                    const SpD2 a = mi[(o - 1) * STRIDE];  // cell -1 holds zeros
-                    const double e = (SP_BIT(mm, o) ? eA : eB) * bMo;
+                for (int jj = N - 1; jj >= 0; jj--) {
+                    const SpD2 a = mi[(o0 + jj - 1) * STRIDE];  // (cell -1 holds zeros)
+                    const double e = ((mb >> jj) & 1 ? emA : emB) * bMo;
+                    SpD2 v;
+                    v.x = SP_FMA(m2, cD, SP_FMA(e, m0, eim1 * a.y));
+                    v.y = SP_FMA(e, m3, eim4 * a.y);
+                    cD = SP_FMA(m8e, cD, e * m6e);
+                    mi[(o0 + jj) * STRIDE] = v;
+                    bMo = a.x;
+                }
+            };
+            if constexpr (NC % CH != 0) chunk(NC - NC % CH, SpInt<NC % CH>());
+#pragma unroll UF
+            for (int o0 = NC - NC % CH - CH; o0 >= 0; o0 -= CH) chunk(o0, SpInt<CH>());
+        } else {
+            SpBits<NW> vm;
+            int lo, hi;
+            valid_range(i, lo, hi);
+            sp_bits_range(vm, lo, hi);
+            const double eA = emA * r1, eB = emB * r1, eN = r1, c1 = eim1 * r1, c4 = eim4 * r1;
+            auto chunk = [&](int o0, auto nc_tag) {
+                constexpr int N = decltype(nc_tag)::value;
+                const uint32_t mb = mm.from(o0), nb = nn.from(o0), vb = vm.from(o0);
+#pragma unroll
+                for (int jj = N - 1; jj >= 0; jj--) {
+                    const SpD2 a = mi[(o0 + jj - 1) * STRIDE];
+                    const double e = ((nb >> jj) & 1 ? eN : ((mb >> jj) & 1 ? eA : eB)) * bMo;
                     SpD2 v;
                     v.x = SP_FMA(m2, cD, SP_FMA(e, m0, c1 * a.y));
                     v.y = SP_FMA(e, m3, c4 * a.y);
                     cD = SP_FMA(m8e, cD, e * m6e);
-                    mi[o * STRIDE] = v;
+                    if (!((vb >> jj) & 1)) { v.x = 0.; v.y = 0.; cD = 0.; }
+                    mi[(o0 + jj) * STRIDE] = v;
                     bMo = a.x;
                 }
-            } else {
-#pragma unroll
-                for (int o = NC - 1; o >= 0; o--) {
-                    const SpD2 a = mi[(o - 1) * STRIDE];
-                    const double e = (SP_BIT(nn, o) ? eN : (SP_BIT(mm, o) ? eA : eB)) * bMo;
-                    SpD2 v;
-                    v.x = SP_FMA(m2, cD, SP_FMA(e, m0, c1 * a.y));
-                    v.y = SP_FMA(e, m3, c4 * a.y);
-                    cD = SP_FMA(m8e, cD, e * m6e);
-                    if (!SP_BIT(vm, o)) { v.x = 0.; v.y = 0.; cD = 0.; }
-                    mi[o * STRIDE] = v;
-                    bMo = a.x;
-                }
-            }
+            };
+            if constexpr (NC % CH != 0) chunk(NC - NC % CH, SpInt<NC % CH>());
+#pragma unroll 2
+            for (int o0 = NC - NC % CH - CH; o0 >= 0; o0 -= CH) chunk(o0, SpInt<CH>());
+            r1 = 1.;
         }
         if (live && t_next + 1 == i) {
             map_row(nr);
@@ -388,7 +430,7 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
         }
         if (j % SP_HMMF_RS == SP_HMMF_RS - 1) {
             int mh = 0;
-#pragma unroll
+#pragma unroll 8
             for (int o = 0; o < NC; o++) {
                 const SpD2 a = mi[o * STRIDE];
                 const int hx = sp_dbl_hi(a.x), hy = sp_dbl_hi(a.y);
@@ -398,6 +440,7 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
             const int ex = (mh >> 20) & 0x7ff;
             if (ex == 0 || ex == 0x7ff || mh < 0) {
                 if (live) flag |= SP_HMMF_NUMERIC;
+                r1 = 1.;
             } else {
                 r1 = sp_dbl_from_hi((2046 - ex) << 20);
             }

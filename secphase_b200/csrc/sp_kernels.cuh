@@ -415,13 +415,17 @@ __global__ void __launch_bounds__(224, 1) k_hmm2(const SpConst *__restrict__ Cp,
     }
 }
 
-// Fast-arithmetic K4 kernel (sp_hmmf.cuh) for the band classes that have a fully unrolled body: persistent
-// CTAs, one instance per lane, per-warp slab of (NC+2) x 32 double2 (M,I) cells -- the forward D state
-// lives in registers, so eight warps fit an SM.  Every lane of a warp runs an instance (the last,
+// Fast-arithmetic K4 kernel (sp_hmmf.cuh), every band class of the shared-memory kernels: persistent
+// CTAs, one instance per lane, per-warp slab of (NC+2) x 32 16-byte cells and nothing else -- no state
+// is carried in registers between rows, so up to ten warps fit an SM.  Every lane of a warp runs an instance (the last,
 // partial set repeats its last instance with no rows) because the row bodies are chosen by warp votes.
 // Instances whose guard band fired are appended to rerun_list[first ...] for the strict kernel.
+// warps per CTA = 16-byte-cell slabs that fit the 227 KB of shared memory of an SM, at most ten
+constexpr int sp_hmmf_warps(int nc) {
+    return 232448 / ((nc + 2) * 512) > 10 ? 10 : 232448 / ((nc + 2) * 512);
+}
 template <int NC>
-__global__ void __launch_bounds__(256, 1) k_hmmf(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
+__global__ void __launch_bounds__(32 * sp_hmmf_warps(NC), 1) k_hmmf(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
                                                  const int32_t *__restrict__ order, int first, int count,
                                                  const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qbytes,
                                                  const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,

@@ -59,6 +59,10 @@ static int hs_hmmf_dispatch(const SpConst &C, const SpHmmIn &in, int bw, double 
         case 43: return sp_hmmf_instance<1, 43>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
         case 45: return sp_hmmf_instance<1, 45>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
         case 55: return sp_hmmf_instance<1, 55>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
+        case 73: return sp_hmmf_instance<1, 73>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
+        case 97: return sp_hmmf_instance<1, 97>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
+        case 125: return sp_hmmf_instance<1, 125>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
+        case 189: return sp_hmmf_instance<1, 189>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
         default: return -1;
     }
 }

@@ -96,6 +96,7 @@ def test_write_qual_mode_bit_exact_vs_oracle(sp, oracle, name, spreset, ppreset,
         got2 = eng.run(sp.pin_batch(b), slot=1)
         assert np.array_equal(got2["baq_qual"], exp["qual"])
         eng.set_write_qual(False)
+        eng.rng_seed(1)  # (the tie-break stream runs on across the batches of a context)
         got3 = eng.run_debug(b)
         assert "baq_qual" not in got3
         assert not compare_results(exp, got3, label="cuda-after-full")

@@ -11,7 +11,8 @@ for step in "$@"; do
 case $step in
 test)
   ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $out/${tag}_pytest_gpu.log 2>&1
-  tail -5 $out/${tag}_pytest_gpu.log ;;
+  tail -5 $out/${tag}_pytest_gpu.log
+  grep -E "^E  |Error|FAILED" $out/${tag}_pytest_gpu.log | head -20 ;;
 smoke)
   ( timeout 300 python __graft_entry__.py smoke ) > $out/${tag}_smoke.log 2>&1
   tail -2 $out/${tag}_smoke.log ;;
@@ -53,9 +54,12 @@ cli)
 ncu_launch)
   timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_launch.log 2>&1 ;;
-ncu_hmm)
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_hmm -s 8 -c 16 -f -o $out/${tag}_k_hmm \
-    python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --iters 1 > $out/${tag}_ncu_full.log 2>&1 ;;
+ncu_hmm)  # launch list of one stage-bench run, then a full capture of the bulk class kernels of the 3rd batch (<= 64 MiB come back)
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_hmm --csv --log-file $out/${tag}_hmm_launches.csv \
+    python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --iters 1 > $out/${tag}_ncu_l.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_hmmf|k_hmm2' -s 16 -c 8 -f -o $out/${tag}_k_hmm \
+    python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --iters 1 > $out/${tag}_ncu_full.log 2>&1
+  ls -la $out/${tag}_k_hmm.ncu-rep ;;
 ncu_int)
   for p in ont stress; do
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_walk|k_group|k_emit' -s 3 -c 3 -f -o $out/${tag}_int_$p \
