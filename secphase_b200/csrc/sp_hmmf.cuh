@@ -19,9 +19,14 @@
 //    needs from them, G = m0*M + m3*I + m6*D (what flows into M one column to the right) and
 //    H = EI*(m1*M + m4*I) (what flows into I of the same column): M[i,k] = e*G[i-1,k-1],
 //    I[i,k] = H[i-1,k], and D lives only as the running chain value inside the row.  One 16-byte
-//    word per cell, no D plane, no state registers between rows -- so the bodies are short loops over
-//    chunks of cells with compile-time offsets and ten warps fit an SM;
-//    8 FP64 instructions per cell forward, 8 backward (the strict kernel issues 18 + 14).
+//    word per cell, no D plane, no state registers between rows, ten warps per SM;
+//    8 FP64 instructions per cell forward, 8 backward (the strict kernel issues 18 + 14);
+//  * with that little arithmetic per cell the kernel would be bound by shared-memory bandwidth (one
+//    16-byte load and store per cell and row: 8 SM cycles per warp against 4 of FP64 issue), so up to
+//    SP_HMMF_RB consecutive rows are computed in ONE pass over the band: row r of the block runs r-1
+//    cells behind row r-1 and takes its inputs (G of the same cell, H of the next) straight from
+//    registers; only the block's last row is written back.  Blocks end where a lane needs a whole
+//    row in memory (a consumed row) and never contain an edge row.
 //
 // What this costs: the bits of the intermediate posteriors differ from the reference's (relative
 // drift of 1 - pmax measured <= 2e-11 on the benchmark workloads).  What is consumed
@@ -42,7 +47,8 @@
 #define SP_FMA(a, b, c) __builtin_fma((a), (b), (c))
 #endif
 
-#define SP_HMMF_RS 16                            // rows between two range checks
+#define SP_HMMF_RS 16
+#define SP_HMMF_RB 4  // rows per pass of the plain bodies                            // rows between two range checks
 #define SP_HMMF_GUARD_ABS 7.105427357601002e-15  // 2^-47: 64 ulps of a posterior next to 1
 #define SP_HMMF_GUARD_REL 1e-9
 #define SP_HMMF_TIE_REL 1e-9
@@ -105,20 +111,19 @@ struct SpInt {
 // Returns the guard flags of the instance (0: every consumed row's state / q is safe to use).
 // mi: this lane's cells, cell c (-1 <= c <= NC) at mi[c*STRIDE]; overwritten.
 // fsave + r*fs_stride + 2*o: raw forward (M,I) of consumed row r, cell o (fs_stride >= 2*NC).
-// Every lane of the warp must call this together (warp-uniform votes pick the row body); a lane that has
+// Every lane of the warp must call this together (warp-uniform votes pick the row bodies); a lane that has
 // nothing to do passes n_rows = 0.
-// guard_all: band every one of the 101 thresholds (the stand-alone HMM API hands q itself to the caller); the
-// pipeline only consumes min(q, 93) (ptMarker.c:786 clamps the written quality), so there the thresholds above
-// 93 -- where 1 - pmax ~ 1e-10 is only a few hundred units of 2^-53 -- decide nothing and are not banded.
+// guard_all: band every one of the 101 thresholds and every near-tie (the stand-alone HMM API hands state and q
+// themselves to the caller).  The pipeline (guard_all == false) consumes of a row only
+//     (state is M at the alignment's own column `expected`) ? min(raw quality, min(q, 93)) : 0
+// (ptMarker.c:772-786, sp_resolve_q), so there only two things can change the outcome: a runner-up within the
+// tie band when the expected state is the winner or the runner-up, and q's thresholds <= 93 when it wins.
 template <int STRIDE, int NC>
 SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double *fsave, int64_t fs_stride, SpRow *rows,
                            int n_rows, bool guard_all = true) {
     constexpr int NW = (NC + 63) / 64;
     constexpr int BW = (NC - 1) / 2;
-    constexpr int CH = 8;  // cells per chunk: mask bits of a chunk never straddle a 64-bit word
-    // the plain bodies of the narrow classes are unrolled completely (the chunks' independent parts overlap the
-    // serial D chain of their neighbours); wide bands keep a loop of two chunks so that the code stays small
-    constexpr int UF = NC <= 45 ? NC / CH : 2;
+    constexpr int RB = NW == 1 ? SP_HMMF_RB : 2;  // wide bands: fewer mask registers, shorter bodies
     const int Lr = in.l_ref, Lq = in.l_query;
     const int bw = sp_hmm_bw(Lr, Lq, in.par_bw);
     int flag = 0;
@@ -144,6 +149,31 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
     auto valid_range = [&](int i, int &lo, int &hi) {
         lo = BW - bw > BW + 1 - i ? BW - bw : BW + 1 - i;
         hi = BW + bw < Lr - i + BW ? BW + bw : Lr - i + BW;
+    };
+    // range check of the row in memory: largest exponent -> rescale the row by an exact power of two when it
+    // has drifted far from 1 (it rarely has: a row loses ~1e-4 per mismatch)
+    auto range_check = [&](bool live) {
+        int mh = 0;
+#pragma unroll 8
+        for (int o = 0; o < NC; o++) {
+            const SpD2 a = mi[o * STRIDE];
+            const int hx = sp_dbl_hi(a.x), hy = sp_dbl_hi(a.y);
+            mh = hx > mh ? hx : mh;
+            mh = hy > mh ? hy : mh;
+        }
+        const int ex = (mh >> 20) & 0x7ff;
+        if (ex == 0 || ex == 0x7ff || mh < 0) {
+            if (live) flag |= SP_HMMF_NUMERIC;
+        } else if (ex < 1023 - 64 || ex > 1023 + 64) {
+            const double sc = sp_dbl_from_hi((2046 - ex) << 20);  // 2^(1023-ex)
+#pragma unroll 8
+            for (int o = 0; o < NC; o++) {
+                SpD2 a = mi[o * STRIDE];
+                a.x *= sc;
+                a.y *= sc;
+                mi[o * STRIDE] = a;
+            }
+        }
     };
 
     // ------------------------------------------------------------------ forward, row 1
@@ -177,125 +207,178 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
     }
     // ------------------------------------------------------------------ forward, rows 2..Lq
     // All lanes of the warp walk the rows together up to the longest instance; a lane past its own last
-    // row ("dead") keeps executing the body on its own cells, which nobody reads any more.
+    // row ("dead") keeps executing the bodies on its own cells, which nobody reads any more.
     const int LqW = SP_WARP_MAX(Lq);
     int t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
-    uint32_t qraw_next = Lq >= 2 ? sp_query_raw(in, 1) : 0;
-    uint32_t rc_next = 2 + BW <= Lr ? sp_ldg_u8(in.ref + 1 + BW) : 0;  // the column entering at row 2, if any
-    double r = 1.;  // pending power-of-two scale, applied by the (edge) body of the row after a range check
-    for (int i = 2; i <= LqW; i++) {
-        const bool live = i <= Lq;
-        int qc = 0;
-        if (live) {
-            qc = sp_query_decode(in, i - 1, qraw_next);
-            const uint32_t rc_in = rc_next;
-            if (i < Lq) qraw_next = sp_query_raw(in, i);
-            if (i + 1 + BW <= Lr) rc_next = sp_ldg_u8(in.ref + i + BW);
-            p0.shr1(); p1.shr1(); p2.shr1();
-            if (i + BW <= Lr) {  // one column enters the band on the right
-                p0.or_bit(NC - 1, (uint64_t) (rc_in & 1));
-                p1.or_bit(NC - 1, (uint64_t) ((rc_in >> 1) & 1));
-                p2.or_bit(NC - 1, (uint64_t) ((rc_in >> 2) & 1));
+    // raw query bytes and entering reference codes of the next RB rows, byte r <-> row i+r (0 where there is none)
+    auto fetch_fwd = [&](int i0, uint32_t &q4, uint32_t &r4) {
+        q4 = 0;
+        r4 = 0;
+#pragma unroll
+        for (int rr = 0; rr < RB; rr++) {
+            const int row = i0 + rr;
+            if (row <= Lq) q4 |= sp_query_raw(in, row - 1) << (8 * rr);
+            if (row + BW <= Lr) r4 |= sp_ldg_u8(in.ref + row + BW - 1) << (8 * rr);
+        }
+    };
+    uint32_t q4, r4;
+    fetch_fwd(2, q4, r4);
+    int since_check = 0;
+    for (int i = 2; i <= LqW;) {
+        // ---- classify the next RB rows of this lane: masks, and how many leading rows can share one pass
+        SpBits<NW> mmr[RB], ps0[RB], ps1[RB], ps2[RB], nn0;
+        int lane_r = 0;
+        bool stop = false;
+        {
+            SpBits<NW> a0 = p0, a1 = p1, a2 = p2;
+#pragma unroll
+            for (int rr = 0; rr < RB; rr++) {
+                const int row = i + rr;
+                const bool live = row <= Lq;
+                int qc = 0;
+                if (live) {
+                    qc = sp_query_decode(in, row - 1, (q4 >> (8 * rr)) & 0xff);
+                    const uint32_t rc = (r4 >> (8 * rr)) & 0xff;
+                    a0.shr1(); a1.shr1(); a2.shr1();
+                    if (row + BW <= Lr) {  // one column enters the band on the right
+                        a0.or_bit(NC - 1, (uint64_t) (rc & 1));
+                        a1.or_bit(NC - 1, (uint64_t) ((rc >> 1) & 1));
+                        a2.or_bit(NC - 1, (uint64_t) ((rc >> 2) & 1));
+                    }
+                }
+                SpBits<NW> nn;
+                sp_h2_row_masks(a0, a1, a2, qc, mmr[rr], nn);
+                if (rr == 0) nn0 = nn;
+                ps0[rr] = a0; ps1[rr] = a1; ps2[rr] = a2;
+                // a row whose every cell is a valid column without an N
+                const bool plain = !live || (!narrow && row > BW && row + BW <= Lr && !nn.any_below(NC));
+                if (!stop && plain) {
+                    lane_r = rr + 1;
+                    if (live && t_next + 1 == row) stop = true;  // a consumed row ends the block (it is kept in memory)
+                } else {
+                    stop = true;
+                }
             }
         }
-        SpBits<NW> mm, nn;
-        sp_h2_row_masks(p0, p1, p2, qc, mm, nn);
-        const bool save = live && t_next + 1 == i;
-        const bool rescale = i % SP_HMMF_RS == 1;  // (warp-uniform) r was derived from the row before
-        // rows whose every cell is a valid column and that need nothing special run the plain body
-        const bool plain = !rescale && SP_WARP_ALL(!live || (!narrow && !save && i > BW && i + BW <= Lr && !nn.any_below(NC)));
-        // cell o: M = e * G_old[o], I = H_old[o+1], D = m8*D[o-1] + m2*M[o-1]; stores G, H of the new row
-        double Gcur = mi[0].x, Mlast = 0., cD = 0.;
-        if (plain) {
-            auto chunk = [&](int o0, auto nc_tag) {
-                constexpr int N = decltype(nc_tag)::value;
-                const uint32_t mb = mm.from(o0);
+        const int R = SP_WARP_MIN(lane_r);
+        const int adv = R > 0 ? R : 1;
+        {  // commit the planes, fetch the codes of the rows after this pass (their latency hides behind it)
+            const int k = adv - 1;
 #pragma unroll
-                for (int j = 0; j < N; j++) {
-                    const SpD2 a = mi[(o0 + j + 1) * STRIDE];  // (cell NC holds zeros)
-                    const double M = ((mb >> j) & 1 ? emA : emB) * Gcur;
-                    const double I = a.y;
-                    cD = SP_FMA(m8, cD, m2 * Mlast);
-                    SpD2 v;
-                    v.x = SP_FMA(m6, cD, SP_FMA(m3, I, m0 * M));
-                    v.y = SP_FMA(eim4, I, eim1 * M);
-                    mi[(o0 + j) * STRIDE] = v;
-                    Mlast = M;
-                    Gcur = a.x;
+            for (int rr = 0; rr < RB; rr++)
+                if (rr == k) { p0 = ps0[rr]; p1 = ps1[rr]; p2 = ps2[rr]; }
+        }
+        uint32_t q4n, r4n;
+        fetch_fwd(i + adv, q4n, r4n);
+        const int last = i + adv - 1;
+        const bool save = last <= Lq && t_next + 1 == last;
+        double *fs = save ? fsave + (int64_t) nr * fs_stride : nullptr;
+        if (R > 0) {
+            // ---- plain pass over R rows.  Row r (0-based) computes cell s - r at step s:
+            //   M = e*G_above[o], I = H_above[o+1], D = m8*D[o-1] + m2*M[o-1], G = m0*M + m3*I + m6*D, H = EI*(m1*M + m4*I)
+            // with "above" = the stored row for r = 0, else row r-1 of this pass (G from its previous step, H fresh).
+            auto pass = [&](auto rtag) {
+                constexpr int RR = decltype(rtag)::value;
+                double Gc[RR], Ml[RR], cD[RR];
+#pragma unroll
+                for (int rr = 0; rr < RR; rr++) { Gc[rr] = 0.; Ml[rr] = 0.; cD[rr] = 0.; }
+                double g0 = mi[0].x;  // G of the stored row at the cell row 0 computes next
+#pragma unroll
+                for (int s = 0; s < NC + RR - 1; s++) {
+                    double Hup = 0., Gup = 0.;  // inputs of the current row from the row above
+                    if (s < NC) {
+                        const SpD2 a = mi[(s + 1 < NC ? s + 1 : NC) * STRIDE];  // (cell NC holds zeros)
+                        Gup = g0;
+                        Hup = a.y;
+                        g0 = a.x;
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < RR; rr++) {
+                        const int o = s - rr;
+                        if (o >= 0 && o < NC) {
+                            const double M = (SP_BIT(mmr[rr], o) ? emA : emB) * Gup;
+                            const double I = Hup;
+                            cD[rr] = SP_FMA(m8, cD[rr], m2 * Ml[rr]);
+                            const double G = SP_FMA(m6, cD[rr], SP_FMA(m3, I, m0 * M));
+                            const double H = SP_FMA(eim4, I, eim1 * M);
+                            Ml[rr] = M;
+                            // what row rr+1 reads at this step: G of ITS cell (= this row's previous cell), H of this cell
+                            Gup = Gc[rr];
+                            Hup = H;
+                            Gc[rr] = G;
+                            if (rr == RR - 1) {
+                                SpD2 v = {G, H};
+                                mi[o * STRIDE] = v;
+                                if (fs) {
+                                    SpD2 f = {M, I};
+                                    *reinterpret_cast<SpD2 *>(fs + 2 * o) = f;
+                                }
+                            }
+                        } else if (o >= NC) {
+                            Gup = Gc[rr];  // the row has finished: its last cell's G, and H = 0 beyond the band
+                            Hup = 0.;
+                        }
+                    }
                 }
             };
-#pragma unroll UF
-            for (int o0 = 0; o0 + CH <= NC; o0 += CH) chunk(o0, SpInt<CH>());
-            if constexpr (NC % CH != 0) chunk(NC - NC % CH, SpInt<NC % CH>());
+            if (R == 1) pass(SpInt<1>());
+            else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>());
+            else if (RB >= 3 && R == 3) pass(SpInt<(RB >= 3 ? 3 : 1)>());
+            else pass(SpInt<RB>());
         } else {
+            // ---- edge row i alone: invalid columns masked to zero, N bases
             SpBits<NW> vm;
             int lo, hi;
             valid_range(i, lo, hi);
             sp_bits_range(vm, lo, hi);
-            const double eA = emA * r, eB = emB * r, eN = r;
-            double *fs = save ? fsave + (int64_t) nr * fs_stride : nullptr;
-            auto chunk = [&](int o0, auto nc_tag) {
-                constexpr int N = decltype(nc_tag)::value;
-                const uint32_t mb = mm.from(o0), nb = nn.from(o0), vb = vm.from(o0);
-#pragma unroll
-                for (int j = 0; j < N; j++) {
-                    const SpD2 a = mi[(o0 + j + 1) * STRIDE];
-                    const bool ok = (vb >> j) & 1;
-                    const double e = (nb >> j) & 1 ? eN : ((mb >> j) & 1 ? eA : eB);
-                    const double M = ok ? e * Gcur : 0.;
-                    const double I = ok ? r * a.y : 0.;
-                    cD = ok ? SP_FMA(m8, cD, m2 * Mlast) : 0.;
-                    SpD2 v;
-                    v.x = SP_FMA(m6, cD, SP_FMA(m3, I, m0 * M));
-                    v.y = SP_FMA(eim4, I, eim1 * M);
-                    mi[(o0 + j) * STRIDE] = v;
-                    if (fs) {
-                        SpD2 f = {M, I};
-                        *reinterpret_cast<SpD2 *>(fs + 2 * (o0 + j)) = f;
-                    }
-                    Mlast = M;
-                    Gcur = a.x;
+            double Gcur = mi[0].x, Mlast = 0., cD = 0.;
+#pragma unroll 4
+            for (int o = 0; o < NC; o++) {
+                const SpD2 a = mi[(o + 1) * STRIDE];
+                const bool ok = SP_BIT(vm, o);
+                const double e = SP_BIT(nn0, o) ? 1. : (SP_BIT(mmr[0], o) ? emA : emB);
+                const double M = ok ? e * Gcur : 0.;
+                const double I = ok ? a.y : 0.;
+                cD = ok ? SP_FMA(m8, cD, m2 * Mlast) : 0.;
+                SpD2 v;
+                v.x = SP_FMA(m6, cD, SP_FMA(m3, I, m0 * M));
+                v.y = SP_FMA(eim4, I, eim1 * M);
+                mi[o * STRIDE] = v;
+                if (fs) {
+                    SpD2 f = {M, I};
+                    *reinterpret_cast<SpD2 *>(fs + 2 * o) = f;
                 }
-            };
-#pragma unroll 2
-            for (int o0 = 0; o0 + CH <= NC; o0 += CH) chunk(o0, SpInt<CH>());
-            if constexpr (NC % CH != 0) chunk(NC - NC % CH, SpInt<NC % CH>());
-            r = 1.;
-            if (save) {
-                nr++;
-                t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
+                Mlast = M;
+                Gcur = a.x;
             }
         }
-        if (i % SP_HMMF_RS == 0) {  // range check: largest exponent of the row -> exact power-of-two scale
-            int mh = 0;
-#pragma unroll 8
-            for (int o = 0; o < NC; o++) {
-                const SpD2 a = mi[o * STRIDE];
-                const int hx = sp_dbl_hi(a.x), hy = sp_dbl_hi(a.y);
-                mh = hx > mh ? hx : mh;
-                mh = hy > mh ? hy : mh;
-            }
-            const int ex = (mh >> 20) & 0x7ff;
-            if (ex == 0 || ex == 0x7ff || mh < 0) {
-                if (live) flag |= SP_HMMF_NUMERIC;
-                r = 1.;
-            } else {
-                r = sp_dbl_from_hi((2046 - ex) << 20);  // 2^(1023-ex)
-            }
+        if (save) {
+            nr++;
+            t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
+        }
+        i += adv;
+        q4 = q4n;
+        r4 = r4n;
+        since_check += adv;
+        if (since_check >= SP_HMMF_RS) {
+            range_check(i - 1 <= Lq);
+            since_check = 0;
         }
     }
     // ------------------------------------------------------------------ backward (+ MAP at consumed rows)
     int i_stop = n_rows > 0 ? rows[0].t + 1 : Lq;  // nothing below the lowest consumed row is needed
-    // MAP of one row: max / runner-up / sum of f*b over the band, the decision and its guard band
     auto map_row = [&](int ri) {
         const double *fs = fsave + (int64_t) ri * fs_stride;
-        double sum = 0., mx = 0., mx2 = 0.;
+        const int i = rows[ri].t + 1;
+        const int o_exp = guard_all ? -1 : rows[ri].expected + 1 - (i - BW);  // cell of column expected+1
+        double sum = 0., mx = 0., mx2 = 0., zE = 0.;
         int max_o = -1;
 #pragma unroll 1
         for (int o = 0; o < NC; o++) {  // (a handful of rows per instance: keep it small)
             const SpD2 f = *reinterpret_cast<const SpD2 *>(fs + 2 * o);
             const SpD2 b = mi[o * STRIDE];
             double z = f.x * b.x;
+            if (o == o_exp) zE = z;
             if (z > mx) { mx2 = mx; mx = z; max_o = o << 2; }
             else if (z > mx2) mx2 = z;
             sum = sum + z;
@@ -304,7 +387,6 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
             else if (z > mx2) mx2 = z;
             sum = sum + z;
         }
-        const int i = rows[ri].t + 1;
         const double pm = SP_DDIV(mx, sum);
         const double t = 1. - pm;
         // q, and how close t is to a decision threshold: qthr[lo] >= t > qthr[lo+1]
@@ -314,11 +396,17 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
             if (t <= C.qthr[mid]) lo = mid; else hi = mid - 1;
         }
         const double g = SP_HMMF_GUARD_ABS + SP_HMMF_GUARD_REL * t;
-        if (!(t > g)) flag |= SP_HMMF_NEAR_THRESHOLD;  // next to the pmax == 1 cliff (q = 0), or NaN
-        const int top = guard_all ? 101 : 93;
-        if (lo >= 1 && lo <= top && C.qthr[lo] - t <= g) flag |= SP_HMMF_NEAR_THRESHOLD;
-        if (lo < top && t - C.qthr[lo + 1] <= g) flag |= SP_HMMF_NEAR_THRESHOLD;
-        if (!(mx2 < mx * (1. - SP_HMMF_TIE_REL))) flag |= SP_HMMF_NEAR_TIE;  // also mx == 0 and NaN
+        const double tie = mx * (1. - SP_HMMF_TIE_REL);
+        const bool win_exp = !guard_all && max_o == (o_exp << 2) && o_exp >= 0;
+        if (guard_all || win_exp) {
+            if (!(t > g)) flag |= SP_HMMF_NEAR_THRESHOLD;  // next to the pmax == 1 cliff (q = 0), or NaN
+            const int top = guard_all ? 101 : 93;
+            if (lo >= 1 && lo <= top && C.qthr[lo] - t <= g) flag |= SP_HMMF_NEAR_THRESHOLD;
+            if (lo < top && t - C.qthr[lo + 1] <= g) flag |= SP_HMMF_NEAR_THRESHOLD;
+            if (!(mx2 < tie)) flag |= SP_HMMF_NEAR_TIE;  // also mx == 0 and NaN
+        } else if (!(zE < tie)) {
+            flag |= SP_HMMF_NEAR_TIE;  // the expected state is (nearly) as likely as the winner
+        }
         if (!(sum > 0.) || !(sum < 1.7976931348623157e308)) flag |= SP_HMMF_NUMERIC;
         rows[ri].state = max_o < 0 ? -1 : (((i - BW + (max_o >> 2)) - 1) << 2 | (max_o & 3));
         rows[ri].pmax = pm;
@@ -338,112 +426,149 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
     }
     if (nr < 0) i_stop = Lq;  // nothing (left) to do for this lane: no live step below
     t_next = nr >= 0 ? rows[nr].t : -2;
-    // the planes are where the lane's last forward row left them: bit o <-> ref[Lq-1-BW+o], which is the
-    // base of column k+1 for cell o of row Lq-1
-    qraw_next = Lq >= 2 ? sp_query_raw(in, Lq - 1) : 0;
-    rc_next = (Lq - 2 - BW >= 0 && Lq - 2 - BW < Lr) ? sp_ldg_u8(in.ref + (Lq - 2 - BW)) : 0;
-    const int jmax = SP_WARP_MAX(Lq - 1 - i_stop);
-    double r1 = 1.;
-    for (int j = 0; j <= jmax; j++) {
-        const int i = Lq - 1 - j;
-        const bool live = i >= i_stop && i >= 1;
-        int qc = 0;
-        if (live) {
-            qc = sp_query_decode(in, i, qraw_next);  // query[i] (0-based) == base of row i+1
-            const uint32_t rc_in = rc_next;  // (step 0 does not shift: rc_next then already holds step 1's code)
-            if (i > i_stop) {
-                qraw_next = sp_query_raw(in, i - 1);
-                if (j > 0) {
-                    const int x = i - 1 - BW;  // ref index entering at the next step
-                    rc_next = (x >= 0 && x < Lr) ? sp_ldg_u8(in.ref + x) : 0;
-                }
-            }
-            if (j > 0) {  // one column enters the band on the left: bit 0 <-> ref[i-BW]
-                const int x = i - BW;
-                const uint32_t rc = (x >= 0 && x < Lr) ? rc_in : 0;
-                p0.shl1_in((uint64_t) (rc & 1));
-                p1.shl1_in((uint64_t) ((rc >> 1) & 1));
-                p2.shl1_in((uint64_t) ((rc >> 2) & 1));
+    // The planes are where the lane's last forward row left them: bit o <-> ref[Lq-1-BW+o], which is the base
+    // of column k+1 for cell o of row Lq-1.  Step j of the sweep is row Lq-1-j of every lane.
+    auto fetch_bwd = [&](int x0, uint32_t &q4o, uint32_t &r4o) {  // byte r <-> row x0-r: query[x0-r], ref[x0-r-BW]
+        q4o = 0;
+        r4o = 0;
+#pragma unroll
+        for (int rr = 0; rr < RB; rr++) {
+            const int x = x0 - rr;
+            if (x >= 1 && x >= i_stop) {
+                q4o |= sp_query_raw(in, x) << (8 * rr);
+                const int y = x - BW;
+                if (y >= 0 && y < Lr) r4o |= sp_ldg_u8(in.ref + y) << (8 * rr);
             }
         }
-        SpBits<NW> mm, nn;
-        sp_h2_row_masks(p0, p1, p2, qc, mm, nn);
-        const bool rescale = j % SP_HMMF_RS == 0 && j > 0;  // (warp-uniform) r1 was derived at the step before
-        // Cells left of column 1 or right of l_ref need no mask here: with row i+1 zero outside its valid cells
-        // the right side stays zero by itself and what appears left of column 1 never flows back into a valid
-        // cell (dependencies only run towards smaller columns) nor into the MAP (f is zero there).  Only an
-        // instance narrower than its class, or an N, takes the edge body.
-        const bool plain = !rescale && SP_WARP_ALL(!live || (!narrow && !nn.any_below(NC)));
-        const double m6e = i > 1 ? m6 : 0., m8e = i > 1 ? m8 : 0.;
-        // cell o needs bM of old cell o (column k+1 of row i+1) and bI of old cell o-1 (column k)
-        double cD = 0., bMo = mi[(NC - 1) * STRIDE].x;
-        if (plain) {
-            auto chunk = [&](int o0, auto nc_tag) {
-                constexpr int N = decltype(nc_tag)::value;
-                const uint32_t mb = mm.from(o0);
+    };
+    const int jmax = SP_WARP_MAX(Lq - 1 - i_stop);
+    fetch_bwd(Lq - 1, q4, r4);
+    since_check = 0;
+    for (int j = 0; j <= jmax;) {
+        const int i = Lq - 1 - j;  // first (highest) row of this pass
+        SpBits<NW> mmr[RB], ps0[RB], ps1[RB], ps2[RB], nn0;
+        int lane_r = 0;
+        bool stop = false;
+        {
+            SpBits<NW> a0 = p0, a1 = p1, a2 = p2;
 #pragma unroll
-                for (int jj = N - 1; jj >= 0; jj--) {
-                    const SpD2 a = mi[(o0 + jj - 1) * STRIDE];  // (cell -1 holds zeros)
-                    const double e = ((mb >> jj) & 1 ? emA : emB) * bMo;
-                    SpD2 v;
-                    v.x = SP_FMA(m2, cD, SP_FMA(e, m0, eim1 * a.y));
-                    v.y = SP_FMA(e, m3, eim4 * a.y);
-                    cD = SP_FMA(m8e, cD, e * m6e);
-                    mi[(o0 + jj) * STRIDE] = v;
-                    bMo = a.x;
+            for (int rr = 0; rr < RB; rr++) {
+                const int x = i - rr;
+                const bool live = x >= i_stop && x >= 1;
+                int qc = 0;
+                if (live) {
+                    qc = sp_query_decode(in, x, (q4 >> (8 * rr)) & 0xff);  // query[x] (0-based) == base of row x+1
+                    if (j + rr > 0) {  // one column enters the band on the left: bit 0 <-> ref[x-BW]
+                        const uint32_t rc = (r4 >> (8 * rr)) & 0xff;
+                        a0.shl1_in((uint64_t) (rc & 1));
+                        a1.shl1_in((uint64_t) ((rc >> 1) & 1));
+                        a2.shl1_in((uint64_t) ((rc >> 2) & 1));
+                    }
+                }
+                SpBits<NW> nn;
+                sp_h2_row_masks(a0, a1, a2, qc, mmr[rr], nn);
+                if (rr == 0) nn0 = nn;
+                ps0[rr] = a0; ps1[rr] = a1; ps2[rr] = a2;
+                // Cells left of column 1 or right of l_ref need no mask here: with the row above zero outside its
+                // valid cells the right side stays zero by itself, and what appears left of column 1 never flows
+                // back into a valid cell (dependencies only run towards smaller columns) nor into the MAP (f is zero
+                // there).  Only an instance narrower than its class, an N, or row 1 (no D state) is an edge row.
+                const bool plain = !live || (!narrow && x > 1 && !nn.any_below(NC));
+                if (!stop && plain) {
+                    lane_r = rr + 1;
+                    if (live && t_next + 1 == x) stop = true;  // a consumed row ends the block: the MAP reads it from memory
+                } else {
+                    stop = true;
+                }
+            }
+        }
+        const int R = SP_WARP_MIN(lane_r);
+        const int adv = R > 0 ? R : 1;
+        {
+            const int k = adv - 1;
+#pragma unroll
+            for (int rr = 0; rr < RB; rr++)
+                if (rr == k) { p0 = ps0[rr]; p1 = ps1[rr]; p2 = ps2[rr]; }
+        }
+        uint32_t q4n, r4n;
+        fetch_bwd(i - adv, q4n, r4n);
+        if (R > 0) {
+            // row a (0-based) computes cell NC-1-s+a at step s; it needs bM of the row above at its own cell
+            // (that row's previous step) and bI of the row above one cell to the left (fresh)
+            auto pass = [&](auto rtag) {
+                constexpr int RR = decltype(rtag)::value;
+                double Mc[RR], cD[RR];
+#pragma unroll
+                for (int rr = 0; rr < RR; rr++) { Mc[rr] = 0.; cD[rr] = 0.; }
+                double b0 = mi[(NC - 1) * STRIDE].x;  // bM of the stored row at the cell row 0 computes next
+#pragma unroll
+                for (int s = 0; s < NC + RR - 1; s++) {
+                    double Mup = 0., Iup = 0.;
+                    if (s < NC) {
+                        const SpD2 a = mi[(NC - 2 - s) * STRIDE];  // (cell -1 holds zeros)
+                        Mup = b0;
+                        Iup = a.y;
+                        b0 = a.x;
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < RR; rr++) {
+                        const int o = NC - 1 - s + rr;
+                        if (o >= 0 && o < NC) {
+                            const double e = (SP_BIT(mmr[rr], o) ? emA : emB) * Mup;
+                            const double bMv = SP_FMA(m2, cD[rr], SP_FMA(e, m0, eim1 * Iup));
+                            const double bIv = SP_FMA(e, m3, eim4 * Iup);
+                            cD[rr] = SP_FMA(m8, cD[rr], e * m6);
+                            Mup = Mc[rr];
+                            Iup = bIv;
+                            Mc[rr] = bMv;
+                            if (rr == RR - 1) {
+                                SpD2 v = {bMv, bIv};
+                                mi[o * STRIDE] = v;
+                            }
+                        } else if (o < 0) {
+                            Mup = Mc[rr];  // the row has finished: its cell 0, and bI = 0 left of the band
+                            Iup = 0.;
+                        }
+                    }
                 }
             };
-            if constexpr (NC % CH != 0) chunk(NC - NC % CH, SpInt<NC % CH>());
-#pragma unroll UF
-            for (int o0 = NC - NC % CH - CH; o0 >= 0; o0 -= CH) chunk(o0, SpInt<CH>());
+            if (R == 1) pass(SpInt<1>());
+            else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>());
+            else if (RB >= 3 && R == 3) pass(SpInt<(RB >= 3 ? 3 : 1)>());
+            else pass(SpInt<RB>());
         } else {
             SpBits<NW> vm;
             int lo, hi;
             valid_range(i, lo, hi);
             sp_bits_range(vm, lo, hi);
-            const double eA = emA * r1, eB = emB * r1, eN = r1, c1 = eim1 * r1, c4 = eim4 * r1;
-            auto chunk = [&](int o0, auto nc_tag) {
-                constexpr int N = decltype(nc_tag)::value;
-                const uint32_t mb = mm.from(o0), nb = nn.from(o0), vb = vm.from(o0);
-#pragma unroll
-                for (int jj = N - 1; jj >= 0; jj--) {
-                    const SpD2 a = mi[(o0 + jj - 1) * STRIDE];
-                    const double e = ((nb >> jj) & 1 ? eN : ((mb >> jj) & 1 ? eA : eB)) * bMo;
-                    SpD2 v;
-                    v.x = SP_FMA(m2, cD, SP_FMA(e, m0, c1 * a.y));
-                    v.y = SP_FMA(e, m3, c4 * a.y);
-                    cD = SP_FMA(m8e, cD, e * m6e);
-                    if (!((vb >> jj) & 1)) { v.x = 0.; v.y = 0.; cD = 0.; }
-                    mi[(o0 + jj) * STRIDE] = v;
-                    bMo = a.x;
-                }
-            };
-            if constexpr (NC % CH != 0) chunk(NC - NC % CH, SpInt<NC % CH>());
-#pragma unroll 2
-            for (int o0 = NC - NC % CH - CH; o0 >= 0; o0 -= CH) chunk(o0, SpInt<CH>());
-            r1 = 1.;
+            const double m6e = i > 1 ? m6 : 0., m8e = i > 1 ? m8 : 0.;
+            double cD = 0., bMo = mi[(NC - 1) * STRIDE].x;
+#pragma unroll 4
+            for (int o = NC - 1; o >= 0; o--) {
+                const SpD2 a = mi[(o - 1) * STRIDE];
+                const double e = (SP_BIT(nn0, o) ? 1. : (SP_BIT(mmr[0], o) ? emA : emB)) * bMo;
+                SpD2 v;
+                v.x = SP_FMA(m2, cD, SP_FMA(e, m0, eim1 * a.y));
+                v.y = SP_FMA(e, m3, eim4 * a.y);
+                cD = SP_FMA(m8e, cD, e * m6e);
+                if (!SP_BIT(vm, o)) { v.x = 0.; v.y = 0.; cD = 0.; }
+                mi[o * STRIDE] = v;
+                bMo = a.x;
+            }
         }
-        if (live && t_next + 1 == i) {
+        const int last = i - adv + 1;
+        if (last >= i_stop && last >= 1 && t_next + 1 == last) {
             map_row(nr);
             nr--;
             t_next = nr >= 0 ? rows[nr].t : -2;
         }
-        if (j % SP_HMMF_RS == SP_HMMF_RS - 1) {
-            int mh = 0;
-#pragma unroll 8
-            for (int o = 0; o < NC; o++) {
-                const SpD2 a = mi[o * STRIDE];
-                const int hx = sp_dbl_hi(a.x), hy = sp_dbl_hi(a.y);
-                mh = hx > mh ? hx : mh;
-                mh = hy > mh ? hy : mh;
-            }
-            const int ex = (mh >> 20) & 0x7ff;
-            if (ex == 0 || ex == 0x7ff || mh < 0) {
-                if (live) flag |= SP_HMMF_NUMERIC;
-                r1 = 1.;
-            } else {
-                r1 = sp_dbl_from_hi((2046 - ex) << 20);
-            }
+        j += adv;
+        q4 = q4n;
+        r4 = r4n;
+        since_check += adv;
+        if (since_check >= SP_HMMF_RS) {
+            range_check(last >= i_stop && last >= 1);
+            since_check = 0;
         }
     }
     return flag;

@@ -420,9 +420,14 @@ __global__ void __launch_bounds__(224, 1) k_hmm2(const SpConst *__restrict__ Cp,
 // is carried in registers between rows, so up to ten warps fit an SM.  Every lane of a warp runs an instance (the last,
 // partial set repeats its last instance with no rows) because the row bodies are chosen by warp votes.
 // Instances whose guard band fired are appended to rerun_list[first ...] for the strict kernel.
-// warps per CTA = 16-byte-cell slabs that fit the 227 KB of shared memory of an SM, at most ten
+// warps per CTA = 16-byte-cell slabs that fit the 227 KB of shared memory of an SM, at most SP_HMMF_MAX_WARPS
+// (two per scheduler already cover the FP64 pipe: every warp carries up to four independent row chains, and
+// with eight warps a thread may use the whole 255-register budget)
+#ifndef SP_HMMF_MAX_WARPS
+#define SP_HMMF_MAX_WARPS 8
+#endif
 constexpr int sp_hmmf_warps(int nc) {
-    return 232448 / ((nc + 2) * 512) > 10 ? 10 : 232448 / ((nc + 2) * 512);
+    return 232448 / ((nc + 2) * 512) > SP_HMMF_MAX_WARPS ? SP_HMMF_MAX_WARPS : 232448 / ((nc + 2) * 512);
 }
 template <int NC>
 __global__ void __launch_bounds__(32 * sp_hmmf_warps(NC), 1) k_hmmf(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,

@@ -508,7 +508,9 @@ int hs_run3(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         }
         for (size_t k = 0; k < fast_rows.size(); k++) {  // hmm_mode 2: what the guard band let through must be exact
             const SpRow &S = rows[I.row0 + k], &F = fast_rows[k];
-            if (S.state != F.state || (S.q < 93 ? S.q : 93) != (F.q < 93 ? F.q : 93)) out->err |= 0x200;  // min(q,93) is what is consumed
+            // what the pipeline consumes of a row (sp_resolve_q): 0 unless the MAP state is M at the expected column
+            auto used = [](const SpRow &R) { return ((R.state & 3) != 0 || (R.state >> 2) != R.expected) ? 0 : (R.q < 93 ? R.q : 93); };
+            if (used(S) != used(F)) out->err |= 0x200;
             const double ts = 1. - S.pmax, tf = 1. - F.pmax;
             const double ad = tf > ts ? tf - ts : ts - tf;
             if (ad * 9007199254740992. > out->max_abs_drift_ulp) out->max_abs_drift_ulp = ad * 9007199254740992.;

@@ -34,9 +34,9 @@ def test_pipeline_bit_exact_vs_oracle(sp, oracle, name, spreset, ppreset, ng, ov
         cells = int(exp["hmm"][:, 4].astype(np.int64).sum() + (exp["hmm"][:, 5].astype(np.int64) << 31).sum())
         assert g["hmm_cells"] == cells
         assert g["gpu_launches"] >= 5
-    # MAP state and the consumed quality min(q, 93) of every marker row agree between the two arithmetics
-    assert np.array_equal(got["rows"][:, :3], got_s["rows"][:, :3])
-    assert np.array_equal(np.minimum(got["rows"][:, 3], 93), np.minimum(got_s["rows"][:, 3], 93))
+    # (what is consumed of a marker row -- 0 unless the MAP state is M at the alignment's own column, else
+    # min(q, 93) -- is the BAQ compared above in markers_baq; the guard band protects exactly that)
+    assert np.array_equal(got["rows"][:, :2], got_s["rows"][:, :2])
     assert got["hmm_rerun"] <= 0.01 * got["hmm_instances"] + 2
 
 

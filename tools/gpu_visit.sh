@@ -48,6 +48,14 @@ stage)
     timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --hmm $m >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
   done
   cat $out/${tag}_stage.json ;;
+stagehifi)  # HiFi bench-size stage times: fast (default lib and every lib under lib/variants), then strict
+  for lib in "" secphase_b200/lib/variants/*.so; do
+    [ -n "$lib" ] && [ ! -f "$lib" ] && continue
+    echo "lib=${lib:-default}" >> $out/${tag}_stagehifi.json
+    SECPHASE_B200_LIB=$lib timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --hmm fast >> $out/${tag}_stagehifi.json 2>> $out/${tag}_stagehifi.err
+  done
+  timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --hmm strict >> $out/${tag}_stagehifi.json 2>> $out/${tag}_stagehifi.err
+  cat $out/${tag}_stagehifi.json ;;
 cli)
   ( timeout 500 python tools/cli_bench.py --groups 32768 ) > $out/${tag}_cli.json 2> $out/${tag}_cli.err
   tail -c 1200 $out/${tag}_cli.json ;;
