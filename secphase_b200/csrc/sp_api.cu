@@ -659,7 +659,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
     if ((rc = S.fin_wide.ensure(24 * (size_t) (pl.total_ent + 1)))) return rc;
     if ((rc = S.fin.ensure(24 * (size_t) (pl.total_ent + 1)))) return rc;
     if ((rc = S.totals.ensure(sizeof(SpTotals)))) return rc;
-    if ((rc = S.bins.ensure(4 * (size_t) ((SP_N_CLASSES + 1) * SP_SORT_LBINS)))) return rc;
+    if ((rc = S.bins.ensure(4 * (size_t) (SP_SORT_BWBINS * SP_SORT_LBINS)))) return rc;
     if ((rc = S.class_start.ensure(4 * (SP_N_CLASSES + 3)))) return rc;
     if ((rc = S.h_tot.ensure(sizeof(SpTotals)))) return rc;
     if ((rc = S.h_gout.ensure(sizeof(SpGroupOut) * (G + 1)))) return rc;
@@ -918,7 +918,7 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
             k_fill_rows<<<(T.n_items * 32 + 255) / 256, 256, 0, st>>>(P, S.items.as<SpItem>(), T.n_items, S.rows.as<SpRow>());
             S.launches++;
         }
-        const int nbins = (SP_N_CLASSES + 1) * SP_SORT_LBINS;
+        const int nbins = SP_SORT_BWBINS * SP_SORT_LBINS;
         CK(cudaMemsetAsync(S.bins.p, 0, 4 * (size_t) nbins, st));
         k_sort_hist<<<(T.n_items + 255) / 256, 256, 0, st>>>(S.items.as<SpItem>(), T.n_items, S.bins.as<int32_t>());
         k_sort_scan<<<1, 1024, 0, st>>>(S.bins.as<int32_t>(), nbins, S.class_start.as<int32_t>());
@@ -1506,13 +1506,13 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
     if (fast && sp_hmmf_class_cells(sp_band_class(max_bw)) > fs_cells) fs_cells = sp_hmmf_class_cells(sp_band_class(max_bw));
     const int64_t fs_stride = 2 * fs_cells;
     if ((rc = S.fsave.ensure(8 * (size_t) (n_rows * fs_stride + 2)))) return rc;
-    if ((rc = S.bins.ensure(4 * (size_t) ((SP_N_CLASSES + 1) * SP_SORT_LBINS)))) return rc;
+    if ((rc = S.bins.ensure(4 * (size_t) (SP_SORT_BWBINS * SP_SORT_LBINS)))) return rc;
     if ((rc = S.class_start.ensure(4 * (SP_N_CLASSES + 3)))) return rc;
     CK(cudaMemcpyAsync(d_ref.p, ref_pool, (size_t) ref_total, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_q.p, query_pool, (size_t) q_total, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S.items.p, items.data(), sizeof(SpItem) * (size_t) n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S.rows.p, rows.data(), sizeof(SpRow) * (size_t) n_rows, cudaMemcpyHostToDevice, st));
-    const int nbins = (SP_N_CLASSES + 1) * SP_SORT_LBINS;
+    const int nbins = SP_SORT_BWBINS * SP_SORT_LBINS;
     CK(cudaMemsetAsync(S.bins.p, 0, 4 * (size_t) nbins, st));
     k_sort_hist<<<(n + 255) / 256, 256, 0, st>>>(S.items.as<SpItem>(), n, S.bins.as<int32_t>());
     k_sort_scan<<<1, 1024, 0, st>>>(S.bins.as<int32_t>(), nbins, S.class_start.as<int32_t>());

@@ -10,7 +10,8 @@
 //    transition coefficients (power-of-two scaling commutes with rounding: the results are those of
 //    an unscaled evaluation in a wider exponent range); hence no 1/s[i] array in HBM and no division
 //    per row;
-//  * a virtual band of NC = 2*BW+1 cells that slides by exactly one column per row for every row
+//  * a virtual band of NC = 2*BW+1 cells (BW = the widest band among the warp's 32 instances; instances
+//    are sorted by band width, so almost every warp is uniform) that slides by exactly one column per row
 //    (cell o of row i is column i-BW+o); columns outside [1, l_ref] or outside the instance's own
 //    band |k-i| <= bw are held at exact zeros -- which is what the reference's zero padding means --
 //    by an edge variant of the row body that runs only for rows that have such columns (or an N, or a
@@ -26,7 +27,8 @@
 //    SP_HMMF_RB consecutive rows are computed in ONE pass over the band: row r of the block runs r-1
 //    cells behind row r-1 and takes its inputs (G of the same cell, H of the next) straight from
 //    registers; only the block's last row is written back.  Blocks end where a lane needs a whole
-//    row in memory (a consumed row) and never contain an edge row.
+//    row in memory (a consumed row) and never contain an edge row.  The passes are loops over chunks of
+//    eight cells (the band width is a run-time value), small enough to live in the instruction cache.
 //
 // What this costs: the bits of the intermediate posteriors differ from the reference's (relative
 // drift of 1 - pmax measured <= 2e-11 on the benchmark workloads).  What is consumed
@@ -103,14 +105,43 @@ SP_HD bool sp_bits_all(const SpBits<NW> &b) {  // bits 0..NC-1 all set
     return ok;
 }
 #define SP_BIT(b, o) (((b).w[(o) >> 6] >> ((o) & 63)) & 1)
+template <int NW>
+SP_HD uint32_t sp_bit_rt(const SpBits<NW> &b, int o) {  // bit o, run-time position (selects, no indexing)
+    uint64_t x = b.w[0];
+#pragma unroll
+    for (int k = 1; k < NW; k++)
+        if ((o >> 6) == k) x = b.w[k];
+    return (uint32_t) (x >> (o & 63)) & 1;
+}
+template <int NW>
+SP_HD uint32_t sp_bits8_rt(const SpBits<NW> &b, int o) {  // bits o..o+7 (o >= 0), may straddle two words
+    uint64_t lo = b.w[0], hi = NW > 1 ? b.w[NW > 1 ? 1 : 0] : 0;
+#pragma unroll
+    for (int k = 1; k < NW; k++)
+        if ((o >> 6) == k) { lo = b.w[k]; hi = k + 1 < NW ? b.w[k + 1 < NW ? k + 1 : k] : 0; }
+    const int sh = o & 63;
+    uint64_t x = lo >> sh;
+    if (sh > 56) x |= hi << (64 - sh);
+    return (uint32_t) x & 0xff;
+}
 template <int N>
 struct SpInt {
     static constexpr int value = N;
 };
+// f(SpInt<A>()), f(SpInt<A+1>()), ... f(SpInt<B-1>()): a loop whose counter is a compile-time constant in the body
+template <int A, int B, class F>
+SP_HD void sp_static_for(F &&f) {
+    if constexpr (A < B) {
+        f(SpInt<A>());
+        sp_static_for<A + 1, B>(f);
+    }
+}
 
 // Returns the guard flags of the instance (0: every consumed row's state / q is safe to use).
-// mi: this lane's cells, cell c (-1 <= c <= NC) at mi[c*STRIDE]; overwritten.
-// fsave + r*fs_stride + 2*o: raw forward (M,I) of consumed row r, cell o (fs_stride >= 2*NC).
+// mi: this lane's cells, cell c (-1 <= c <= 2*BW+1) at mi[c*STRIDE]; overwritten.
+// BW: half-width of the virtual band, >= the instance's own band half-width and the same for every lane of the
+// warp (the kernel passes the warp's maximum); NW: 64-bit words of a row mask, 64*NW >= 2*BW+1.
+// fsave + r*fs_stride + 2*o: raw forward (M,I) of consumed row r, cell o (fs_stride >= 2*(2*BW+1)).
 // Every lane of the warp must call this together (warp-uniform votes pick the row bodies); a lane that has
 // nothing to do passes n_rows = 0.
 // guard_all: band every one of the 101 thresholds and every near-tie (the stand-alone HMM API hands state and q
@@ -118,16 +149,15 @@ struct SpInt {
 //     (state is M at the alignment's own column `expected`) ? min(raw quality, min(q, 93)) : 0
 // (ptMarker.c:772-786, sp_resolve_q), so there only two things can change the outcome: a runner-up within the
 // tie band when the expected state is the winner or the runner-up, and q's thresholds <= 93 when it wins.
-template <int STRIDE, int NC>
-SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double *fsave, int64_t fs_stride, SpRow *rows,
-                           int n_rows, bool guard_all = true) {
-    constexpr int NW = (NC + 63) / 64;
-    constexpr int BW = (NC - 1) / 2;
-    constexpr int RB = NW == 1 ? SP_HMMF_RB : 2;  // wide bands: fewer mask registers, shorter bodies
+template <int STRIDE, int NW>
+SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW, double *fsave, int64_t fs_stride,
+                           SpRow *rows, int n_rows, bool guard_all = true) {
+    constexpr int RB = NW == 1 ? SP_HMMF_RB : 2;  // wide bands: fewer mask registers
+    const int NC = 2 * BW + 1;
     const int Lr = in.l_ref, Lq = in.l_query;
     const int bw = sp_hmm_bw(Lr, Lq, in.par_bw);
     int flag = 0;
-    if (bw > BW || Lq < 1 || Lr < 1) {  // not this class's instance (the launcher never sends one)
+    if (bw > BW || NC > 64 * NW || Lq < 1 || Lr < 1) {  // (the launcher never sends such an instance)
         flag = SP_HMMF_NUMERIC;
         n_rows = 0;
     }
@@ -139,7 +169,7 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
     const double eim1 = SP_HMM_EI * m1, eim4 = SP_HMM_EI * m4;
     const double emA = C.em_match, emB = C.em_mis;
     const SpD2 zero2 = {0., 0.};
-    const bool narrow = bw < BW;  // the instance's own band is narrower than the class's: every row is an edge row
+    const bool narrow = bw < BW;  // the instance's own band is narrower than the warp's: every row is an edge row
 
     SpBits<NW> p0, p1, p2;  // bit-planes of the reference codes under the band
     p0.clear(); p1.clear(); p2.clear();
@@ -154,7 +184,7 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
     // has drifted far from 1 (it rarely has: a row loses ~1e-4 per mismatch)
     auto range_check = [&](bool live) {
         int mh = 0;
-#pragma unroll 8
+#pragma unroll 4
         for (int o = 0; o < NC; o++) {
             const SpD2 a = mi[o * STRIDE];
             const int hx = sp_dbl_hi(a.x), hy = sp_dbl_hi(a.y);
@@ -166,7 +196,7 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
             if (live) flag |= SP_HMMF_NUMERIC;
         } else if (ex < 1023 - 64 || ex > 1023 + 64) {
             const double sc = sp_dbl_from_hi((2046 - ex) << 20);  // 2^(1023-ex)
-#pragma unroll 8
+#pragma unroll 4
             for (int o = 0; o < NC; o++) {
                 SpD2 a = mi[o * STRIDE];
                 a.x *= sc;
@@ -283,43 +313,64 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
 #pragma unroll
                 for (int rr = 0; rr < RR; rr++) { Gc[rr] = 0.; Ml[rr] = 0.; cD[rr] = 0.; }
                 double g0 = mi[0].x;  // G of the stored row at the cell row 0 computes next
-#pragma unroll
-                for (int s = 0; s < NC + RR - 1; s++) {
-                    double Hup = 0., Gup = 0.;  // inputs of the current row from the row above
-                    if (s < NC) {
-                        const SpD2 a = mi[(s + 1 < NC ? s + 1 : NC) * STRIDE];  // (cell NC holds zeros)
+                // one step; rows [ra, rb) are inside the band, rows < ra have finished; bit(rr) = emission mask bit
+                auto step = [&](SpD2 *cell, int sidx, auto ra_tag, auto rb_tag, auto bit) {  // cell = &mi[sidx]
+                    constexpr int RA = decltype(ra_tag)::value, RBB = decltype(rb_tag)::value;
+                    double Gup = 0., Hup = 0.;
+                    if constexpr (RA == 0) {
+                        const SpD2 a = cell[STRIDE];  // cell s+1 of the stored row (cell NC holds zeros)
                         Gup = g0;
                         Hup = a.y;
                         g0 = a.x;
+                    } else {
+                        Gup = Gc[RA - 1];  // the row above has finished: its last cell's G, H = 0 beyond the band
                     }
 #pragma unroll
-                    for (int rr = 0; rr < RR; rr++) {
-                        const int o = s - rr;
-                        if (o >= 0 && o < NC) {
-                            const double M = (SP_BIT(mmr[rr], o) ? emA : emB) * Gup;
-                            const double I = Hup;
-                            cD[rr] = SP_FMA(m8, cD[rr], m2 * Ml[rr]);
-                            const double G = SP_FMA(m6, cD[rr], SP_FMA(m3, I, m0 * M));
-                            const double H = SP_FMA(eim4, I, eim1 * M);
-                            Ml[rr] = M;
-                            // what row rr+1 reads at this step: G of ITS cell (= this row's previous cell), H of this cell
-                            Gup = Gc[rr];
-                            Hup = H;
-                            Gc[rr] = G;
-                            if (rr == RR - 1) {
-                                SpD2 v = {G, H};
-                                mi[o * STRIDE] = v;
-                                if (fs) {
-                                    SpD2 f = {M, I};
-                                    *reinterpret_cast<SpD2 *>(fs + 2 * o) = f;
-                                }
+                    for (int rr = RA; rr < RBB; rr++) {
+                        const double M = (bit(rr) ? emA : emB) * Gup;
+                        const double I = Hup;
+                        cD[rr] = SP_FMA(m8, cD[rr], m2 * Ml[rr]);
+                        const double G = SP_FMA(m6, cD[rr], SP_FMA(m3, I, m0 * M));
+                        const double H = SP_FMA(eim4, I, eim1 * M);
+                        Ml[rr] = M;
+                        Gup = Gc[rr];  // what row rr+1 reads: G of ITS cell (this row's previous cell), H of this cell
+                        Hup = H;
+                        Gc[rr] = G;
+                        if (rr == RR - 1) {
+                            SpD2 v = {G, H};
+                            cell[-(RR - 1) * STRIDE] = v;  // cell s-(RR-1)
+                            if (fs) {
+                                SpD2 f = {M, I};
+                                *reinterpret_cast<SpD2 *>(fs + 2 * (sidx - (RR - 1))) = f;
                             }
-                        } else if (o >= NC) {
-                            Gup = Gc[rr];  // the row has finished: its last cell's G, and H = 0 beyond the band
-                            Hup = 0.;
                         }
                     }
+                };
+                // fill: steps 0..RR-2, rows 0..s
+                sp_static_for<0, RR - 1>([&](auto st) {
+                    constexpr int S = decltype(st)::value;
+                    step(mi + S * STRIDE, S, SpInt<0>(), SpInt<S + 1>(), [&](int rr) { return sp_bit_rt(mmr[rr], S - rr); });
+                });
+                // steady: steps RR-1..NC-1, all rows; chunks of 8 steps share one mask extraction per row
+                int s = RR - 1;
+                for (; s + 8 <= NC; s += 8) {
+                    uint32_t mb[RR];
+#pragma unroll
+                    for (int rr = 0; rr < RR; rr++) mb[rr] = sp_bits8_rt(mmr[rr], s - rr);
+                    SpD2 *cell = mi + s * STRIDE;
+                    sp_static_for<0, 8>([&](auto jt) {
+                        constexpr int J = decltype(jt)::value;
+                        step(cell + J * STRIDE, s + J, SpInt<0>(), SpInt<RR>(), [&](int rr) { return (mb[rr] >> J) & 1; });
+                    });
                 }
+                for (; s < NC; s++)
+                    step(mi + s * STRIDE, s, SpInt<0>(), SpInt<RR>(), [&](int rr) { return sp_bit_rt(mmr[rr], s - rr); });
+                // drain: steps NC..NC+RR-2, rows d+1..RR-1
+                sp_static_for<0, RR - 1>([&](auto dt) {
+                    constexpr int D = decltype(dt)::value;
+                    step(mi + (NC + D) * STRIDE, NC + D, SpInt<D + 1>(), SpInt<RR>(),
+                         [&](int rr) { return sp_bit_rt(mmr[rr], NC + D - rr); });
+                });
             };
             if (R == 1) pass(SpInt<1>());
             else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>());
@@ -332,11 +383,11 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
             valid_range(i, lo, hi);
             sp_bits_range(vm, lo, hi);
             double Gcur = mi[0].x, Mlast = 0., cD = 0.;
-#pragma unroll 4
+#pragma unroll 2
             for (int o = 0; o < NC; o++) {
                 const SpD2 a = mi[(o + 1) * STRIDE];
-                const bool ok = SP_BIT(vm, o);
-                const double e = SP_BIT(nn0, o) ? 1. : (SP_BIT(mmr[0], o) ? emA : emB);
+                const bool ok = sp_bit_rt(vm, o);
+                const double e = sp_bit_rt(nn0, o) ? 1. : (sp_bit_rt(mmr[0], o) ? emA : emB);
                 const double M = ok ? e * Gcur : 0.;
                 const double I = ok ? a.y : 0.;
                 cD = ok ? SP_FMA(m8, cD, m2 * Mlast) : 0.;
@@ -472,7 +523,7 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
                 // Cells left of column 1 or right of l_ref need no mask here: with the row above zero outside its
                 // valid cells the right side stays zero by itself, and what appears left of column 1 never flows
                 // back into a valid cell (dependencies only run towards smaller columns) nor into the MAP (f is zero
-                // there).  Only an instance narrower than its class, an N, or row 1 (no D state) is an edge row.
+                // there).  Only an instance narrower than its warp, an N, or row 1 (no D state) is an edge row.
                 const bool plain = !live || (!narrow && x > 1 && !nn.any_below(NC));
                 if (!stop && plain) {
                     lane_r = rr + 1;
@@ -501,36 +552,58 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
 #pragma unroll
                 for (int rr = 0; rr < RR; rr++) { Mc[rr] = 0.; cD[rr] = 0.; }
                 double b0 = mi[(NC - 1) * STRIDE].x;  // bM of the stored row at the cell row 0 computes next
-#pragma unroll
-                for (int s = 0; s < NC + RR - 1; s++) {
+                // cell = &mi[NC-1-s]: the cell row 0 computes at this step
+                auto step = [&](SpD2 *cell, auto ra_tag, auto rb_tag, auto bit) {
+                    constexpr int RA = decltype(ra_tag)::value, RBB = decltype(rb_tag)::value;
                     double Mup = 0., Iup = 0.;
-                    if (s < NC) {
-                        const SpD2 a = mi[(NC - 2 - s) * STRIDE];  // (cell -1 holds zeros)
+                    if constexpr (RA == 0) {
+                        const SpD2 a = cell[-STRIDE];  // (cell -1 holds zeros)
                         Mup = b0;
                         Iup = a.y;
                         b0 = a.x;
+                    } else {
+                        Mup = Mc[RA - 1];  // the row above has finished: its cell 0, bI = 0 left of the band
                     }
 #pragma unroll
-                    for (int rr = 0; rr < RR; rr++) {
-                        const int o = NC - 1 - s + rr;
-                        if (o >= 0 && o < NC) {
-                            const double e = (SP_BIT(mmr[rr], o) ? emA : emB) * Mup;
-                            const double bMv = SP_FMA(m2, cD[rr], SP_FMA(e, m0, eim1 * Iup));
-                            const double bIv = SP_FMA(e, m3, eim4 * Iup);
-                            cD[rr] = SP_FMA(m8, cD[rr], e * m6);
-                            Mup = Mc[rr];
-                            Iup = bIv;
-                            Mc[rr] = bMv;
-                            if (rr == RR - 1) {
-                                SpD2 v = {bMv, bIv};
-                                mi[o * STRIDE] = v;
-                            }
-                        } else if (o < 0) {
-                            Mup = Mc[rr];  // the row has finished: its cell 0, and bI = 0 left of the band
-                            Iup = 0.;
+                    for (int rr = RA; rr < RBB; rr++) {
+                        const double e = (bit(rr) ? emA : emB) * Mup;
+                        const double bMv = SP_FMA(m2, cD[rr], SP_FMA(e, m0, eim1 * Iup));
+                        const double bIv = SP_FMA(e, m3, eim4 * Iup);
+                        cD[rr] = SP_FMA(m8, cD[rr], e * m6);
+                        Mup = Mc[rr];
+                        Iup = bIv;
+                        Mc[rr] = bMv;
+                        if (rr == RR - 1) {
+                            SpD2 v = {bMv, bIv};
+                            cell[(RR - 1) * STRIDE] = v;  // cell NC-1-s+(RR-1)
                         }
                     }
+                };
+                sp_static_for<0, RR - 1>([&](auto st) {
+                    constexpr int S = decltype(st)::value;
+                    step(mi + (NC - 1 - S) * STRIDE, SpInt<0>(), SpInt<S + 1>(),
+                         [&](int rr) { return sp_bit_rt(mmr[rr], NC - 1 - S + rr); });
+                });
+                int s = RR - 1;
+                for (; s + 8 <= NC; s += 8) {
+                    // rows' cells at step s+J: NC-1-(s+J)+rr; the 8 cells of row rr are bits (NC-8-s+rr)..(NC-1-s+rr)
+                    uint32_t mb[RR];
+#pragma unroll
+                    for (int rr = 0; rr < RR; rr++) mb[rr] = sp_bits8_rt(mmr[rr], NC - 8 - s + rr);
+                    SpD2 *cell = mi + (NC - 1 - s) * STRIDE;
+                    sp_static_for<0, 8>([&](auto jt) {
+                        constexpr int J = decltype(jt)::value;
+                        step(cell - J * STRIDE, SpInt<0>(), SpInt<RR>(), [&](int rr) { return (mb[rr] >> (7 - J)) & 1; });
+                    });
                 }
+                for (; s < NC; s++)
+                    step(mi + (NC - 1 - s) * STRIDE, SpInt<0>(), SpInt<RR>(),
+                         [&](int rr) { return sp_bit_rt(mmr[rr], NC - 1 - s + rr); });
+                sp_static_for<0, RR - 1>([&](auto dt) {
+                    constexpr int D = decltype(dt)::value;
+                    step(mi + (-1 - D) * STRIDE, SpInt<D + 1>(), SpInt<RR>(),
+                         [&](int rr) { return sp_bit_rt(mmr[rr], -1 - D + rr); });
+                });
             };
             if (R == 1) pass(SpInt<1>());
             else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>());
@@ -543,15 +616,15 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, double
             sp_bits_range(vm, lo, hi);
             const double m6e = i > 1 ? m6 : 0., m8e = i > 1 ? m8 : 0.;
             double cD = 0., bMo = mi[(NC - 1) * STRIDE].x;
-#pragma unroll 4
+#pragma unroll 2
             for (int o = NC - 1; o >= 0; o--) {
                 const SpD2 a = mi[(o - 1) * STRIDE];
-                const double e = (SP_BIT(nn0, o) ? 1. : (SP_BIT(mmr[0], o) ? emA : emB)) * bMo;
+                const double e = (sp_bit_rt(nn0, o) ? 1. : (sp_bit_rt(mmr[0], o) ? emA : emB)) * bMo;
                 SpD2 v;
                 v.x = SP_FMA(m2, cD, SP_FMA(e, m0, eim1 * a.y));
                 v.y = SP_FMA(e, m3, eim4 * a.y);
                 cD = SP_FMA(m8e, cD, e * m6e);
-                if (!SP_BIT(vm, o)) { v.x = 0.; v.y = 0.; cD = 0.; }
+                if (!sp_bit_rt(vm, o)) { v.x = 0.; v.y = 0.; cD = 0.; }
                 mi[o * STRIDE] = v;
                 bMo = a.x;
             }

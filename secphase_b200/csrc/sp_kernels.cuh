@@ -270,12 +270,16 @@ __global__ void __launch_bounds__(256) k_fill_rows(SpBatchPtrs B, const SpItem *
     for (int k = lane; k < it.n_rows; k += 32) rows[it.row0 + k] = sp_fill_row(it, w, k, ops, rev, blk_rfs);
 }
 
-// ---- instance ordering: key = class * LBINS + (LBINS-1 - min(l_query, LBINS-1)) --------------
+// ---- instance ordering: by band half-width (all widths beyond the shared-memory kernels share one bin), then by
+// descending window length: key = min(bw, MAXBW+1) * LBINS + (LBINS-1 - min(l_query, LBINS-1)).  Band classes are
+// ranges of widths, so every class is a contiguous stretch of the order; inside it the 32-instance sets a warp
+// pulls are uniform in width (what the fast kernel's virtual band wants) except where two widths meet.
+#define SP_SORT_BWBINS (SP_H2_MAXBW + 3)
 __device__ __forceinline__ int sp_item_key(const SpItem &it) {
     const int bw = sp_hmm_bw(it.l_ref, it.l_query, it.par_bw);
     const int lq = it.l_query < SP_SORT_LBINS - 1 ? it.l_query : SP_SORT_LBINS - 1;
-    const int cls = it.n_rows > 0 ? sp_band_class(bw) : SP_N_CLASSES;  // row-less instances are not run
-    return cls * SP_SORT_LBINS + (SP_SORT_LBINS - 1 - lq);
+    const int b = it.n_rows > 0 ? (bw <= SP_H2_MAXBW ? bw : SP_H2_MAXBW + 1) : SP_H2_MAXBW + 2;  // row-less instances are not run
+    return b * SP_SORT_LBINS + (SP_SORT_LBINS - 1 - lq);
 }
 __global__ void k_sort_hist(const SpItem *items, int n, int32_t *bins) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,10 +305,9 @@ __global__ void __launch_bounds__(1024) k_sort_scan(int32_t *bins, int nbins, in
     for (int b = b0; b < b1; b++) {
         const int32_t c = bins[b];
         bins[b] = run;
-        if (b % SP_SORT_LBINS == 0) class_start[b / SP_SORT_LBINS] = run;
         run += c;
     }
-    if (t == 1023) class_start[SP_N_CLASSES + 1] = s[1023];
+    (void) class_start;
 }
 __global__ void k_sort_scatter(const SpItem *items, int n, int32_t *bins, int32_t *order) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,8 +466,10 @@ __global__ void __launch_bounds__(32 * sp_hmmf_warps(NC), 1) k_hmmf(const SpCons
         in.l_ref = it.l_ref;
         in.l_query = it.l_query;
         in.par_bw = it.par_bw;
-        const int flag = sp_hmmf_instance<32, NC>(*Cp, in, mi, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
-                                                  rows + it.row0, dup ? 0 : it.n_rows, guard_all != 0);
+        // the warp's virtual band: as wide as its widest instance (instances are ordered by width)
+        const int bww = __reduce_max_sync(0xffffffffu, sp_hmm_bw(it.l_ref, it.l_query, it.par_bw));
+        const int flag = sp_hmmf_instance<32, (NC + 63) / 64>(*Cp, in, mi, bww, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
+                                                             rows + it.row0, dup ? 0 : it.n_rows, guard_all != 0);
         if (!dup && flag) rerun_list[first + atomicAdd(rerun_count, 1)] = idx;
         __syncwarp();
     }
@@ -484,11 +489,13 @@ __global__ void __launch_bounds__(1024) k_fs_sets(SpSetPlan pl, const SpItem *__
     const int n_sets = pl.first_set[SP_N_CLASSES];
     const int per = (n_sets + 1023) / 1024;
     const int s0 = min(n_sets, t * per), s1 = min(n_sets, s0 + per);
-    auto size_of = [&](int k) -> int64_t {
+    auto size_of = [&](int k) -> int64_t {  // rows of the set's longest window (a set may span two band widths)
         int c = 0;
         while (c + 1 < SP_N_CLASSES && k >= pl.first_set[c + 1]) c++;
-        const SpItem it = items[order[pl.first_item[c] + (k - pl.first_set[c]) * 32]];
-        return (int64_t) it.n_rows * pl.cells[c] * 64;
+        const int i0 = (k - pl.first_set[c]) * 32, i1 = min(i0 + 32, pl.count[c]);
+        int nr = 0;
+        for (int i = i0; i < i1; i++) nr = max(nr, items[order[pl.first_item[c] + i]].n_rows);
+        return (int64_t) nr * pl.cells[c] * 64;
     };
     int64_t l = 0;
     for (int k = s0; k < s1; k++) l += size_of(k);

@@ -46,27 +46,6 @@ struct HsOut {
     double max_abs_drift_ulp = 0, max_rel_drift = 0;
 };
 
-// the fast kernel body (sp_hmmf.cuh) for the band class of `bw`; returns the guard flags, or -1 when the
-// class has no fast body (the launcher then runs the strict kernel)
-static int hs_hmmf_dispatch(const SpConst &C, const SpHmmIn &in, int bw, double *fsave, int64_t fss, SpRow *rows, int n_rows,
-                            bool guard_all) {
-    const int cls = sp_band_class(bw);
-    const int nc = sp_hmmf_class_cells(cls);
-    if (nc == 0) return -1;
-    std::vector<SpD2> mi((size_t) nc + 2);
-    switch (nc) {
-        case 41: return sp_hmmf_instance<1, 41>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
-        case 43: return sp_hmmf_instance<1, 43>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
-        case 45: return sp_hmmf_instance<1, 45>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
-        case 55: return sp_hmmf_instance<1, 55>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
-        case 73: return sp_hmmf_instance<1, 73>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
-        case 97: return sp_hmmf_instance<1, 97>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
-        case 125: return sp_hmmf_instance<1, 125>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
-        case 189: return sp_hmmf_instance<1, 189>(C, in, mi.data() + 1, fsave, fss, rows, n_rows, guard_all);
-        default: return -1;
-    }
-}
-
 // the instantiation launch_hmm() (sp_api.cu) picks for a band half-width; `unrolled` = what a full
 // warp of that class runs, otherwise what a partial last warp runs
 // `il_lane` >= 0: the -w mode's lane-interleaved forward-row block (k_hmm2<.,.,true>), this instance
@@ -107,6 +86,20 @@ static void hs_hmm2_dispatch(const SpConst &C, const SpHmmIn &in, const SpBand2<
         case 1: sp_hmm2_instance<1, 1, 0>(C, in, B, rinv, fsave, fss, rows, n_rows, false); break;
         case 2: sp_hmm2_instance<1, 2, 0>(C, in, B, rinv, fsave, fss, rows, n_rows, false); break;
         default: sp_hmm2_instance<1, 3, 0>(C, in, B, rinv, fsave, fss, rows, n_rows, false); break;
+    }
+}
+
+// the fast kernel body (sp_hmmf.cuh); bwv = half-width of the virtual band (the product passes the warp's widest
+// band; >= bw).  Returns the guard flags, or -1 when the band is beyond the shared-memory kernels.
+static int hs_hmmf_dispatch(const SpConst &C, const SpHmmIn &in, int bwv, double *fsave, int64_t fss, SpRow *rows, int n_rows,
+                            bool guard_all) {
+    if (bwv > SP_H2_MAXBW) return -1;
+    const int nc = 2 * bwv + 1;
+    std::vector<SpD2> mi((size_t) nc + 2);
+    switch (sp_h2_words(bwv)) {
+        case 1: return sp_hmmf_instance<1, 1>(C, in, mi.data() + 1, bwv, fsave, fss, rows, n_rows, guard_all);
+        case 2: return sp_hmmf_instance<1, 2>(C, in, mi.data() + 1, bwv, fsave, fss, rows, n_rows, guard_all);
+        default: return sp_hmmf_instance<1, 3>(C, in, mi.data() + 1, bwv, fsave, fss, rows, n_rows, guard_all);
     }
 }
 
@@ -213,12 +206,13 @@ int hs_hmm2(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *qu
 
 // The fast-arithmetic body (sp_hmmf.cuh) alone; returns the guard flags (>= 0) or -1 when the band class has none.
 int hs_hmmf(const sp_params *p, const uint8_t *ref, int l_ref, const uint8_t *query, int l_query, int par_bw,
-            const int32_t *rows_t, int n_rows, int32_t *state, uint8_t *q, double *pmax) {
+            const int32_t *rows_t, int n_rows, int32_t *state, uint8_t *q, double *pmax, int extra_bw) {
     SpConst C;
     sp_fill_const(*p, C);
-    const int bw = sp_hmm_bw(l_ref, l_query, par_bw);
-    const int nc = sp_hmmf_class_cells(sp_band_class(bw));
-    if (nc == 0) return -1;
+    int bw = sp_hmm_bw(l_ref, l_query, par_bw);
+    if (bw > SP_H2_MAXBW) return -1;
+    bw = bw + extra_bw > SP_H2_MAXBW ? SP_H2_MAXBW : bw + extra_bw;  // a wider virtual band: the lane of a mixed warp
+    const int nc = 2 * bw + 1;
     std::vector<double> fsave((size_t) n_rows * 2 * nc + 2, 0.0);
     std::vector<SpRow> rows((size_t) (n_rows > 0 ? n_rows : 1));
     for (int i = 0; i < n_rows; i++) {
@@ -476,10 +470,12 @@ int hs_run3(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         in.l_ref = I.l_ref; in.l_query = I.l_query; in.par_bw = I.par_bw;
         bool strict = true;
         std::vector<SpRow> fast_rows;
-        if (hmm_mode != 0 && !full_baq && sp_hmmf_class_cells(sp_band_class(bw)) != 0 && I.n_rows > 0) {
-            const int nc = sp_hmmf_class_cells(sp_band_class(bw));
+        if (hmm_mode != 0 && !full_baq && bw <= SP_H2_MAXBW && I.n_rows > 0) {
+            // every third instance plays a lane of a mixed warp (virtual band = its class's widest)
+            const int bwv = it % 3 == 2 ? sp_class_bw(sp_band_class(bw)) : bw;
+            const int nc = 2 * bwv + 1;
             std::vector<double> ff((size_t) I.n_rows * 2 * nc + 2, 0.0);
-            const int fl = hs_hmmf_dispatch(C, in, bw, ff.data(), 2 * nc, rows.data() + I.row0, I.n_rows, false);  // as k_hmmf does
+            const int fl = hs_hmmf_dispatch(C, in, bwv, ff.data(), 2 * nc, rows.data() + I.row0, I.n_rows, false);  // as k_hmmf does
             out->fast_instances++;
             strict = fl != 0;
             if (fl) {

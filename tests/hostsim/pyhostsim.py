@@ -52,7 +52,7 @@ def lib():
         L.hs_run3.restype = C.c_int
         L.hs_fast_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_hmmf.argtypes = [C.POINTER(SpParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.hs_hmmf.restype = C.c_int
         L.hs_plan_sig.argtypes = [C.POINTER(CFlatBatch), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.hs_plan_sig.restype = C.c_uint64
@@ -157,8 +157,9 @@ def hmm2(params, ref, query, par_bw, rows_t, unrolled=True):
     return dict(state=state, q=q, pmax=pmax)
 
 
-def hmmf(params, ref, query, par_bw, rows_t):
-    """The fast-arithmetic kernel body (sp_hmmf.cuh) on the host; None if the band class has no fast body."""
+def hmmf(params, ref, query, par_bw, rows_t, extra_bw=0):
+    """The fast-arithmetic kernel body (sp_hmmf.cuh) on the host; None if the band is too wide for it.
+    extra_bw > 0: run in a virtual band that much wider than the instance's own (a lane of a mixed warp)."""
     L = lib()
     ref = np.ascontiguousarray(ref, np.uint8)
     query = np.ascontiguousarray(query, np.uint8)
@@ -168,7 +169,7 @@ def hmmf(params, ref, query, par_bw, rows_t):
     q = np.zeros(n, np.uint8)
     pmax = np.zeros(n, np.float64)
     fl = L.hs_hmmf(C.byref(params), ref.ctypes.data, len(ref), query.ctypes.data, len(query), par_bw,
-                   rows_t.ctypes.data, n, state.ctypes.data, q.ctypes.data, pmax.ctypes.data)
+                   rows_t.ctypes.data, n, state.ctypes.data, q.ctypes.data, pmax.ctypes.data, extra_bw)
     if fl < 0:
         return None
     return dict(state=state, q=q, pmax=pmax, flags=fl)

@@ -167,8 +167,8 @@ def test_hmm_fast_body_guard_band(hostsim, oracle, preset):
         if len(query) > 40:
             picks += [np.sort(rng.choice(np.arange(10, len(query) - 11), size=3, replace=False)).astype(np.int32)
                       for _ in range(3)]
-        for rows in picks:
-            got = hostsim.hmmf(hp, ref, query, bw, rows)
+        for k, rows in enumerate(picks):
+            got = hostsim.hmmf(hp, ref, query, bw, rows, extra_bw=(0, 3, 0, 7)[k % 4])
             if got is None:   # band class without a fast body: the launcher uses the strict kernel
                 continue
             n_fast += 1
