@@ -116,7 +116,10 @@ typedef struct sp_result {
  * holds in memory (secphase.c:303, 338); the equivalent here is that the BAM reader decodes
  * straight into these buffers, from which sp_submit copies to the device without an intermediate
  * host copy.  Pools in ordinary (pageable) memory are accepted too and are staged first.
- * The caller must keep a submitted batch's pools unchanged until sp_wait returns. */
+ * The caller must keep a submitted batch's pools unchanged until sp_wait returns: a page-locked quality pool of a
+ * batch whose markers are sparse (HiFi) is not copied at all -- the kernels read the few dozen quality bytes per
+ * alignment they need in place, over PCIe (sp_result.h2d_bytes then counts a 32-byte sector per such read instead
+ * of the pool; SECPHASE_B200_NO_ZERO_COPY=1 turns it off). */
 void *sp_host_alloc(size_t bytes); /* NULL on error */
 void sp_host_free(void *p);
 

@@ -113,6 +113,8 @@ struct Slot {
         rerun_list;
     // host results
     PinBuf h_tot, h_gout, h_score, h_info, h_fin, h_qual, h_rerun;
+    const uint8_t *qual_zero_copy = nullptr;  // device view of the caller's page-locked quality pool, when it is read in place
+    int64_t zero_copy_bytes = 0;
     bool fast_hmm = false;  // this batch's HMM launches used the fast kernel (+ strict re-run of flagged instances)
     size_t qual_bytes = 0;  // size of the batch's quality pool (== of qual_out in full_baq mode)
     bool full_baq = false;  // this batch was planned with SpConst::full_baq set
@@ -569,7 +571,8 @@ static InLayout make_layout(const sp_flat_batch *b, const SpPlan &pl) {
     return L;
 }
 
-static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
+// zero_copy_ok: the caller's pools stay valid until sp_wait (sp_submit's contract), so a pool may be read in place
+static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b, bool zero_copy_ok = false) {
     // the plan scans every cs/MD byte once: a few threads when the batch carries a lot of tag text (ONT)
     int plan_threads = 1;
     if (b->n_alns > 0 && b->tag_off[b->n_alns] > ((int64_t) 4 << 20)) {
@@ -626,7 +629,26 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
     };
     S.meta_bytes = L.cigar_pool.off;  // everything before the pools is small per-alignment metadata
     pool(L.cigar_pool, b->cigar_pool); pool(L.tag_pool, b->tag_pool); pool(L.seq_pool, b->seq_pool);
-    pool(L.qual_pool, b->qual_pool);
+    // Raw qualities are two thirds of a HiFi batch, yet the marker path reads only the bases inside X runs (k_walk,
+    // ptMarker.c:50-70) and one base per alignment at every marker position (k_group, ptMarker.c:91-105): a few dozen
+    // bytes per alignment.  When the pool is page-locked (hence mapped into the device's address space) and the
+    // batch is that sparse, the kernels read those bytes in place over PCIe instead of copying the whole pool.
+    // Upper bound on the reads: per group (alignments) x (mismatched bases of all its alignments), known from the plan.
+    S.qual_zero_copy = nullptr;
+    S.zero_copy_bytes = 0;
+    if (zero_copy_ok && !c->full_baq && L.qual_pool.bytes > 0 && !getenv("SECPHASE_B200_NO_ZERO_COPY") && is_pinned(b->qual_pool)) {
+        int64_t reads = 0;
+        for (int g = 0; g < pl.G; g++) reads += (int64_t) (b->grp_aln_off[g + 1] - b->grp_aln_off[g]) * pl.g_msum[(size_t) g];
+        void *dp = nullptr;
+        if (reads * 96 < (int64_t) L.qual_pool.bytes &&
+            cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(b->qual_pool), 0) == cudaSuccess && dp) {
+            S.qual_zero_copy = static_cast<const uint8_t *>(dp);
+            S.zero_copy_bytes = reads * 32;  // one 32-byte sector per read
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (!S.qual_zero_copy) pool(L.qual_pool, b->qual_pool);
     S.tag_pad_off = L.tag_pool.off + L.tag_pool.bytes;
     S.in_bytes = L.total;
     S.qual_bytes = L.qual_pool.bytes;
@@ -681,7 +703,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b) {
     P.gpos_off = DP(int64_t, gpos_off); P.gent_off = DP(int64_t, gent_off); P.gblk_off = DP(int64_t, gblk_off);
     P.giv_off = DP(int64_t, giv_off);
     P.cigar_pool = DP(uint32_t, cigar_pool); P.tag_pool = DP(uint8_t, tag_pool); P.seq_pool = DP(uint8_t, seq_pool);
-    P.qual_pool = DP(uint8_t, qual_pool);
+    P.qual_pool = S.qual_zero_copy ? S.qual_zero_copy : DP(uint8_t, qual_pool);
 #undef DP
     P.ops = S.ops.as<SpOp>(); P.imk = S.imk.as<SpInitMarker>(); P.info = S.info.as<SpAlnInfo>();
     P.blk = S.blk.as<SpBlock>(); P.iv = S.iv.as<SpIv>(); P.nb = S.nb.as<int32_t>(); P.gpos = S.gpos.as<int32_t>();
@@ -731,7 +753,9 @@ static void launch_hmmf(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first,
     const size_t slab = (size_t) (NC + 2) * 32 * 16;
     int wpc = (int) (c->max_smem / slab);
     if (wpc > sp_hmmf_warps(NC)) wpc = sp_hmmf_warps(NC);  // k_hmmf<NC>'s launch bound
-    if (wpc > nblk) wpc = nblk;
+    // a small class spreads over as many SMs as it has sets (one warp each) instead of filling a few CTAs
+    const int per_sm = (nblk + c->hmm_sms - 1) / c->hmm_sms;
+    if (wpc > per_sm) wpc = per_sm;
     int grid = (nblk + wpc - 1) / wpc;
     if (grid > c->hmm_sms) grid = c->hmm_sms;
     k_hmmf<NC><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(), first, cnt,
@@ -1086,12 +1110,15 @@ int sp_submit(sp_ctx *c, const sp_flat_batch *b, int slot) {
         return SP_ESTATE;
     }
     S.safe_caps = false;
-    int rc = stage_batch(c, S, b);
+    int rc = stage_batch(c, S, b, /*zero_copy_ok=*/true);
     if (rc) return rc;
     CK(cudaEventRecord(S.ev[EV_START], S.stream));
     if ((rc = enqueue_h2d(S))) return rc;
     CK(cudaEventRecord(S.ev[EV_H2D], S.stream));
-    S.h2d_bytes = (int64_t) S.in_bytes;
+    // bytes that cross to the device: what is copied, plus (an upper bound on) the sectors read in place
+    S.h2d_bytes = (int64_t) S.meta_bytes + 16;
+    for (int k = 0; k < S.n_copies; k++) S.h2d_bytes += (int64_t) S.copies[k].bytes;
+    S.h2d_bytes += S.zero_copy_bytes;
     rc = run_phase_a(c, S);
     if (rc) return rc;
     S.state = 2;

@@ -240,27 +240,33 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
     // row ("dead") keeps executing the bodies on its own cells, which nobody reads any more.
     const int LqW = SP_WARP_MAX(Lq);
     int t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
-    // raw query bytes and entering reference codes of the next RB rows, byte r <-> row i+r (0 where there is none)
-    auto fetch_fwd = [&](int i0, uint32_t &q4, uint32_t &r4) {
-        q4 = 0;
-        r4 = 0;
+    // raw query bytes and entering reference codes of the next RB rows (kept apart: nothing may hang off a load
+    // before the pass that hides its latency has run)
+    uint32_t qn[RB], rn[RB], q4 = 0, r4 = 0;
+    auto fetch_fwd = [&](int i0) {
 #pragma unroll
         for (int rr = 0; rr < RB; rr++) {
             const int row = i0 + rr;
-            if (row <= Lq) q4 |= sp_query_raw(in, row - 1) << (8 * rr);
-            if (row + BW <= Lr) r4 |= sp_ldg_u8(in.ref + row + BW - 1) << (8 * rr);
+            qn[rr] = row <= Lq ? sp_query_raw(in, row - 1) : 0;
+            rn[rr] = row + BW <= Lr ? sp_ldg_u8(in.ref + row + BW - 1) : 0;
         }
     };
-    uint32_t q4, r4;
-    fetch_fwd(2, q4, r4);
+    auto pack = [&]() {  // byte r <-> row i+r
+        q4 = 0;
+        r4 = 0;
+#pragma unroll
+        for (int rr = 0; rr < RB; rr++) { q4 |= qn[rr] << (8 * rr); r4 |= rn[rr] << (8 * rr); }
+    };
+    fetch_fwd(2);
+    pack();
     int since_check = 0;
     for (int i = 2; i <= LqW;) {
-        // ---- classify the next RB rows of this lane: masks, and how many leading rows can share one pass
-        SpBits<NW> mmr[RB], ps0[RB], ps1[RB], ps2[RB], nn0;
-        int lane_r = 0;
-        bool stop = false;
+        // ---- the next RB rows of this lane: masks, and how many of them share one pass (a consumed row ends it)
+        SpBits<NW> mmr[RB], nnr[RB], vmr[RB], ps0[RB], ps1[RB], ps2[RB];
+        int lane_r = RB;
         {
             SpBits<NW> a0 = p0, a1 = p1, a2 = p2;
+            bool stop = false;
 #pragma unroll
             for (int rr = 0; rr < RB; rr++) {
                 const int row = i + rr;
@@ -276,141 +282,147 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
                         a2.or_bit(NC - 1, (uint64_t) ((rc >> 2) & 1));
                     }
                 }
-                SpBits<NW> nn;
-                sp_h2_row_masks(a0, a1, a2, qc, mmr[rr], nn);
-                if (rr == 0) nn0 = nn;
+                sp_h2_row_masks(a0, a1, a2, qc, mmr[rr], nnr[rr]);
                 ps0[rr] = a0; ps1[rr] = a1; ps2[rr] = a2;
-                // a row whose every cell is a valid column without an N
-                const bool plain = !live || (!narrow && row > BW && row + BW <= Lr && !nn.any_below(NC));
-                if (!stop && plain) {
+                int lo, hi;
+                valid_range(row, lo, hi);
+                sp_bits_range(vmr[rr], lo, hi);
+                if (!stop && live && t_next + 1 == row) {  // a consumed row ends the block (it is kept in memory)
                     lane_r = rr + 1;
-                    if (live && t_next + 1 == row) stop = true;  // a consumed row ends the block (it is kept in memory)
-                } else {
                     stop = true;
                 }
             }
         }
         const int R = SP_WARP_MIN(lane_r);
-        const int adv = R > 0 ? R : 1;
         {  // commit the planes, fetch the codes of the rows after this pass (their latency hides behind it)
-            const int k = adv - 1;
 #pragma unroll
             for (int rr = 0; rr < RB; rr++)
-                if (rr == k) { p0 = ps0[rr]; p1 = ps1[rr]; p2 = ps2[rr]; }
+                if (rr == R - 1) { p0 = ps0[rr]; p1 = ps1[rr]; p2 = ps2[rr]; }
         }
-        uint32_t q4n, r4n;
-        fetch_fwd(i + adv, q4n, r4n);
-        const int last = i + adv - 1;
+        fetch_fwd(i + R);
+        // a row with an invalid column (outside 1..l_ref or the instance's own band) or an N needs the masked pass
+        bool mask_lane = false;
+#pragma unroll
+        for (int rr = 0; rr < RB; rr++) {
+            const int row = i + rr;
+            if (rr < R && row <= Lq && (narrow || row <= BW || row + BW > Lr || nnr[rr].any_below(NC))) mask_lane = true;
+        }
+        const bool masked = SP_WARP_ANY(mask_lane);
+        const int last = i + R - 1;
         const bool save = last <= Lq && t_next + 1 == last;
         double *fs = save ? fsave + (int64_t) nr * fs_stride : nullptr;
-        if (R > 0) {
-            // ---- plain pass over R rows.  Row r (0-based) computes cell s - r at step s:
-            //   M = e*G_above[o], I = H_above[o+1], D = m8*D[o-1] + m2*M[o-1], G = m0*M + m3*I + m6*D, H = EI*(m1*M + m4*I)
-            // with "above" = the stored row for r = 0, else row r-1 of this pass (G from its previous step, H fresh).
-            auto pass = [&](auto rtag) {
-                constexpr int RR = decltype(rtag)::value;
-                double Gc[RR], Ml[RR], cD[RR];
+        // ---- one pass over R rows.  Row r (0-based) computes cell s - r at step s:
+        //   M = e*G_above[o], I = H_above[o+1], D = m8*D[o-1] + m2*M[o-1], G = m0*M + m3*I + m6*D, H = EI*(m1*M + m4*I)
+        // with "above" = the stored row for r = 0, else row r-1 of this pass (G from its previous step, H fresh).
+        // MK: invalid cells are forced to zero and an N emits 1 (rows at the ends of the window, N bases).
+        auto pass = [&](auto rtag, auto mtag) {
+            constexpr int RR = decltype(rtag)::value;
+            constexpr bool MK = decltype(mtag)::value != 0;
+            double Gc[RR], Ml[RR], cD[RR];
 #pragma unroll
-                for (int rr = 0; rr < RR; rr++) { Gc[rr] = 0.; Ml[rr] = 0.; cD[rr] = 0.; }
-                double g0 = mi[0].x;  // G of the stored row at the cell row 0 computes next
-                // one step; rows [ra, rb) are inside the band, rows < ra have finished; bit(rr) = emission mask bit
-                auto step = [&](SpD2 *cell, int sidx, auto ra_tag, auto rb_tag, auto bit) {  // cell = &mi[sidx]
-                    constexpr int RA = decltype(ra_tag)::value, RBB = decltype(rb_tag)::value;
-                    double Gup = 0., Hup = 0.;
-                    if constexpr (RA == 0) {
-                        const SpD2 a = cell[STRIDE];  // cell s+1 of the stored row (cell NC holds zeros)
-                        Gup = g0;
-                        Hup = a.y;
-                        g0 = a.x;
+            for (int rr = 0; rr < RR; rr++) { Gc[rr] = 0.; Ml[rr] = 0.; cD[rr] = 0.; }
+            double g0 = mi[0].x;  // G of the stored row at the cell row 0 computes next
+            // one step; rows [RA, RBB) are inside the band, rows < RA have finished; bits(rr) = mask bits of row rr's cell:
+            // bit 0 match, bit 1 N, bit 2 valid
+            auto step = [&](SpD2 *cell, int sidx, auto ra_tag, auto rb_tag, auto bits) {  // cell = &mi[sidx]
+                constexpr int RA = decltype(ra_tag)::value, RBB = decltype(rb_tag)::value;
+                double Gup = 0., Hup = 0.;
+                if constexpr (RA == 0) {
+                    const SpD2 a = cell[STRIDE];  // cell s+1 of the stored row (cell NC holds zeros)
+                    Gup = g0;
+                    Hup = a.y;
+                    g0 = a.x;
+                } else {
+                    Gup = Gc[RA - 1];  // the row above has finished: its last cell's G, H = 0 beyond the band
+                }
+#pragma unroll
+                for (int rr = RA; rr < RBB; rr++) {
+                    const uint32_t b = bits(rr);
+                    double M, I;
+                    if constexpr (MK) {
+                        const bool ok = (b & 4) != 0;
+                        const double e = (b & 2) ? 1. : ((b & 1) ? emA : emB);
+                        M = ok ? e * Gup : 0.;
+                        I = ok ? Hup : 0.;
+                        cD[rr] = ok ? SP_FMA(m8, cD[rr], m2 * Ml[rr]) : 0.;
                     } else {
-                        Gup = Gc[RA - 1];  // the row above has finished: its last cell's G, H = 0 beyond the band
-                    }
-#pragma unroll
-                    for (int rr = RA; rr < RBB; rr++) {
-                        const double M = (bit(rr) ? emA : emB) * Gup;
-                        const double I = Hup;
+                        M = ((b & 1) ? emA : emB) * Gup;
+                        I = Hup;
                         cD[rr] = SP_FMA(m8, cD[rr], m2 * Ml[rr]);
-                        const double G = SP_FMA(m6, cD[rr], SP_FMA(m3, I, m0 * M));
-                        const double H = SP_FMA(eim4, I, eim1 * M);
-                        Ml[rr] = M;
-                        Gup = Gc[rr];  // what row rr+1 reads: G of ITS cell (this row's previous cell), H of this cell
-                        Hup = H;
-                        Gc[rr] = G;
-                        if (rr == RR - 1) {
-                            SpD2 v = {G, H};
-                            cell[-(RR - 1) * STRIDE] = v;  // cell s-(RR-1)
-                            if (fs) {
-                                SpD2 f = {M, I};
-                                *reinterpret_cast<SpD2 *>(fs + 2 * (sidx - (RR - 1))) = f;
-                            }
+                    }
+                    const double G = SP_FMA(m6, cD[rr], SP_FMA(m3, I, m0 * M));
+                    const double H = SP_FMA(eim4, I, eim1 * M);
+                    Ml[rr] = M;
+                    Gup = Gc[rr];  // what row rr+1 reads: G of ITS cell (this row's previous cell), H of this cell
+                    Hup = H;
+                    Gc[rr] = G;
+                    if (rr == RR - 1) {
+                        SpD2 v = {G, H};
+                        cell[-(RR - 1) * STRIDE] = v;  // cell s-(RR-1)
+                        if (fs) {
+                            SpD2 f = {M, I};
+                            *reinterpret_cast<SpD2 *>(fs + 2 * (sidx - (RR - 1))) = f;
                         }
                     }
-                };
-                // fill: steps 0..RR-2, rows 0..s
-                sp_static_for<0, RR - 1>([&](auto st) {
-                    constexpr int S = decltype(st)::value;
-                    step(mi + S * STRIDE, S, SpInt<0>(), SpInt<S + 1>(), [&](int rr) { return sp_bit_rt(mmr[rr], S - rr); });
-                });
-                // steady: steps RR-1..NC-1, all rows; chunks of 8 steps share one mask extraction per row
-                int s = RR - 1;
-                for (; s + 8 <= NC; s += 8) {
-                    uint32_t mb[RR];
-#pragma unroll
-                    for (int rr = 0; rr < RR; rr++) mb[rr] = sp_bits8_rt(mmr[rr], s - rr);
-                    SpD2 *cell = mi + s * STRIDE;
-                    sp_static_for<0, 8>([&](auto jt) {
-                        constexpr int J = decltype(jt)::value;
-                        step(cell + J * STRIDE, s + J, SpInt<0>(), SpInt<RR>(), [&](int rr) { return (mb[rr] >> J) & 1; });
-                    });
                 }
-                for (; s < NC; s++)
-                    step(mi + s * STRIDE, s, SpInt<0>(), SpInt<RR>(), [&](int rr) { return sp_bit_rt(mmr[rr], s - rr); });
-                // drain: steps NC..NC+RR-2, rows d+1..RR-1
-                sp_static_for<0, RR - 1>([&](auto dt) {
-                    constexpr int D = decltype(dt)::value;
-                    step(mi + (NC + D) * STRIDE, NC + D, SpInt<D + 1>(), SpInt<RR>(),
-                         [&](int rr) { return sp_bit_rt(mmr[rr], NC + D - rr); });
-                });
             };
-            if (R == 1) pass(SpInt<1>());
-            else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>());
-            else if (RB >= 3 && R == 3) pass(SpInt<(RB >= 3 ? 3 : 1)>());
-            else pass(SpInt<RB>());
-        } else {
-            // ---- edge row i alone: invalid columns masked to zero, N bases
-            SpBits<NW> vm;
-            int lo, hi;
-            valid_range(i, lo, hi);
-            sp_bits_range(vm, lo, hi);
-            double Gcur = mi[0].x, Mlast = 0., cD = 0.;
-#pragma unroll 2
-            for (int o = 0; o < NC; o++) {
-                const SpD2 a = mi[(o + 1) * STRIDE];
-                const bool ok = sp_bit_rt(vm, o);
-                const double e = sp_bit_rt(nn0, o) ? 1. : (sp_bit_rt(mmr[0], o) ? emA : emB);
-                const double M = ok ? e * Gcur : 0.;
-                const double I = ok ? a.y : 0.;
-                cD = ok ? SP_FMA(m8, cD, m2 * Mlast) : 0.;
-                SpD2 v;
-                v.x = SP_FMA(m6, cD, SP_FMA(m3, I, m0 * M));
-                v.y = SP_FMA(eim4, I, eim1 * M);
-                mi[o * STRIDE] = v;
-                if (fs) {
-                    SpD2 f = {M, I};
-                    *reinterpret_cast<SpD2 *>(fs + 2 * o) = f;
+            auto bit_rt = [&](int rr, int o) -> uint32_t {
+                uint32_t v = sp_bit_rt(mmr[rr], o);
+                if constexpr (MK) v |= sp_bit_rt(nnr[rr], o) << 1 | sp_bit_rt(vmr[rr], o) << 2;
+                return v;
+            };
+            // fill: steps 0..RR-2, rows 0..s
+            sp_static_for<0, RR - 1>([&](auto st) {
+                constexpr int S = decltype(st)::value;
+                step(mi + S * STRIDE, S, SpInt<0>(), SpInt<S + 1>(), [&](int rr) { return bit_rt(rr, S - rr); });
+            });
+            // steady: steps RR-1..NC-1, all rows; chunks of 8 steps share one mask extraction per row
+            int s = RR - 1;
+            for (; s + 8 <= NC; s += 8) {
+                uint32_t mb[RR], nb[MK ? RR : 1], vb[MK ? RR : 1];
+#pragma unroll
+                for (int rr = 0; rr < RR; rr++) {
+                    mb[rr] = sp_bits8_rt(mmr[rr], s - rr);
+                    if constexpr (MK) {
+                        nb[rr] = sp_bits8_rt(nnr[rr], s - rr);
+                        vb[rr] = sp_bits8_rt(vmr[rr], s - rr);
+                    }
                 }
-                Mlast = M;
-                Gcur = a.x;
+                SpD2 *cell = mi + s * STRIDE;
+                sp_static_for<0, 8>([&](auto jt) {
+                    constexpr int J = decltype(jt)::value;
+                    step(cell + J * STRIDE, s + J, SpInt<0>(), SpInt<RR>(), [&](int rr) -> uint32_t {
+                        uint32_t v = (mb[rr] >> J) & 1;
+                        if constexpr (MK) v |= ((nb[rr] >> J) & 1) << 1 | ((vb[rr] >> J) & 1) << 2;
+                        return v;
+                    });
+                });
             }
+            for (; s < NC; s++) step(mi + s * STRIDE, s, SpInt<0>(), SpInt<RR>(), [&](int rr) { return bit_rt(rr, s - rr); });
+            // drain: steps NC..NC+RR-2, rows d+1..RR-1
+            sp_static_for<0, RR - 1>([&](auto dt) {
+                constexpr int D = decltype(dt)::value;
+                step(mi + (NC + D) * STRIDE, NC + D, SpInt<D + 1>(), SpInt<RR>(), [&](int rr) { return bit_rt(rr, NC + D - rr); });
+            });
+        };
+        if (!masked) {
+            if (R == 1) pass(SpInt<1>(), SpInt<0>());
+            else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>(), SpInt<0>());
+            else if (RB >= 3 && R == 3) pass(SpInt<(RB >= 3 ? 3 : 1)>(), SpInt<0>());
+            else pass(SpInt<RB>(), SpInt<0>());
+        } else {
+            if (R == 1) pass(SpInt<1>(), SpInt<1>());
+            else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>(), SpInt<1>());
+            else if (RB >= 3 && R == 3) pass(SpInt<(RB >= 3 ? 3 : 1)>(), SpInt<1>());
+            else pass(SpInt<RB>(), SpInt<1>());
         }
         if (save) {
             nr++;
             t_next = nr < n_rows ? rows[nr].t : 0x7fffffff;
         }
-        i += adv;
-        q4 = q4n;
-        r4 = r4n;
-        since_check += adv;
+        i += R;
+        pack();
+        since_check += R;
         if (since_check >= SP_HMMF_RS) {
             range_check(i - 1 <= Lq);
             since_check = 0;
@@ -479,29 +491,27 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
     t_next = nr >= 0 ? rows[nr].t : -2;
     // The planes are where the lane's last forward row left them: bit o <-> ref[Lq-1-BW+o], which is the base
     // of column k+1 for cell o of row Lq-1.  Step j of the sweep is row Lq-1-j of every lane.
-    auto fetch_bwd = [&](int x0, uint32_t &q4o, uint32_t &r4o) {  // byte r <-> row x0-r: query[x0-r], ref[x0-r-BW]
-        q4o = 0;
-        r4o = 0;
+    auto fetch_bwd = [&](int x0) {  // entry r <-> row x0-r: query[x0-r], ref[x0-r-BW]
 #pragma unroll
         for (int rr = 0; rr < RB; rr++) {
             const int x = x0 - rr;
-            if (x >= 1 && x >= i_stop) {
-                q4o |= sp_query_raw(in, x) << (8 * rr);
-                const int y = x - BW;
-                if (y >= 0 && y < Lr) r4o |= sp_ldg_u8(in.ref + y) << (8 * rr);
-            }
+            const bool on = x >= 1 && x >= i_stop;
+            const int y = x - BW;
+            qn[rr] = on ? sp_query_raw(in, x) : 0;
+            rn[rr] = (on && y >= 0 && y < Lr) ? sp_ldg_u8(in.ref + y) : 0;
         }
     };
     const int jmax = SP_WARP_MAX(Lq - 1 - i_stop);
-    fetch_bwd(Lq - 1, q4, r4);
+    fetch_bwd(Lq - 1);
+    pack();
     since_check = 0;
     for (int j = 0; j <= jmax;) {
         const int i = Lq - 1 - j;  // first (highest) row of this pass
-        SpBits<NW> mmr[RB], ps0[RB], ps1[RB], ps2[RB], nn0;
-        int lane_r = 0;
-        bool stop = false;
+        SpBits<NW> mmr[RB], nnr[RB], vmr[RB], ps0[RB], ps1[RB], ps2[RB];
+        int lane_r = RB;
         {
             SpBits<NW> a0 = p0, a1 = p1, a2 = p2;
+            bool stop = false;
 #pragma unroll
             for (int rr = 0; rr < RB; rr++) {
                 const int x = i - rr;
@@ -516,129 +526,141 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
                         a2.shl1_in((uint64_t) ((rc >> 2) & 1));
                     }
                 }
-                SpBits<NW> nn;
-                sp_h2_row_masks(a0, a1, a2, qc, mmr[rr], nn);
-                if (rr == 0) nn0 = nn;
+                sp_h2_row_masks(a0, a1, a2, qc, mmr[rr], nnr[rr]);
                 ps0[rr] = a0; ps1[rr] = a1; ps2[rr] = a2;
-                // Cells left of column 1 or right of l_ref need no mask here: with the row above zero outside its
-                // valid cells the right side stays zero by itself, and what appears left of column 1 never flows
-                // back into a valid cell (dependencies only run towards smaller columns) nor into the MAP (f is zero
-                // there).  Only an instance narrower than its warp, an N, or row 1 (no D state) is an edge row.
-                const bool plain = !live || (!narrow && x > 1 && !nn.any_below(NC));
-                if (!stop && plain) {
+                int lo, hi;
+                valid_range(x, lo, hi);
+                sp_bits_range(vmr[rr], lo, hi);
+                if (!stop && live && t_next + 1 == x) {  // a consumed row ends the block: the MAP reads it from memory
                     lane_r = rr + 1;
-                    if (live && t_next + 1 == x) stop = true;  // a consumed row ends the block: the MAP reads it from memory
-                } else {
                     stop = true;
                 }
             }
         }
         const int R = SP_WARP_MIN(lane_r);
-        const int adv = R > 0 ? R : 1;
         {
-            const int k = adv - 1;
 #pragma unroll
             for (int rr = 0; rr < RB; rr++)
-                if (rr == k) { p0 = ps0[rr]; p1 = ps1[rr]; p2 = ps2[rr]; }
+                if (rr == R - 1) { p0 = ps0[rr]; p1 = ps1[rr]; p2 = ps2[rr]; }
         }
-        uint32_t q4n, r4n;
-        fetch_bwd(i - adv, q4n, r4n);
-        if (R > 0) {
-            // row a (0-based) computes cell NC-1-s+a at step s; it needs bM of the row above at its own cell
-            // (that row's previous step) and bI of the row above one cell to the left (fresh)
-            auto pass = [&](auto rtag) {
-                constexpr int RR = decltype(rtag)::value;
-                double Mc[RR], cD[RR];
+        fetch_bwd(i - R);
+        // Cells left of column 1 or right of l_ref need no mask here: with the row above zero outside its valid
+        // cells the right side stays zero by itself, and what appears left of column 1 never flows back into a valid
+        // cell (dependencies only run towards smaller columns) nor into the MAP (f is zero there).  Only an instance
+        // narrower than its warp's band, an N, or row 1 (no D state there) takes the masked pass.
+        bool mask_lane = false;
+        double m6r[RB], m8r[RB];
 #pragma unroll
-                for (int rr = 0; rr < RR; rr++) { Mc[rr] = 0.; cD[rr] = 0.; }
-                double b0 = mi[(NC - 1) * STRIDE].x;  // bM of the stored row at the cell row 0 computes next
-                // cell = &mi[NC-1-s]: the cell row 0 computes at this step
-                auto step = [&](SpD2 *cell, auto ra_tag, auto rb_tag, auto bit) {
-                    constexpr int RA = decltype(ra_tag)::value, RBB = decltype(rb_tag)::value;
-                    double Mup = 0., Iup = 0.;
-                    if constexpr (RA == 0) {
-                        const SpD2 a = cell[-STRIDE];  // (cell -1 holds zeros)
-                        Mup = b0;
-                        Iup = a.y;
-                        b0 = a.x;
-                    } else {
-                        Mup = Mc[RA - 1];  // the row above has finished: its cell 0, bI = 0 left of the band
-                    }
+        for (int rr = 0; rr < RB; rr++) {
+            const int x = i - rr;
+            if (rr < R && x >= i_stop && x >= 1 && (narrow || x <= 1 || nnr[rr].any_below(NC))) mask_lane = true;
+            m6r[rr] = x > 1 ? m6 : 0.;
+            m8r[rr] = x > 1 ? m8 : 0.;
+        }
+        const bool masked = SP_WARP_ANY(mask_lane);
+        // row a (0-based) computes cell NC-1-s+a at step s; it needs bM of the row above at its own cell
+        // (that row's previous step) and bI of the row above one cell to the left (fresh)
+        auto pass = [&](auto rtag, auto mtag) {
+            constexpr int RR = decltype(rtag)::value;
+            constexpr bool MK = decltype(mtag)::value != 0;
+            double Mc[RR], cD[RR];
 #pragma unroll
-                    for (int rr = RA; rr < RBB; rr++) {
-                        const double e = (bit(rr) ? emA : emB) * Mup;
-                        const double bMv = SP_FMA(m2, cD[rr], SP_FMA(e, m0, eim1 * Iup));
-                        const double bIv = SP_FMA(e, m3, eim4 * Iup);
-                        cD[rr] = SP_FMA(m8, cD[rr], e * m6);
-                        Mup = Mc[rr];
-                        Iup = bIv;
-                        Mc[rr] = bMv;
-                        if (rr == RR - 1) {
-                            SpD2 v = {bMv, bIv};
-                            cell[(RR - 1) * STRIDE] = v;  // cell NC-1-s+(RR-1)
-                        }
-                    }
-                };
-                sp_static_for<0, RR - 1>([&](auto st) {
-                    constexpr int S = decltype(st)::value;
-                    step(mi + (NC - 1 - S) * STRIDE, SpInt<0>(), SpInt<S + 1>(),
-                         [&](int rr) { return sp_bit_rt(mmr[rr], NC - 1 - S + rr); });
-                });
-                int s = RR - 1;
-                for (; s + 8 <= NC; s += 8) {
-                    // rows' cells at step s+J: NC-1-(s+J)+rr; the 8 cells of row rr are bits (NC-8-s+rr)..(NC-1-s+rr)
-                    uint32_t mb[RR];
-#pragma unroll
-                    for (int rr = 0; rr < RR; rr++) mb[rr] = sp_bits8_rt(mmr[rr], NC - 8 - s + rr);
-                    SpD2 *cell = mi + (NC - 1 - s) * STRIDE;
-                    sp_static_for<0, 8>([&](auto jt) {
-                        constexpr int J = decltype(jt)::value;
-                        step(cell - J * STRIDE, SpInt<0>(), SpInt<RR>(), [&](int rr) { return (mb[rr] >> (7 - J)) & 1; });
-                    });
+            for (int rr = 0; rr < RR; rr++) { Mc[rr] = 0.; cD[rr] = 0.; }
+            double b0 = mi[(NC - 1) * STRIDE].x;  // bM of the stored row at the cell row 0 computes next
+            auto step = [&](SpD2 *cell, auto ra_tag, auto rb_tag, auto bits) {  // cell = &mi[NC-1-s]: row 0's cell
+                constexpr int RA = decltype(ra_tag)::value, RBB = decltype(rb_tag)::value;
+                double Mup = 0., Iup = 0.;
+                if constexpr (RA == 0) {
+                    const SpD2 a = cell[-STRIDE];  // (cell -1 holds zeros)
+                    Mup = b0;
+                    Iup = a.y;
+                    b0 = a.x;
+                } else {
+                    Mup = Mc[RA - 1];  // the row above has finished: its cell 0, bI = 0 left of the band
                 }
-                for (; s < NC; s++)
-                    step(mi + (NC - 1 - s) * STRIDE, SpInt<0>(), SpInt<RR>(),
-                         [&](int rr) { return sp_bit_rt(mmr[rr], NC - 1 - s + rr); });
-                sp_static_for<0, RR - 1>([&](auto dt) {
-                    constexpr int D = decltype(dt)::value;
-                    step(mi + (-1 - D) * STRIDE, SpInt<D + 1>(), SpInt<RR>(),
-                         [&](int rr) { return sp_bit_rt(mmr[rr], -1 - D + rr); });
-                });
+#pragma unroll
+                for (int rr = RA; rr < RBB; rr++) {
+                    const uint32_t b = bits(rr);
+                    double bMv, bIv;
+                    if constexpr (MK) {
+                        const double e = ((b & 2) ? 1. : ((b & 1) ? emA : emB)) * Mup;
+                        bMv = SP_FMA(m2, cD[rr], SP_FMA(e, m0, eim1 * Iup));
+                        bIv = SP_FMA(e, m3, eim4 * Iup);
+                        cD[rr] = SP_FMA(m8r[rr], cD[rr], e * m6r[rr]);
+                        if (!(b & 4)) { bMv = 0.; bIv = 0.; cD[rr] = 0.; }
+                    } else {
+                        const double e = ((b & 1) ? emA : emB) * Mup;
+                        bMv = SP_FMA(m2, cD[rr], SP_FMA(e, m0, eim1 * Iup));
+                        bIv = SP_FMA(e, m3, eim4 * Iup);
+                        cD[rr] = SP_FMA(m8, cD[rr], e * m6);
+                    }
+                    Mup = Mc[rr];
+                    Iup = bIv;
+                    Mc[rr] = bMv;
+                    if (rr == RR - 1) {
+                        SpD2 v = {bMv, bIv};
+                        cell[(RR - 1) * STRIDE] = v;  // cell NC-1-s+(RR-1)
+                    }
+                }
             };
-            if (R == 1) pass(SpInt<1>());
-            else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>());
-            else if (RB >= 3 && R == 3) pass(SpInt<(RB >= 3 ? 3 : 1)>());
-            else pass(SpInt<RB>());
-        } else {
-            SpBits<NW> vm;
-            int lo, hi;
-            valid_range(i, lo, hi);
-            sp_bits_range(vm, lo, hi);
-            const double m6e = i > 1 ? m6 : 0., m8e = i > 1 ? m8 : 0.;
-            double cD = 0., bMo = mi[(NC - 1) * STRIDE].x;
-#pragma unroll 2
-            for (int o = NC - 1; o >= 0; o--) {
-                const SpD2 a = mi[(o - 1) * STRIDE];
-                const double e = (sp_bit_rt(nn0, o) ? 1. : (sp_bit_rt(mmr[0], o) ? emA : emB)) * bMo;
-                SpD2 v;
-                v.x = SP_FMA(m2, cD, SP_FMA(e, m0, eim1 * a.y));
-                v.y = SP_FMA(e, m3, eim4 * a.y);
-                cD = SP_FMA(m8e, cD, e * m6e);
-                if (!sp_bit_rt(vm, o)) { v.x = 0.; v.y = 0.; cD = 0.; }
-                mi[o * STRIDE] = v;
-                bMo = a.x;
+            auto bit_rt = [&](int rr, int o) -> uint32_t {
+                uint32_t v = sp_bit_rt(mmr[rr], o);
+                if constexpr (MK) v |= sp_bit_rt(nnr[rr], o) << 1 | sp_bit_rt(vmr[rr], o) << 2;
+                return v;
+            };
+            sp_static_for<0, RR - 1>([&](auto st) {
+                constexpr int S = decltype(st)::value;
+                step(mi + (NC - 1 - S) * STRIDE, SpInt<0>(), SpInt<S + 1>(), [&](int rr) { return bit_rt(rr, NC - 1 - S + rr); });
+            });
+            int s = RR - 1;
+            for (; s + 8 <= NC; s += 8) {
+                // rows' cells at step s+J: NC-1-(s+J)+rr; the 8 cells of row rr are bits (NC-8-s+rr)..(NC-1-s+rr)
+                uint32_t mb[RR], nb[MK ? RR : 1], vb[MK ? RR : 1];
+#pragma unroll
+                for (int rr = 0; rr < RR; rr++) {
+                    mb[rr] = sp_bits8_rt(mmr[rr], NC - 8 - s + rr);
+                    if constexpr (MK) {
+                        nb[rr] = sp_bits8_rt(nnr[rr], NC - 8 - s + rr);
+                        vb[rr] = sp_bits8_rt(vmr[rr], NC - 8 - s + rr);
+                    }
+                }
+                SpD2 *cell = mi + (NC - 1 - s) * STRIDE;
+                sp_static_for<0, 8>([&](auto jt) {
+                    constexpr int J = decltype(jt)::value;
+                    step(cell - J * STRIDE, SpInt<0>(), SpInt<RR>(), [&](int rr) -> uint32_t {
+                        uint32_t v = (mb[rr] >> (7 - J)) & 1;
+                        if constexpr (MK) v |= ((nb[rr] >> (7 - J)) & 1) << 1 | ((vb[rr] >> (7 - J)) & 1) << 2;
+                        return v;
+                    });
+                });
             }
+            for (; s < NC; s++)
+                step(mi + (NC - 1 - s) * STRIDE, SpInt<0>(), SpInt<RR>(), [&](int rr) { return bit_rt(rr, NC - 1 - s + rr); });
+            sp_static_for<0, RR - 1>([&](auto dt) {
+                constexpr int D = decltype(dt)::value;
+                step(mi + (-1 - D) * STRIDE, SpInt<D + 1>(), SpInt<RR>(), [&](int rr) { return bit_rt(rr, -1 - D + rr); });
+            });
+        };
+        if (!masked) {
+            if (R == 1) pass(SpInt<1>(), SpInt<0>());
+            else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>(), SpInt<0>());
+            else if (RB >= 3 && R == 3) pass(SpInt<(RB >= 3 ? 3 : 1)>(), SpInt<0>());
+            else pass(SpInt<RB>(), SpInt<0>());
+        } else {
+            if (R == 1) pass(SpInt<1>(), SpInt<1>());
+            else if (RB >= 2 && R == 2) pass(SpInt<(RB >= 2 ? 2 : 1)>(), SpInt<1>());
+            else if (RB >= 3 && R == 3) pass(SpInt<(RB >= 3 ? 3 : 1)>(), SpInt<1>());
+            else pass(SpInt<RB>(), SpInt<1>());
         }
-        const int last = i - adv + 1;
+        const int last = i - R + 1;
         if (last >= i_stop && last >= 1 && t_next + 1 == last) {
             map_row(nr);
             nr--;
             t_next = nr >= 0 ? rows[nr].t : -2;
         }
-        j += adv;
-        q4 = q4n;
-        r4 = r4n;
-        since_check += adv;
+        j += R;
+        pack();
+        since_check += R;
         if (since_check >= SP_HMMF_RS) {
             range_check(last >= i_stop && last >= 1);
             since_check = 0;

@@ -466,12 +466,21 @@ __global__ void __launch_bounds__(32 * sp_hmmf_warps(NC), 1) k_hmmf(const SpCons
         in.l_ref = it.l_ref;
         in.l_query = it.l_query;
         in.par_bw = it.par_bw;
-        // the warp's virtual band: as wide as its widest instance (instances are ordered by width)
-        const int bww = __reduce_max_sync(0xffffffffu, sp_hmm_bw(it.l_ref, it.l_query, it.par_bw));
-        const int flag = sp_hmmf_instance<32, (NC + 63) / 64>(*Cp, in, mi, bww, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
-                                                             rows + it.row0, dup ? 0 : it.n_rows, guard_all != 0);
-        if (!dup && flag) rerun_list[first + atomicAdd(rerun_count, 1)] = idx;
-        __syncwarp();
+        // The virtual band is as wide as the instances' own: instances are ordered by width, so a set is uniform except
+        // where two widths meet -- such a set is run once per width it holds, the other lanes idling along (no rows).
+        const int mybw = sp_hmm_bw(it.l_ref, it.l_query, it.par_bw);
+        bool todo = !dup;
+        for (;;) {
+            const unsigned left = __ballot_sync(0xffffffffu, todo);
+            if (!left) break;
+            const int bww = __shfl_sync(0xffffffffu, mybw, __ffs(left) - 1);
+            const bool mine = todo && mybw == bww;
+            const int flag = sp_hmmf_instance<32, (NC + 63) / 64>(*Cp, in, mi, bww, fsave + (int64_t) it.row0 * fs_stride,
+                                                                 fs_stride, rows + it.row0, mine ? it.n_rows : 0, guard_all != 0);
+            if (mine && flag) rerun_list[first + atomicAdd(rerun_count, 1)] = idx;
+            if (mine) todo = false;
+            __syncwarp();
+        }
     }
 }
 
