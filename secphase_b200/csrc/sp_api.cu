@@ -387,7 +387,7 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
 #endif
 #undef SP_ATTR
 #define SP_ATTRF(NC) attr_ok = attr_ok && cudaFuncSetAttribute(k_hmmf<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) == cudaSuccess
-    SP_ATTRF(41); SP_ATTRF(43); SP_ATTRF(45); SP_ATTRF(55); SP_ATTRF(73); SP_ATTRF(97); SP_ATTRF(125); SP_ATTRF(189);
+    SP_ATTRF(41); SP_ATTRF(43); SP_ATTRF(45); SP_ATTRF(55);
 #undef SP_ATTRF
     if (const char *e = getenv("SECPHASE_B200_HMM")) c->hmm_mode = strcmp(e, "strict") == 0 ? 0 : 1;
     if (!attr_ok) {
@@ -759,8 +759,8 @@ static void launch_hmmf(sp_ctx *c, Slot &S, cudaStream_t st, int cls, int first,
     int grid = (nblk + wpc - 1) / wpc;
     if (grid > c->hmm_sms) grid = c->hmm_sms;
     k_hmmf<NC><<<grid, 32 * wpc, slab * wpc, st>>>(c->dC.as<SpConst>(), S.items.as<SpItem>(), S.order.as<int32_t>(), first, cnt,
-                                                  ref, qbytes, seq_pool, seq_off, S.fsave.as<double>(), fs_stride,
-                                                  S.rows.as<SpRow>(), S.work_counter.as<int>() + cls, S.rerun_list.as<int32_t>(),
+                                                  ref, qbytes, seq_pool, seq_off, S.s_pool.as<double>(), S.fsave.as<double>(),
+                                                  fs_stride, S.rows.as<SpRow>(), S.work_counter.as<int>() + cls,
                                                   S.work_counter.as<int>() + 2 * SP_N_CLASSES + cls, guard_all ? 1 : 0);
 }
 
@@ -806,22 +806,9 @@ static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_
                 case 41: launch_hmmf<41>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
                 case 43: launch_hmmf<43>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
                 case 45: launch_hmmf<45>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
-                case 55: launch_hmmf<55>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
-                case 73: launch_hmmf<73>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
-                case 97: launch_hmmf<97>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
-                case 125: launch_hmmf<125>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
-                default: launch_hmmf<189>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                default: launch_hmmf<55>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
             }
             S.launches++;
-            // the instances its guard band flagged, recomputed in the reference's rounding order (generic strict body:
-            // their number is tiny and only known on the device)
-            int32_t *rl = S.rerun_list.as<int32_t>();
-            int *rcnt = S.work_counter.as<int>() + 2 * SP_N_CLASSES + cls, *rwork = S.work_counter.as<int>() + SP_N_CLASSES + cls;
-            switch (sp_h2_words(bwc)) {
-                case 1: launch_hmm2<1, 0, false>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, nullptr, 0, rl, rcnt, rwork); break;
-                case 2: launch_hmm2<2, 0, false>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, nullptr, 0, rl, rcnt, rwork); break;
-                default: launch_hmm2<3, 0, false>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, nullptr, 0, rl, rcnt, rwork); break;
-            }
         } else if (bwc != 0) {
             const int nw = sp_h2_words(bwc);
 #define SP_LAUNCH(NW, NC)                                                                                          \

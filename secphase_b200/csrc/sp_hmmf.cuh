@@ -50,17 +50,32 @@
 #endif
 
 #define SP_HMMF_RS 16
-#define SP_HMMF_RB 4  // rows per pass of the plain bodies                            // rows between two range checks
+#define SP_HMMF_RB 4  // rows per pass of the plain bodies
+#ifndef SP_HMMF_CHUNK
+#define SP_HMMF_CHUNK 8  // cells per iteration of a pass's steady loop (one mask extraction per row and chunk)
+#endif
+// a global byte load that stays where it is written (the rows' codes are fetched BEFORE the pass that hides their
+// latency; a plain load would be sunk to its first use behind the pass)
+SP_HD uint32_t sp_ldg_u8_here(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}                            // rows between two range checks
 #define SP_HMMF_GUARD_ABS 7.105427357601002e-15  // 2^-47: 64 ulps of a posterior next to 1
 #define SP_HMMF_GUARD_REL 1e-9
 #define SP_HMMF_TIE_REL 1e-9
 enum { SP_HMMF_NEAR_THRESHOLD = 1, SP_HMMF_NEAR_TIE = 2, SP_HMMF_NUMERIC = 4 };
 
-// cells of the fast kernel's virtual band for a band class (sp_common.h): every class the shared-memory
-// kernels cover (bw <= SP_H2_MAXBW); 0 = no fast body (the generic class)
+// cells of the fast kernel's slab for a band class (sp_common.h), 0 = the class runs the strict kernel: the fast
+// kernel serves the classes whose row masks fit one 64-bit word (bw <= 27: 99 % of the HiFi band cells, a third of
+// ONT's); the wider ones keep too few warps on an SM to gain from it (measured)
 SP_HD int sp_hmmf_class_cells(int cls) {
     const int bw = sp_class_bw(cls);
-    return bw > 0 ? 2 * bw + 1 : 0;
+    return (bw > 0 && 2 * bw + 1 <= 64) ? 2 * bw + 1 : 0;
 }
 
 SP_HD int sp_dbl_hi(double x) {
@@ -247,8 +262,8 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
 #pragma unroll
         for (int rr = 0; rr < RB; rr++) {
             const int row = i0 + rr;
-            qn[rr] = row <= Lq ? sp_query_raw(in, row - 1) : 0;
-            rn[rr] = row + BW <= Lr ? sp_ldg_u8(in.ref + row + BW - 1) : 0;
+            qn[rr] = row <= Lq ? sp_ldg_u8_here(in.qbytes ? in.qbytes + in.q0 + (row - 1) : in.qseq4 + ((in.q0 + row - 1) >> 1)) : 0;
+            rn[rr] = row + BW <= Lr ? sp_ldg_u8_here(in.ref + row + BW - 1) : 0;
         }
     };
     auto pack = [&]() {  // byte r <-> row i+r
@@ -378,7 +393,8 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
             });
             // steady: steps RR-1..NC-1, all rows; chunks of 8 steps share one mask extraction per row
             int s = RR - 1;
-            for (; s + 8 <= NC; s += 8) {
+            constexpr int CK = SP_HMMF_CHUNK;
+            for (; s + CK <= NC; s += CK) {
                 uint32_t mb[RR], nb[MK ? RR : 1], vb[MK ? RR : 1];
 #pragma unroll
                 for (int rr = 0; rr < RR; rr++) {
@@ -389,7 +405,7 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
                     }
                 }
                 SpD2 *cell = mi + s * STRIDE;
-                sp_static_for<0, 8>([&](auto jt) {
+                sp_static_for<0, CK>([&](auto jt) {
                     constexpr int J = decltype(jt)::value;
                     step(cell + J * STRIDE, s + J, SpInt<0>(), SpInt<RR>(), [&](int rr) -> uint32_t {
                         uint32_t v = (mb[rr] >> J) & 1;
@@ -497,8 +513,8 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
             const int x = x0 - rr;
             const bool on = x >= 1 && x >= i_stop;
             const int y = x - BW;
-            qn[rr] = on ? sp_query_raw(in, x) : 0;
-            rn[rr] = (on && y >= 0 && y < Lr) ? sp_ldg_u8(in.ref + y) : 0;
+            qn[rr] = on ? sp_ldg_u8_here(in.qbytes ? in.qbytes + in.q0 + x : in.qseq4 + ((in.q0 + x) >> 1)) : 0;
+            rn[rr] = (on && y >= 0 && y < Lr) ? sp_ldg_u8_here(in.ref + y) : 0;
         }
     };
     const int jmax = SP_WARP_MAX(Lq - 1 - i_stop);
@@ -613,23 +629,24 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
                 step(mi + (NC - 1 - S) * STRIDE, SpInt<0>(), SpInt<S + 1>(), [&](int rr) { return bit_rt(rr, NC - 1 - S + rr); });
             });
             int s = RR - 1;
-            for (; s + 8 <= NC; s += 8) {
-                // rows' cells at step s+J: NC-1-(s+J)+rr; the 8 cells of row rr are bits (NC-8-s+rr)..(NC-1-s+rr)
+            constexpr int CK = SP_HMMF_CHUNK;
+            for (; s + CK <= NC; s += CK) {
+                // rows' cells at step s+J: NC-1-(s+J)+rr; the CK cells of row rr are bits (NC-CK-s+rr)..(NC-1-s+rr)
                 uint32_t mb[RR], nb[MK ? RR : 1], vb[MK ? RR : 1];
 #pragma unroll
                 for (int rr = 0; rr < RR; rr++) {
-                    mb[rr] = sp_bits8_rt(mmr[rr], NC - 8 - s + rr);
+                    mb[rr] = sp_bits8_rt(mmr[rr], NC - CK - s + rr);
                     if constexpr (MK) {
-                        nb[rr] = sp_bits8_rt(nnr[rr], NC - 8 - s + rr);
-                        vb[rr] = sp_bits8_rt(vmr[rr], NC - 8 - s + rr);
+                        nb[rr] = sp_bits8_rt(nnr[rr], NC - CK - s + rr);
+                        vb[rr] = sp_bits8_rt(vmr[rr], NC - CK - s + rr);
                     }
                 }
                 SpD2 *cell = mi + (NC - 1 - s) * STRIDE;
-                sp_static_for<0, 8>([&](auto jt) {
+                sp_static_for<0, CK>([&](auto jt) {
                     constexpr int J = decltype(jt)::value;
                     step(cell - J * STRIDE, SpInt<0>(), SpInt<RR>(), [&](int rr) -> uint32_t {
-                        uint32_t v = (mb[rr] >> (7 - J)) & 1;
-                        if constexpr (MK) v |= ((nb[rr] >> (7 - J)) & 1) << 1 | ((vb[rr] >> (7 - J)) & 1) << 2;
+                        uint32_t v = (mb[rr] >> (CK - 1 - J)) & 1;
+                        if constexpr (MK) v |= ((nb[rr] >> (CK - 1 - J)) & 1) << 1 | ((vb[rr] >> (CK - 1 - J)) & 1) << 2;
                         return v;
                     });
                 });

@@ -418,14 +418,14 @@ __global__ void __launch_bounds__(224, 1) k_hmm2(const SpConst *__restrict__ Cp,
     }
 }
 
-// Fast-arithmetic K4 kernel (sp_hmmf.cuh), every band class of the shared-memory kernels: persistent
-// CTAs, one instance per lane, per-warp slab of (NC+2) x 32 16-byte cells and nothing else -- no state
-// is carried in registers between rows, so up to ten warps fit an SM.  Every lane of a warp runs an instance (the last,
-// partial set repeats its last instance with no rows) because the row bodies are chosen by warp votes.
-// Instances whose guard band fired are appended to rerun_list[first ...] for the strict kernel.
+// Fast-arithmetic K4 kernel (sp_hmmf.cuh): persistent CTAs, one instance per lane, per-warp slab of (NC+2) x 32
+// 16-byte cells and nothing else.  Every lane of a warp runs an instance (the last, partial set repeats its last
+// instance with no rows) because the row bodies are chosen by warp votes.  An instance whose guard band fired is
+// recomputed at once, by its own lane, with the strict body (sp_hmm2.cuh, the reference's rounding order) in a
+// private corner of the warp's slab -- a strict instance needs ~1 KB when it does not have to share banks with 31
+// others -- so no second launch trails the class.
 // warps per CTA = 16-byte-cell slabs that fit the 227 KB of shared memory of an SM, at most SP_HMMF_MAX_WARPS
-// (two per scheduler already cover the FP64 pipe: every warp carries up to four independent row chains, and
-// with eight warps a thread may use the whole 255-register budget)
+// (two per scheduler; with eight warps a thread may use the whole 255-register budget)
 #ifndef SP_HMMF_MAX_WARPS
 #define SP_HMMF_MAX_WARPS 8
 #endif
@@ -437,11 +437,12 @@ __global__ void __launch_bounds__(32 * sp_hmmf_warps(NC), 1) k_hmmf(const SpCons
                                                  const int32_t *__restrict__ order, int first, int count,
                                                  const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qbytes,
                                                  const uint8_t *__restrict__ seq_pool, const int64_t *__restrict__ seq_off,
-                                                 double *__restrict__ fsave, int64_t fs_stride, SpRow *rows,
-                                                 int *work_counter, int32_t *rerun_list, int *rerun_count, int guard_all) {
+                                                 double *__restrict__ s_pool, double *__restrict__ fsave, int64_t fs_stride,
+                                                 SpRow *rows, int *work_counter, int *rerun_count, int guard_all) {
     extern __shared__ double2 smem2[];
     const int lane = threadIdx.x & 31;
-    double2 *mi = smem2 + (size_t) (threadIdx.x >> 5) * (NC + 2) * 32 + 32 + lane;  // cell -1 sits one row below
+    double2 *slab = smem2 + (size_t) (threadIdx.x >> 5) * (NC + 2) * 32;
+    double2 *mi = slab + 32 + lane;  // cell -1 sits one row below
     const int nwork = (count + 31) >> 5;
     for (;;) {
         int w = 0;
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(32 * sp_hmmf_warps(NC), 1) k_hmmf(const SpCons
         // The virtual band is as wide as the instances' own: instances are ordered by width, so a set is uniform except
         // where two widths meet -- such a set is run once per width it holds, the other lanes idling along (no rows).
         const int mybw = sp_hmm_bw(it.l_ref, it.l_query, it.par_bw);
-        bool todo = !dup;
+        bool todo = !dup, flagged = false;
         for (;;) {
             const unsigned left = __ballot_sync(0xffffffffu, todo);
             if (!left) break;
@@ -477,10 +478,35 @@ __global__ void __launch_bounds__(32 * sp_hmmf_warps(NC), 1) k_hmmf(const SpCons
             const bool mine = todo && mybw == bww;
             const int flag = sp_hmmf_instance<32, (NC + 63) / 64>(*Cp, in, mi, bww, fsave + (int64_t) it.row0 * fs_stride,
                                                                  fs_stride, rows + it.row0, mine ? it.n_rows : 0, guard_all != 0);
-            if (mine && flag) rerun_list[first + atomicAdd(rerun_count, 1)] = idx;
+            if (mine && flag) flagged = true;
             if (mine) todo = false;
             __syncwarp();
         }
+        // guard band fired: the lane recomputes its instance in the reference's order (generic strict body, no votes)
+        unsigned fl = __ballot_sync(0xffffffffu, flagged);
+        if (fl) {
+            constexpr int BWC = (NC - 1) / 2, NCELL = 2 * BWC + 3;     // strict band: cells -1 .. 2bw+1
+            constexpr int PER = NCELL + (NCELL + 1) / 2;                 // (M,I) pairs + the D plane, in 16-byte units
+            constexpr int CAP = (NC + 2) * 32 / PER;                     // instances the slab holds at a time
+            if (lane == 0) atomicAdd(rerun_count, __popc(fl));
+            int rank = __popc(fl & ((1u << lane) - 1));
+            while (fl) {
+                __syncwarp();
+                if (flagged && rank < CAP) {
+                    double2 *reg = slab + rank * PER;
+                    for (int c = 0; c < PER; c++) reg[c] = make_double2(0., 0.);
+                    SpBand2<1> B;
+                    B.mi = reg + 1;
+                    B.d = reinterpret_cast<double *>(reg + NCELL) + 1;
+                    sp_hmm2_instance<1, (NC + 63) / 64, 0>(*Cp, in, B, s_pool + it.s_off, fsave + (int64_t) it.row0 * fs_stride,
+                                                          fs_stride, rows + it.row0, it.n_rows, false);
+                    flagged = false;
+                }
+                rank -= CAP;
+                fl = __ballot_sync(0xffffffffu, flagged);
+            }
+        }
+        __syncwarp();
     }
 }
 

@@ -470,7 +470,7 @@ int hs_run3(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         in.l_ref = I.l_ref; in.l_query = I.l_query; in.par_bw = I.par_bw;
         bool strict = true;
         std::vector<SpRow> fast_rows;
-        if (hmm_mode != 0 && !full_baq && bw <= SP_H2_MAXBW && I.n_rows > 0) {
+        if (hmm_mode != 0 && !full_baq && sp_hmmf_class_cells(sp_band_class(bw)) != 0 && I.n_rows > 0) {  // launch_hmm's choice
             // every third instance plays a lane of a mixed warp (virtual band = its class's widest)
             const int bwv = it % 3 == 2 ? sp_class_bw(sp_band_class(bw)) : bw;
             const int nc = 2 * bwv + 1;
