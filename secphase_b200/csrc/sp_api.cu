@@ -800,15 +800,23 @@ static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_
         if (used < SP_N_AUX) CK(cudaStreamWaitEvent(as, S.ev_fork, 0));
         used++;
         const int bwc = sp_class_bw(cls);
-        const int fcells = fast ? sp_hmmf_class_cells(cls) : 0;
-        if (fcells != 0) {
-            switch (fcells) {
-                case 41: launch_hmmf<41>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
-                case 43: launch_hmmf<43>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
-                case 45: launch_hmmf<45>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
-                default: launch_hmmf<55>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+        if (fast && sp_hmmf_class_cells(cls) != 0) {
+            // Every class the fast kernel serves goes into ONE launch (they are a contiguous stretch of the order: the
+            // band width is a run-time value of each warp, the slab is sized for the widest): one work queue, so no
+            // class leaves SMs idle in a partial last wave of its own and only one tail remains.
+            int lo = cls;
+            while (lo > 0 && sp_hmmf_class_cells(lo - 1) != 0) lo--;
+            const int total = first[cls + 1] - first[lo];
+            int widest = cls;
+            while (widest > lo && class_count[widest] == 0) widest--;
+            switch (sp_hmmf_class_cells(widest)) {
+                case 41: launch_hmmf<41>(c, S, as, lo, first[lo], total, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                case 43: launch_hmmf<43>(c, S, as, lo, first[lo], total, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                case 45: launch_hmmf<45>(c, S, as, lo, first[lo], total, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                default: launch_hmmf<55>(c, S, as, lo, first[lo], total, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
             }
             S.launches++;
+            cls = lo;  // the classes below were part of this launch
         } else if (bwc != 0) {
             const int nw = sp_h2_words(bwc);
 #define SP_LAUNCH(NW, NC)                                                                                          \

@@ -52,7 +52,7 @@
 #define SP_HMMF_RS 16
 #define SP_HMMF_RB 4  // rows per pass of the plain bodies
 #ifndef SP_HMMF_CHUNK
-#define SP_HMMF_CHUNK 8  // cells per iteration of a pass's steady loop (one mask extraction per row and chunk)
+#define SP_HMMF_CHUNK 4  // cells per iteration of a pass's steady loop (one mask extraction per row and chunk)
 #endif
 // a global byte load that stays where it is written (the rows' codes are fetched BEFORE the pass that hides their
 // latency; a plain load would be sunk to its first use behind the pass)
