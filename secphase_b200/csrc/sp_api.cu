@@ -154,6 +154,7 @@ struct sp_ctx {
     int test_block_cap = 0;  // tests: first plan clamps every group's block workspace to this (forces the retry)
     int64_t cap_retries = 0;
     bool full_baq = false;  // sp_set_write_qual: --writeBam mode
+    bool hmm_merge = false; // SECPHASE_B200_HMM_MERGE=1: one fast launch for all classes (best pipelined, longest single-batch tail)
     int hmm_mode = 1;       // sp_set_hmm_mode: 0 strict (the reference's rounding order), 1 fast + guard band + strict re-run
     bool streams_ready = false;  // ensure_streams
     int sm_count = 0;
@@ -390,6 +391,7 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
     SP_ATTRF(41); SP_ATTRF(43); SP_ATTRF(45); SP_ATTRF(55);
 #undef SP_ATTRF
     if (const char *e = getenv("SECPHASE_B200_HMM")) c->hmm_mode = strcmp(e, "strict") == 0 ? 0 : 1;
+    if (const char *e = getenv("SECPHASE_B200_HMM_MERGE")) c->hmm_merge = atoi(e) != 0;
     if (!attr_ok) {
         set_err("sp_create: cudaFuncSetAttribute(k_hmm) failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -800,8 +802,16 @@ static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_
         if (used < SP_N_AUX) CK(cudaStreamWaitEvent(as, S.ev_fork, 0));
         used++;
         const int bwc = sp_class_bw(cls);
-        if (fast && sp_hmmf_class_cells(cls) != 0) {
-            // Every class the fast kernel serves goes into ONE launch (they are a contiguous stretch of the order: the
+        if (fast && sp_hmmf_class_cells(cls) != 0 && !c->hmm_merge) {
+            switch (sp_hmmf_class_cells(cls)) {
+                case 41: launch_hmmf<41>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                case 43: launch_hmmf<43>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                case 45: launch_hmmf<45>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                default: launch_hmmf<55>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+            }
+            S.launches++;
+        } else if (fast && sp_hmmf_class_cells(cls) != 0) {
+            // SECPHASE_B200_HMM_MERGE=1: every class the fast kernel serves goes into ONE launch (they are a contiguous stretch of the order: the
             // band width is a run-time value of each warp, the slab is sized for the widest): one work queue, so no
             // class leaves SMs idle in a partial last wave of its own and only one tail remains.
             int lo = cls;

@@ -168,8 +168,10 @@ SP_HD int sp_query_decode(const SpHmmIn &in, int i0, uint32_t raw) {
 // lives in registers and every cell index is a compile-time constant, which removes a third of
 // the shared-memory traffic and all per-chunk address / mask arithmetic.  full_warp says that all
 // 32 lanes are inside this function (the fast path takes warp-uniform decisions by vote).
+// SOLO: the lane runs on its own (the other lanes of the warp are elsewhere): the unrolled bodies' warp-uniform
+// decisions are then simply this lane's (k_hmmf's in-place recomputation of a guard-banded instance).
 template <int STRIDE, int NW, int NC, int FS_CS = 2, int NCRF_ = (NC > 45 ? SP_H2_NCRF_WIDE : SP_H2_NCRF),
-          int NCRB_ = SP_H2_NCRB>
+          int NCRB_ = SP_H2_NCRB, bool SOLO = false>
 SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<STRIDE> B, double *rinv, double *fsave,
                             int64_t fs_stride, SpRow *rows, int n_rows, bool full_warp) {
     constexpr int fs_cs = FS_CS;  // doubles between consecutive cells of a saved forward row
@@ -180,10 +182,12 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
     int fi0 = 1, fi1 = 0;
     bool unrolled_ok = false;
     if constexpr (NC > 0) {
-        unrolled_ok = full_warp && SP_WARP_ALL(2 * bw + 1 == NC);
+        if constexpr (SOLO) unrolled_ok = 2 * bw + 1 == NC;
+        else unrolled_ok = full_warp && SP_WARP_ALL(2 * bw + 1 == NC);
         if (unrolled_ok) {
             fi0 = bw + 2;
-            fi1 = SP_WARP_MIN(Lq < Lr - bw ? Lq : Lr - bw);
+            if constexpr (SOLO) fi1 = Lq < Lr - bw ? Lq : Lr - bw;
+            else fi1 = SP_WARP_MIN(Lq < Lr - bw ? Lq : Lr - bw);
         }
     }
     constexpr int NCR = NCRF_ < NC ? NCRF_ : NC;               // forward cells with D in registers
@@ -274,7 +278,8 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         double sum = 0.;
         bool fast = false;
         if constexpr (NC > 0) {
-            fast = i >= fi0 && i <= fi1 && !SP_WARP_ANY(has_n);  // warp-uniform: fi0, fi1 are
+            if constexpr (SOLO) fast = i >= fi0 && i <= fi1 && !has_n;
+            else fast = i >= fi0 && i <= fi1 && !SP_WARP_ANY(has_n);  // warp-uniform: fi0, fi1 are
             if (fast != d_regs) {                                 // move D between its plane and registers
 #pragma unroll
                 for (int o = 0; o < NCR; o++) {
@@ -485,7 +490,7 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
     // the first lane finishes.
     int jmax = Lq - 1 - i_stop;
     if constexpr (BWD_UNROLLED) {
-        if (unrolled_ok) jmax = SP_WARP_MAX(jmax);
+        if (unrolled_ok && !SOLO) jmax = SP_WARP_MAX(jmax);
     }
 #define Ir Dr  // backward: the same registers hold bI of the last written row while in the unrolled body
     bool i_regs = false;
@@ -524,7 +529,8 @@ SP_HD void sp_hmm2_instance(const SpConst &C, const SpHmmIn &in, const SpBand2<S
         if constexpr (BWD_UNROLLED) {
             if (unrolled_ok) {
                 // full sliding band with an in-range top cell: i >= bw+1 and i+bw < Lr
-                fast = SP_WARP_ALL(!live || (i >= bw + 1 && i + bw < Lr && !has_n));
+                if constexpr (SOLO) fast = !live || (i >= bw + 1 && i + bw < Lr && !has_n);
+                else fast = SP_WARP_ALL(!live || (i >= bw + 1 && i + bw < Lr && !has_n));
                 if (fast != i_regs) {  // unrolled body, cells < NCB: bM in the dense 8-byte plane, bI in registers
 #pragma unroll
                     for (int o = 0; o < NCB; o++) {

@@ -37,6 +37,9 @@ PY
 benchq)  # the bench line only (no CPU legs)
   ( timeout 600 python bench.py --no-cpu-baseline ) > $out/${tag}_benchq.json 2> $out/${tag}_benchq.err
   tail -c 900 $out/${tag}_benchq.json ;;
+benchm)  # the bench line only, one fast launch for all classes
+  ( SECPHASE_B200_HMM_MERGE=1 timeout 600 python bench.py --no-cpu-baseline ) > $out/${tag}_benchm.json 2> $out/${tag}_benchm.err
+  tail -c 900 $out/${tag}_benchm.json ;;
 ref)
   ( timeout 400 python bench.py --impl reference --steps 3 --warmup 1 ) > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
   cat $out/${tag}_bench_ref.json ;;
