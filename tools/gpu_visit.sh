@@ -59,6 +59,16 @@ stagehifi)  # HiFi bench-size stage times: fast (default lib and every lib under
   done
   timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --hmm strict >> $out/${tag}_stagehifi.json 2>> $out/${tag}_stagehifi.err
   cat $out/${tag}_stagehifi.json ;;
+traffic)  # DRAM bytes of the HMM launch set of one step (tools/traffic_from_ncu.py turns it into profiles/r02_traffic_k_hmm.json)
+  timeout 500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_hmm --csv \
+    --log-file $out/${tag}_traffic.csv python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --iters 1 \
+    > $out/${tag}_traffic_stage.json 2> $out/${tag}_traffic.err
+  tail -c 300 $out/${tag}_traffic_stage.json ;;
+ontsize)  # ONT stage times vs batch size (thread-per-alignment integer stages want many alignments in flight)
+  for g in 4096 10240 20480; do
+    timeout 300 python tools/stage_bench.py --preset ont --groups $g --locus-len 5000000 >> $out/${tag}_ontsize.json 2>> $out/${tag}_ontsize.err
+  done
+  cut -c1-330 $out/${tag}_ontsize.json ;;
 cli)
   ( timeout 500 python tools/cli_bench.py --groups 32768 ) > $out/${tag}_cli.json 2> $out/${tag}_cli.err
   tail -c 1200 $out/${tag}_cli.json ;;
