@@ -99,14 +99,17 @@ SPECS = {
                  groups=8192, pool=3, reads="simulated HiFi reads N(15 kb, 2 kb), primary + 1 secondary, --hifi preset"),
     "hifi_small": dict(config="configs[0]", title="hifi-10k", synth="hifi", params="hifi", locus_len=5_000_000,
                        groups=2048, pool=5, reads="10 240 simulated HiFi reads (~15 kb), primary + 1 secondary, --hifi preset"),
-    "ont": dict(config="configs[1]", title="ont-20k", synth="ont", params="ont", locus_len=5_000_000,
-                groups=4096, pool=5, reads="20 480 simulated ONT reads N(30 kb, 8 kb), higher indel rate, primary + 1 secondary, --ont preset"),
+    # large batches: the integer stages are thread-per-alignment / per-group latency chains whose time barely grows with the
+    # batch (profiles/r02_stage_ont_batch_size_v13.json: 4096 groups 38 ms, 20 480 groups 68 ms), so ONT wants many
+    # alignments in flight
+    "ont": dict(config="configs[1]", title="ont-30k", synth="ont", params="ont", locus_len=5_000_000,
+                groups=10240, pool=3, reads="30 720 simulated ONT reads N(30 kb, 8 kb) (the config asks for 20k), higher indel rate, primary + 1 secondary, --ont preset"),
     "wg_offsets": dict(config="configs[3]", title="wg-hifi-30x addressing", synth="hifi", params="hifi", locus_len=20_000_000,
                        groups=8192, pool=3, filler_bp=6_160_000_000,
                        reads="HiFi reads on the last two contigs of a 6.2 Gb replica (25 filler contigs of N first: every "
                              "reference window lies beyond 2^32), --hifi preset"),
     "stress": dict(config="configs[4]", title="stress", synth="stress", params="hifi", locus_len=2_000_000,
-                   groups=8192, pool=2,
+                   groups=8192, pool=3,
                    # a second parity sample from even more similar copies: there several secondaries share the top
                    # score, so the reference's rand() tie-break (ptAlignment.c:156-170) is compared at size too
                    tie_parity=dict(groups=1024, synth_over=dict(snv_rate=2e-4, indel_rate=4e-5, long_indel_rate=4e-6)),
@@ -658,7 +661,7 @@ def main():
     # ---- the other BASELINE configs (N=1 default run only) ------------------------------------
     if rank == 0 and world == 1 and args.preset == "hifi" and not args.no_per_config and not args.no_cpu_baseline:
         per = {}
-        plan = [("hifi_small", 10, 3), ("ont", 10, 3), ("wg_offsets", 6, 3), ("stress", 4, 2)]
+        plan = [("hifi_small", 10, 3), ("ont", 6, 3), ("wg_offsets", 6, 3), ("stress", 6, 3)]
         for name, k_steps, k_warm in plan:
             t_c = time.perf_counter()
             try:

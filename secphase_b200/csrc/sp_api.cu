@@ -388,7 +388,7 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
 #endif
 #undef SP_ATTR
 #define SP_ATTRF(NC) attr_ok = attr_ok && cudaFuncSetAttribute(k_hmmf<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->max_smem) == cudaSuccess
-    SP_ATTRF(41); SP_ATTRF(43); SP_ATTRF(45); SP_ATTRF(55);
+    SP_ATTRF(41); SP_ATTRF(43); SP_ATTRF(45); SP_ATTRF(55); SP_ATTRF(73); SP_ATTRF(97); SP_ATTRF(125);
 #undef SP_ATTRF
     if (const char *e = getenv("SECPHASE_B200_HMM")) c->hmm_mode = strcmp(e, "strict") == 0 ? 0 : 1;
     if (const char *e = getenv("SECPHASE_B200_HMM_MERGE")) c->hmm_merge = atoi(e) != 0;
@@ -802,20 +802,28 @@ static int launch_hmm(sp_ctx *c, Slot &S, cudaStream_t st, const int32_t *class_
         if (used < SP_N_AUX) CK(cudaStreamWaitEvent(as, S.ev_fork, 0));
         used++;
         const int bwc = sp_class_bw(cls);
-        if (fast && sp_hmmf_class_cells(cls) != 0 && !c->hmm_merge) {
-            switch (sp_hmmf_class_cells(cls)) {
+        // the fast kernel wants sets of one width: always true for the exact classes, true enough for the bw <= 27
+        // class, and for the wider ones only when the class is well populated (ONT) -- a sparsely filled wide class
+        // (HiFi's few hundred instances over nine widths) keeps the strict kernel
+        const int fcells = sp_hmmf_class_cells(cls);
+        const bool fast_cls = fast && fcells != 0 && (fcells <= 64 || cnt >= 2048);
+        if (fast_cls && (!c->hmm_merge || fcells > 64)) {
+            switch (fcells) {
                 case 41: launch_hmmf<41>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
                 case 43: launch_hmmf<43>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
                 case 45: launch_hmmf<45>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
-                default: launch_hmmf<55>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                case 55: launch_hmmf<55>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                case 73: launch_hmmf<73>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                case 97: launch_hmmf<97>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
+                default: launch_hmmf<125>(c, S, as, cls, first[cls], cnt, ref, qbytes, seq_pool, seq_off, fs_stride, guard_all); break;
             }
             S.launches++;
-        } else if (fast && sp_hmmf_class_cells(cls) != 0) {
+        } else if (fast_cls) {
             // SECPHASE_B200_HMM_MERGE=1: every class the fast kernel serves goes into ONE launch (they are a contiguous stretch of the order: the
             // band width is a run-time value of each warp, the slab is sized for the widest): one work queue, so no
             // class leaves SMs idle in a partial last wave of its own and only one tail remains.
             int lo = cls;
-            while (lo > 0 && sp_hmmf_class_cells(lo - 1) != 0) lo--;
+            while (lo > 0 && sp_hmmf_class_cells(lo - 1) != 0 && sp_hmmf_class_cells(lo - 1) <= 64) lo--;
             const int total = first[cls + 1] - first[lo];
             int widest = cls;
             while (widest > lo && class_count[widest] == 0) widest--;

@@ -70,12 +70,13 @@ SP_HD uint32_t sp_ldg_u8_here(const uint8_t *p) {
 #define SP_HMMF_TIE_REL 1e-9
 enum { SP_HMMF_NEAR_THRESHOLD = 1, SP_HMMF_NEAR_TIE = 2, SP_HMMF_NUMERIC = 4 };
 
-// cells of the fast kernel's slab for a band class (sp_common.h), 0 = the class runs the strict kernel: the fast
-// kernel serves the classes whose row masks fit one 64-bit word (bw <= 27: 99 % of the HiFi band cells, a third of
-// ONT's); the wider ones keep too few warps on an SM to gain from it (measured)
+// cells of the fast kernel's slab for a band class (sp_common.h), 0 = the class always runs the strict kernel.
+// Row masks of one (bw <= 27: 99 % of the HiFi band cells) or two 64-bit words (bw <= 62); the launcher sends a
+// two-word class to the fast kernel only when it is populated enough for its 32-instance sets to be uniform in
+// width (ONT), see launch_hmm.
 SP_HD int sp_hmmf_class_cells(int cls) {
     const int bw = sp_class_bw(cls);
-    return (bw > 0 && 2 * bw + 1 <= 64) ? 2 * bw + 1 : 0;
+    return (bw > 0 && 2 * bw + 1 <= 128) ? 2 * bw + 1 : 0;
 }
 
 SP_HD int sp_dbl_hi(double x) {

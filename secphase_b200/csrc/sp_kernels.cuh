@@ -467,21 +467,13 @@ __global__ void __launch_bounds__(32 * sp_hmmf_warps(NC), 1) k_hmmf(const SpCons
         in.l_ref = it.l_ref;
         in.l_query = it.l_query;
         in.par_bw = it.par_bw;
-        // The virtual band is as wide as the instances' own: instances are ordered by width, so a set is uniform except
-        // where two widths meet -- such a set is run once per width it holds, the other lanes idling along (no rows).
-        const int mybw = sp_hmm_bw(it.l_ref, it.l_query, it.par_bw);
-        bool todo = !dup, flagged = false;
-        for (;;) {
-            const unsigned left = __ballot_sync(0xffffffffu, todo);
-            if (!left) break;
-            const int bww = __shfl_sync(0xffffffffu, mybw, __ffs(left) - 1);
-            const bool mine = todo && mybw == bww;
-            const int flag = sp_hmmf_instance<32, (NC + 63) / 64>(*Cp, in, mi, bww, fsave + (int64_t) it.row0 * fs_stride,
-                                                                 fs_stride, rows + it.row0, mine ? it.n_rows : 0, guard_all != 0);
-            if (mine && flag) flagged = true;
-            if (mine) todo = false;
-            __syncwarp();
-        }
+        // The virtual band is as wide as the widest instance of the set.  Instances are ordered by width, so a set is
+        // uniform except where two widths meet; there the narrower lanes run every row through the masked pass.
+        const int bww = __reduce_max_sync(0xffffffffu, sp_hmm_bw(it.l_ref, it.l_query, it.par_bw));
+        const int flag = sp_hmmf_instance<32, (NC + 63) / 64>(*Cp, in, mi, bww, fsave + (int64_t) it.row0 * fs_stride, fs_stride,
+                                                             rows + it.row0, dup ? 0 : it.n_rows, guard_all != 0);
+        bool flagged = !dup && flag != 0;
+        __syncwarp();
         // guard band fired: the lane recomputes its instance in the reference's order (generic strict body, no votes)
         unsigned fl = __ballot_sync(0xffffffffu, flagged);
         if (fl) {

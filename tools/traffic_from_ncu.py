@@ -21,16 +21,20 @@ def main():
     for r in rows[h + 1:]:
         if len(r) <= vi or not r[0].isdigit():
             continue
-        d = launches.setdefault(int(r[0]), {"kernel": r[ki].split("(")[0]})
+        nm = r[ki]
+        nm = nm[:nm.index(">(") + 1] if ">(" in nm else nm.split("(")[0]
+        d = launches.setdefault(int(r[0]), {"kernel": nm.replace("(int)", "").replace("(bool)", "")})
         v = float(r[vi].replace(",", ""))
         unit = r[ui].lower()
         if "byte" in unit:
             v *= {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
         d[r[mi]] = v
     ids = sorted(launches)
-    # one step's launch set = the launches after the last repetition of the first kernel name
+    # every step launches the same set: steps = how often the most common kernel of the bulk class appears
     names = [launches[i]["kernel"] for i in ids]
-    per_step = names[1:].index(names[0]) + 1 if names[0] in names[1:] else len(names)
+    bulk = max(set(names), key=lambda n: (("41" in n), names.count(n)))
+    steps = max(1, names.count(bulk))
+    per_step = len(names) // steps
     last = ids[-per_step:]
     st = json.loads(open(stage_json).read().strip().splitlines()[-1])
     out = {
