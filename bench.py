@@ -459,7 +459,9 @@ def measure_config(sp, args, steps, warmup, local, rank, world, barrier, allredu
             out.append(eng.wait(inflight.pop(0), copy=True))
         return out
 
-    e2e_steps(max(warmup, 3))
+    # (with more distinct batches than slots every slot meets every batch size: warm up until the slots' device
+    # and pinned buffers have grown to the largest, or the timed region would contain their re-allocations)
+    e2e_steps(max(warmup, 3) if len(batches) <= n_slots else max(warmup, 3 * len(batches)))
     barrier()
     # the end-to-end arm is a host-visible quantity (pack + H2D + kernels + D2H + result tables in
     # host memory), so it is timed on the host clock around the synchronised region; the device-side
