@@ -49,8 +49,12 @@
 #define SP_FMA(a, b, c) __builtin_fma((a), (b), (c))
 #endif
 
+#ifndef SP_HMMF_RS
 #define SP_HMMF_RS 16
+#endif
+#ifndef SP_HMMF_RB
 #define SP_HMMF_RB 4  // rows per pass of the plain bodies
+#endif
 #ifndef SP_HMMF_CHUNK
 #define SP_HMMF_CHUNK 4  // cells per iteration of a pass's steady loop (one mask extraction per row and chunk)
 #endif
@@ -267,63 +271,67 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
             rn[rr] = row + BW <= Lr ? sp_ldg_u8_here(in.ref + row + BW - 1) : 0;
         }
     };
-    auto pack = [&]() {  // byte r <-> row i+r
-        q4 = 0;
+    auto pack = [&]() {  // byte r <-> row i+r.  Called after the pass: the barrier keeps the compiler from pulling the
+        q4 = 0;          // shifts up to the loads (where they would wait for them) -- volatile asms keep their order
         r4 = 0;
 #pragma unroll
-        for (int rr = 0; rr < RB; rr++) { q4 |= qn[rr] << (8 * rr); r4 |= rn[rr] << (8 * rr); }
+        for (int rr = 0; rr < RB; rr++) {
+#if defined(__CUDA_ARCH__)
+            asm volatile("" : "+r"(qn[rr]), "+r"(rn[rr])::"memory");
+#endif
+            q4 |= qn[rr] << (8 * rr);
+            r4 |= rn[rr] << (8 * rr);
+        }
     };
     fetch_fwd(2);
     pack();
     int since_check = 0;
     for (int i = 2; i <= LqW;) {
-        // ---- the next RB rows of this lane: masks, and how many of them share one pass (a consumed row ends it)
-        SpBits<NW> mmr[RB], nnr[RB], vmr[RB], ps0[RB], ps1[RB], ps2[RB];
+        // ---- rows of this pass: a consumed row ends the block (it is kept in memory), else RB rows
         int lane_r = RB;
-        {
-            SpBits<NW> a0 = p0, a1 = p1, a2 = p2;
-            bool stop = false;
+        if (t_next + 1 >= i && t_next + 1 < i + RB && t_next + 1 <= Lq) lane_r = t_next + 2 - i;
+        const int R = SP_WARP_MIN(lane_r);
+        // ---- advance the bit-planes over those rows; emission / N masks of each; does any row need the masked pass
+        // (an invalid column -- outside 1..l_ref or the instance's own band -- or an N)
+        SpBits<NW> mmr[RB], nnr[RB];
+        bool mask_lane = false;
 #pragma unroll
-            for (int rr = 0; rr < RB; rr++) {
+        for (int rr = 0; rr < RB; rr++) {
+            if (rr < R) {
                 const int row = i + rr;
                 const bool live = row <= Lq;
                 int qc = 0;
                 if (live) {
                     qc = sp_query_decode(in, row - 1, (q4 >> (8 * rr)) & 0xff);
                     const uint32_t rc = (r4 >> (8 * rr)) & 0xff;
-                    a0.shr1(); a1.shr1(); a2.shr1();
+                    p0.shr1(); p1.shr1(); p2.shr1();
                     if (row + BW <= Lr) {  // one column enters the band on the right
-                        a0.or_bit(NC - 1, (uint64_t) (rc & 1));
-                        a1.or_bit(NC - 1, (uint64_t) ((rc >> 1) & 1));
-                        a2.or_bit(NC - 1, (uint64_t) ((rc >> 2) & 1));
+                        p0.or_bit(NC - 1, (uint64_t) (rc & 1));
+                        p1.or_bit(NC - 1, (uint64_t) ((rc >> 1) & 1));
+                        p2.or_bit(NC - 1, (uint64_t) ((rc >> 2) & 1));
                     }
                 }
-                sp_h2_row_masks(a0, a1, a2, qc, mmr[rr], nnr[rr]);
-                ps0[rr] = a0; ps1[rr] = a1; ps2[rr] = a2;
-                int lo, hi;
-                valid_range(row, lo, hi);
-                sp_bits_range(vmr[rr], lo, hi);
-                if (!stop && live && t_next + 1 == row) {  // a consumed row ends the block (it is kept in memory)
-                    lane_r = rr + 1;
-                    stop = true;
-                }
+                sp_h2_row_masks(p0, p1, p2, qc, mmr[rr], nnr[rr]);
+                if (live && (narrow || row <= BW || row + BW > Lr || nnr[rr].any_below(NC))) mask_lane = true;
+            } else {
+                mmr[rr].clear();
+                nnr[rr].clear();
             }
         }
-        const int R = SP_WARP_MIN(lane_r);
-        {  // commit the planes, fetch the codes of the rows after this pass (their latency hides behind it)
-#pragma unroll
-            for (int rr = 0; rr < RB; rr++)
-                if (rr == R - 1) { p0 = ps0[rr]; p1 = ps1[rr]; p2 = ps2[rr]; }
-        }
-        fetch_fwd(i + R);
-        // a row with an invalid column (outside 1..l_ref or the instance's own band) or an N needs the masked pass
-        bool mask_lane = false;
-#pragma unroll
-        for (int rr = 0; rr < RB; rr++) {
-            const int row = i + rr;
-            if (rr < R && row <= Lq && (narrow || row <= BW || row + BW > Lr || nnr[rr].any_below(NC))) mask_lane = true;
-        }
+        fetch_fwd(i + R);  // the codes of the rows after this pass: their latency hides behind it
         const bool masked = SP_WARP_ANY(mask_lane);
+        SpBits<NW> vmr[RB];
+        if (masked) {
+#pragma unroll
+            for (int rr = 0; rr < RB; rr++) {
+                int lo, hi;
+                valid_range(i + rr, lo, hi);
+                sp_bits_range(vmr[rr], lo, hi);
+            }
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < RB; rr++) vmr[rr].clear();
+        }
         const int last = i + R - 1;
         const bool save = last <= Lq && t_next + 1 == last;
         double *fs = save ? fsave + (int64_t) nr * fs_stride : nullptr;
@@ -524,57 +532,54 @@ SP_HD int sp_hmmf_instance(const SpConst &C, const SpHmmIn &in, SpD2 *mi, int BW
     since_check = 0;
     for (int j = 0; j <= jmax;) {
         const int i = Lq - 1 - j;  // first (highest) row of this pass
-        SpBits<NW> mmr[RB], nnr[RB], vmr[RB], ps0[RB], ps1[RB], ps2[RB];
-        int lane_r = RB;
-        {
-            SpBits<NW> a0 = p0, a1 = p1, a2 = p2;
-            bool stop = false;
+        int lane_r = RB;  // a consumed row ends the block: the MAP reads it from memory
+        if (t_next + 1 <= i && t_next + 1 > i - RB && t_next + 1 >= i_stop && t_next + 1 >= 1) lane_r = i - t_next;
+        const int R = SP_WARP_MIN(lane_r);
+        // Cells left of column 1 or right of l_ref need no mask here: with the row above zero outside its valid
+        // cells the right side stays zero by itself, and what appears left of column 1 never flows back into a valid
+        // cell (dependencies only run towards smaller columns) nor into the MAP (f is zero there).  Only an instance
+        // narrower than its warp's band, an N, or row 1 (no D state there) takes the masked pass.
+        SpBits<NW> mmr[RB], nnr[RB];
+        bool mask_lane = false;
+        double m6r[RB], m8r[RB];
 #pragma unroll
-            for (int rr = 0; rr < RB; rr++) {
-                const int x = i - rr;
+        for (int rr = 0; rr < RB; rr++) {
+            const int x = i - rr;
+            m6r[rr] = x > 1 ? m6 : 0.;
+            m8r[rr] = x > 1 ? m8 : 0.;
+            if (rr < R) {
                 const bool live = x >= i_stop && x >= 1;
                 int qc = 0;
                 if (live) {
                     qc = sp_query_decode(in, x, (q4 >> (8 * rr)) & 0xff);  // query[x] (0-based) == base of row x+1
                     if (j + rr > 0) {  // one column enters the band on the left: bit 0 <-> ref[x-BW]
                         const uint32_t rc = (r4 >> (8 * rr)) & 0xff;
-                        a0.shl1_in((uint64_t) (rc & 1));
-                        a1.shl1_in((uint64_t) ((rc >> 1) & 1));
-                        a2.shl1_in((uint64_t) ((rc >> 2) & 1));
+                        p0.shl1_in((uint64_t) (rc & 1));
+                        p1.shl1_in((uint64_t) ((rc >> 1) & 1));
+                        p2.shl1_in((uint64_t) ((rc >> 2) & 1));
                     }
                 }
-                sp_h2_row_masks(a0, a1, a2, qc, mmr[rr], nnr[rr]);
-                ps0[rr] = a0; ps1[rr] = a1; ps2[rr] = a2;
-                int lo, hi;
-                valid_range(x, lo, hi);
-                sp_bits_range(vmr[rr], lo, hi);
-                if (!stop && live && t_next + 1 == x) {  // a consumed row ends the block: the MAP reads it from memory
-                    lane_r = rr + 1;
-                    stop = true;
-                }
+                sp_h2_row_masks(p0, p1, p2, qc, mmr[rr], nnr[rr]);
+                if (live && (narrow || x <= 1 || nnr[rr].any_below(NC))) mask_lane = true;
+            } else {
+                mmr[rr].clear();
+                nnr[rr].clear();
             }
         }
-        const int R = SP_WARP_MIN(lane_r);
-        {
-#pragma unroll
-            for (int rr = 0; rr < RB; rr++)
-                if (rr == R - 1) { p0 = ps0[rr]; p1 = ps1[rr]; p2 = ps2[rr]; }
-        }
         fetch_bwd(i - R);
-        // Cells left of column 1 or right of l_ref need no mask here: with the row above zero outside its valid
-        // cells the right side stays zero by itself, and what appears left of column 1 never flows back into a valid
-        // cell (dependencies only run towards smaller columns) nor into the MAP (f is zero there).  Only an instance
-        // narrower than its warp's band, an N, or row 1 (no D state there) takes the masked pass.
-        bool mask_lane = false;
-        double m6r[RB], m8r[RB];
-#pragma unroll
-        for (int rr = 0; rr < RB; rr++) {
-            const int x = i - rr;
-            if (rr < R && x >= i_stop && x >= 1 && (narrow || x <= 1 || nnr[rr].any_below(NC))) mask_lane = true;
-            m6r[rr] = x > 1 ? m6 : 0.;
-            m8r[rr] = x > 1 ? m8 : 0.;
-        }
         const bool masked = SP_WARP_ANY(mask_lane);
+        SpBits<NW> vmr[RB];
+        if (masked) {
+#pragma unroll
+            for (int rr = 0; rr < RB; rr++) {
+                int lo, hi;
+                valid_range(i - rr, lo, hi);
+                sp_bits_range(vmr[rr], lo, hi);
+            }
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < RB; rr++) vmr[rr].clear();
+        }
         // row a (0-based) computes cell NC-1-s+a at step s; it needs bM of the row above at its own cell
         // (that row's previous step) and bI of the row above one cell to the left (fresh)
         auto pass = [&](auto rtag, auto mtag) {
