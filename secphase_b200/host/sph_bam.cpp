@@ -326,6 +326,31 @@ static bool find_tag(AlnDesc &a) {
     return false;
 }
 
+// BAM stores a CIGAR of more than 65535 operations in the tag CG:B,I and leaves the placeholder <l_seq>S<ref_len>N
+// in the record; htslib's bam_read1, through which the reference reads (secphase.c:268), swaps the real CIGAR back
+// in (bam_tag2cigar).  Same here: the alignment's CIGAR then points at the tag's payload.
+static void restore_long_cigar(AlnDesc &a) {
+    if (a.n_cigar < 1 || a.tid < 0 || a.pos < 0) return;
+    const uint32_t c0 = le32(a.cigar);
+    if ((c0 & 15) != 4 || (int32_t) (c0 >> 4) != a.l_qseq) return;
+    const uint8_t *p = a.aux, *end = a.rec + a.body_len;
+    while (p + 3 <= end) {
+        const uint8_t t0 = p[0], t1 = p[1], type = p[2];
+        p += 3;
+        const size_t sz = aux_size(type, p, end);
+        if (sz == 0 || p + sz > end) return;
+        if (t0 == 'C' && t1 == 'G' && type == 'B' && sz >= 5 && (p[0] == 'I' || p[0] == 'i')) {
+            const uint32_t n = le32(p + 1);
+            if (n > 0 && 5 + 4 * (size_t) n <= sz) {
+                a.cigar = p + 5;
+                a.n_cigar = (int32_t) n;
+            }
+            return;
+        }
+        p += sz;
+    }
+}
+
 // The read name changed or the file ended (secphase.c:279-315).
 int sph_bam::close_group(bool *emitted, GroupDesc *out) {
     *emitted = false;
@@ -339,6 +364,7 @@ int sph_bam::close_group(bool *emitted, GroupDesc *out) {
     if (n > 1 && n <= 10 && supp == 0 && prim == 1) {
         bool ok = true;
         for (AlnDesc &a : open) {
+            restore_long_cigar(a);
             // the marker path is undefined for these in the reference (cigar_it.c:225-291 has no
             // case for N/P; a SEQ that disagrees with the CIGAR indexes out of bounds): skip the group
             int64_t qlen = 0, rlen = 0;
@@ -652,7 +678,7 @@ int sph_bamw_add(sph_bamw *w, const sp_flat_batch *b) {
         for (int32_t a = b->grp_aln_off[g]; a < b->grp_aln_off[g + 1]; a++) {
             v.clear();
             int32_t l_seq = b->l_qseq[a], n_cigar = b->n_cigar[a];
-            const uint32_t *cig = b->cigar_pool + b->cigar_off[a];
+            const uint32_t *cig = b->cigar_pool + b->cigar_off[a];  // (re-pointed at the placeholder for a long CIGAR)
             int64_t rlen = 0;
             for (int i = 0; i < n_cigar; i++) {
                 uint32_t op = cig[i] & 15;
@@ -660,8 +686,18 @@ int sph_bamw_add(sph_bamw *w, const sp_flat_batch *b) {
             }
             size_t tag_len = (size_t) (b->tag_off[a + 1] - b->tag_off[a]);
             int kind = b->tag_kind ? b->tag_kind[a] : 0;
+            // SAM spec 4.2.2: a CIGAR of more than 65535 operations goes into CG:B,I and the record carries the
+            // placeholder <l_seq>S<ref_len>N (SPH_BAM_WRITE_LONG_CIGAR=<n> lowers the limit: tests of the reader)
+            static const int cg_limit = getenv("SPH_BAM_WRITE_LONG_CIGAR") ? atoi(getenv("SPH_BAM_WRITE_LONG_CIGAR")) : 65535;
+            const bool use_cg = n_cigar > cg_limit;
+            const int n_cigar_real = n_cigar;
+            uint32_t fake[2] = {((uint32_t) l_seq << 4) | 4u, ((uint32_t) rlen << 4) | 3u};
+            if (use_cg) {
+                cig = fake;
+                n_cigar = 2;
+            }
             size_t body = 32 + qn_len + 1 + 4 * (size_t) n_cigar + ((size_t) l_seq + 1) / 2 + (size_t) l_seq + 3 +
-                          tag_len + 1;
+                          tag_len + 1 + (use_cg ? 8 + 4 * (size_t) n_cigar_real : 0);
             put32(v, (uint32_t) body);
             put32(v, (uint32_t) b->tid[a]);
             put32(v, (uint32_t) b->pos[a]);
@@ -690,6 +726,12 @@ int sph_bamw_add(sph_bamw *w, const sp_flat_batch *b) {
             const char *tg = b->tag_pool + b->tag_off[a];
             v.insert(v.end(), tg, tg + tag_len);
             v.push_back(0);
+            if (use_cg) {
+                v.push_back('C'); v.push_back('G'); v.push_back('B'); v.push_back('I');
+                put32(v, (uint32_t) n_cigar_real);
+                const uint8_t *rb = (const uint8_t *) (b->cigar_pool + b->cigar_off[a]);
+                v.insert(v.end(), rb, rb + 4 * (size_t) n_cigar_real);
+            }
             int rc = w->w.write(v.data(), v.size());
             if (rc != SPH_OK) return rc;
         }

@@ -12,6 +12,8 @@ from secphase_b200 import hostlib
 from secphase_b200.flatbatch import _FIELDS, FlatBatch
 from tests.conftest import make_case
 
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def assert_same_batch(got, exp):
     for name, _ in _FIELDS:
@@ -208,3 +210,31 @@ def test_fasta_codes(tmp_path):
     open(bad, "wb").write(b"ACGT\n")
     with pytest.raises(hostlib.HostError, match="FASTA"):
         hostlib.load_fasta(bad)
+
+
+def test_long_cigars_in_the_cg_tag_are_restored(tmp_path):
+    """BAM keeps a CIGAR of more than 65535 operations in CG:B,I behind the placeholder <l_seq>S<ref_len>N; htslib's
+    bam_read1 (through which the reference reads, secphase.c:268) swaps it back in.  The writer is told to use that
+    form for every CIGAR longer than 8 operations (SPH_BAM_WRITE_LONG_CIGAR is read once per process: a child
+    process writes), the reader must return the very same batches -- none skipped because of the N operation."""
+    import subprocess, sys, textwrap
+    s, b, _, _ = make_case("ont", 24, locus_len=200000, len_mean=6000, len_sd=1500, len_min=2000)
+    assert int(b.n_cigar.max()) > 100
+    p = str(tmp_path / "cg.bam")
+    child = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r)
+        from secphase_b200 import hostlib
+        from tests.conftest import make_case
+        s, b, _, _ = make_case("ont", 24, locus_len=200000, len_mean=6000, len_sd=1500, len_min=2000)
+        hostlib.write_bam(sys.argv[1], s.names, s.lens, b, level=1, threads=1)
+    """ % ROOT_DIR)
+    r = subprocess.run([sys.executable, "-c", child, p], env=dict(os.environ, SPH_BAM_WRITE_LONG_CIGAR="8"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    plain = str(tmp_path / "plain.bam")
+    hostlib.write_bam(plain, s.names, s.lens, b, level=1, threads=1)
+    assert os.path.getsize(p) != os.path.getsize(plain)   # the CG form really was written
+    got, counts, skipped = read_all(p, max_groups=1 << 20)
+    assert skipped == 0
+    assert_same_batch(FlatBatch.concat(got), b)
