@@ -28,3 +28,41 @@ def test_reference_arm_other_ranks_stay_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_parity_machinery_of_the_bench_matches_a_single_oracle_run():
+    """bench.py checks the GPU at size against a thread-pooled oracle run whose per-chunk tables are concatenated and
+    whose selection is the reference's get_best_record_index replayed in group order: that composite must equal one
+    sequential oracle run (same tables, same selection, ties included), also with filler contigs ahead of the real
+    ones (the configs[3] workload)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import pyoracle
+    from tools.parity import compare_results
+    if "reference" not in pyoracle.available_kinds():
+        pyoracle.build()
+    sp = dict(bench.SPECS["stress"], locus_len=200_000, synth_over=dict(snv_rate=1e-4, indel_rate=2e-5, long_indel_rate=2e-6))
+    wl = bench.Workload(sp)
+    b = wl.generate(0, 40)
+    keep = {}
+    g, cells, dt, kind = bench.cpu_reference_run(wl, [b], "hifi", threads=3, keep=keep)
+    assert g == 40 and cells > 0 and kind == "reference"
+    one = pyoracle.run(b, pyoracle.preset_params("hifi"), wl.oracle_refseq(pyoracle))
+    assert not compare_results(one, keep, label="pooled")
+    sc, gao = one["scores"], b.grp_aln_off
+    ties = sum(1 for gi in range(b.n_groups)
+               if (lambda s: len(s) > 1 and (s == s.max()).sum() > 1)(sc[gao[gi]:gao[gi + 1]][(b.flag[gao[gi]:gao[gi + 1]] & 256) != 0]))
+    assert ties >= 1
+    # filler contigs: same groups, every tid shifted, same tables
+    sp2 = dict(bench.SPECS["hifi"], locus_len=200_000, filler_bp=3_000_000)
+    wl2 = bench.Workload(sp2)
+    assert wl2.tid_shift >= 1 and wl2.off[wl2.tid_shift] == sum(wl2.lens[:wl2.tid_shift]) and len(wl2.codes) == wl2.off[-1]
+    assert (wl2.codes[:wl2.off[wl2.tid_shift]] == 4).all()
+    b2 = wl2.generate(0, 12)
+    plain = bench.Workload(dict(sp2, filler_bp=0))
+    b0 = plain.generate(0, 12)
+    assert np.array_equal(b2.tid, b0.tid + wl2.tid_shift)
+    r2 = pyoracle.run(b2, pyoracle.preset_params("hifi"), wl2.oracle_refseq(pyoracle))
+    r0 = pyoracle.run(b0, pyoracle.preset_params("hifi"), plain.oracle_refseq(pyoracle))
+    assert not compare_results(r0, r2, label="filler")
