@@ -409,6 +409,45 @@ int main(int argc, char *argv[]) {
         sph_bam_set_contig_limits(bam, lim.data());
     }
 
+    // one context per device (there is no CPU path: sp_create fails without a GPU).  SECPHASE_B200_DEVICES
+    // ("0,0", "2,3", ...) maps context k to a CUDA device: lets --gpus N be exercised on fewer physical GPUs
+    // (two contexts on one device behave exactly like two devices to everything above the C ABI).
+    std::vector<int> dev_of((size_t) n_gpus);
+    for (int d = 0; d < n_gpus; d++) dev_of[(size_t) d] = d;
+    if (const char *e = getenv("SECPHASE_B200_DEVICES")) {
+        int k = 0;
+        for (const char *q = e; *q && k < n_gpus;) {
+            dev_of[(size_t) k++] = atoi(q);
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+    }
+    // test hook: SECPHASE_B200_FAIL_AT="<ctx>,<n>" makes GPU thread <ctx> report a failure instead of
+    // submitting its n-th batch (the error path of a multi-device run must end with exit code 1, not hang)
+    int fail_ctx = -1, fail_at = -1;
+    if (const char *e = getenv("SECPHASE_B200_FAIL_AT")) sscanf(e, "%d,%d", &fail_ctx, &fail_at);
+    std::vector<sp_ctx *> ctx((size_t) n_gpus, nullptr);
+    for (int d = 0; d < n_gpus; d++) {
+        ctx[(size_t) d] = sp_create(&par, dev_of[(size_t) d]);
+        if (!ctx[(size_t) d]) {
+            fprintf(stderr, "[%s] Error: cannot initialise GPU %d: %s\n", get_timestamp(), d, sp_last_error());
+            return 1;
+        }
+        if (sp_set_reference_codes(ctx[(size_t) d], n_tid, codes, contig_off.data()) != SP_OK) {
+            fprintf(stderr, "[%s] Error: cannot load the assembly on GPU %d: %s\n", get_timestamp(), d, sp_last_error());
+            return 1;
+        }
+        if (write_bam && sp_set_write_qual(ctx[(size_t) d], 1) != SP_OK) {
+            fprintf(stderr, "[%s] Error: GPU %d: %s\n", get_timestamp(), d, sp_last_error());
+            return 1;
+        }
+    }
+    if (fa) sph_fasta_free(fa);
+    fa = nullptr;
+    codes_tid.clear();
+    codes_tid.shrink_to_fit();
+    auto t_ready = std::chrono::steady_clock::now();
+
     sph_blocks *modified_blocks_by_vars = sph_blocks_create(1);
     sph_blocks *modified_blocks_by_marker = sph_blocks_create(1);
     sph_blocks *variant_blocks_all_haps = sph_blocks_create(0);
@@ -465,49 +504,6 @@ int main(int argc, char *argv[]) {
         }
         work_q.close();
     });
-
-    // one context per device (there is no CPU path: sp_create fails without a GPU).  SECPHASE_B200_DEVICES
-    // ("0,0", "2,3", ...) maps context k to a CUDA device: lets --gpus N be exercised on fewer physical GPUs
-    // (two contexts on one device behave exactly like two devices to everything above the C ABI).
-    std::vector<int> dev_of((size_t) n_gpus);
-    for (int d = 0; d < n_gpus; d++) dev_of[(size_t) d] = d;
-    if (const char *e = getenv("SECPHASE_B200_DEVICES")) {
-        int k = 0;
-        for (const char *q = e; *q && k < n_gpus;) {
-            dev_of[(size_t) k++] = atoi(q);
-            while (*q && *q != ',') q++;
-            if (*q == ',') q++;
-        }
-    }
-    // test hook: SECPHASE_B200_FAIL_AT="<ctx>,<n>" makes GPU thread <ctx> report a failure instead of
-    // submitting its n-th batch (the error path of a multi-device run must end with exit code 1, not hang)
-    int fail_ctx = -1, fail_at = -1;
-    if (const char *e = getenv("SECPHASE_B200_FAIL_AT")) sscanf(e, "%d,%d", &fail_ctx, &fail_at);
-    // (the reader thread is already decoding the BAM into the first batches while the contexts come up)
-    std::vector<sp_ctx *> ctx((size_t) n_gpus, nullptr);
-    {
-        std::string gpu_err;
-        for (int d = 0; d < n_gpus && gpu_err.empty(); d++) {
-            ctx[(size_t) d] = sp_create(&par, dev_of[(size_t) d]);
-            if (!ctx[(size_t) d])
-                gpu_err = "cannot initialise GPU " + std::to_string(d) + ": " + sp_last_error();
-            else if (sp_set_reference_codes(ctx[(size_t) d], n_tid, codes, contig_off.data()) != SP_OK)
-                gpu_err = "cannot load the assembly on GPU " + std::to_string(d) + ": " + sp_last_error();
-            else if (write_bam && sp_set_write_qual(ctx[(size_t) d], 1) != SP_OK)
-                gpu_err = "GPU " + std::to_string(d) + ": " + sp_last_error();
-        }
-        if (!gpu_err.empty()) {
-            shared.fail(gpu_err);  // closes the queues: the reader winds down
-            reader.join();
-            fprintf(stderr, "[%s] Error: %s\n", get_timestamp(), gpu_err.c_str());
-            return 1;
-        }
-    }
-    if (fa) sph_fasta_free(fa);
-    fa = nullptr;
-    codes_tid.clear();
-    codes_tid.shrink_to_fit();
-    auto t_ready = std::chrono::steady_clock::now();
 
     std::vector<std::thread> gpu_threads;
     std::mutex gpu_exit_mu;

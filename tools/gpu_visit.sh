@@ -69,6 +69,10 @@ ontsize)  # ONT stage times vs batch size (thread-per-alignment integer stages w
     timeout 300 python tools/stage_bench.py --preset ont --groups $g --locus-len 5000000 >> $out/${tag}_ontsize.json 2>> $out/${tag}_ontsize.err
   done
   cut -c1-330 $out/${tag}_ontsize.json ;;
+ontlaunch)  # per-class HMM launch times of one ONT batch
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_hmm --csv --log-file $out/${tag}_ont_hmm_launches.csv \
+    python tools/stage_bench.py --preset ont --groups 10240 --locus-len 5000000 --iters 1 > $out/${tag}_ont_l.log 2>&1
+  tail -c 400 $out/${tag}_ont_l.log ;;
 cli)
   ( timeout 500 python tools/cli_bench.py --groups 32768 ) > $out/${tag}_cli.json 2> $out/${tag}_cli.err
   tail -c 1200 $out/${tag}_cli.json ;;
