@@ -109,8 +109,7 @@ struct Slot {
     size_t off_gblk_cap = 0, off_gblk_off = 0, off_giv_off = 0;  // plan-derived sections inside h_in / d_in
     // device work tables
     DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, item_off, row_off, sdbl_off, score,
-        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out, set_base,
-        rerun_list;
+        fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out, set_base;
     // host results
     PinBuf h_tot, h_gout, h_score, h_info, h_fin, h_qual, h_rerun;
     const uint8_t *qual_zero_copy = nullptr;  // device view of the caller's page-locked quality pool, when it is read in place
@@ -441,7 +440,7 @@ void sp_destroy(sp_ctx *c) {
         DevBuf *bufs[] = {&S.d_in, &S.ops, &S.imk, &S.info, &S.blk, &S.iv, &S.nb, &S.gpos, &S.ent, &S.res, &S.baq,
                           &S.gP, &S.gout, &S.gcnt, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
                           &S.fin, &S.items, &S.rows, &S.order, &S.bins, &S.class_start, &S.s_pool, &S.fsave,
-                          &S.gband, &S.totals, &S.work_counter, &S.qual_out, &S.set_base, &S.rerun_list};
+                          &S.gband, &S.totals, &S.work_counter, &S.qual_out, &S.set_base};
         for (DevBuf *b : bufs) b->release();
         PinBuf *pins[] = {&S.h_in, &S.h_tot, &S.h_gout, &S.h_score, &S.h_info, &S.h_fin, &S.h_qual, &S.h_rerun};
         for (PinBuf *b : pins) b->release();
@@ -928,7 +927,6 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
     if ((rc = S.order.ensure(4 * (size_t) (T.n_items + 1)))) return rc;
     if ((rc = S.s_pool.ensure(8 * (size_t) (T.s_doubles + 2)))) return rc;
     const bool fast = c->hmm_mode == 1 && !S.full_baq;
-    if ((rc = S.rerun_list.ensure(4 * (size_t) (T.n_items + 1)))) return rc;
     // doubles per saved forward row: the widest band of the batch -- or, wider still, the cells of the fast
     // kernel's class that band falls in (its virtual band always has the class's full width)
     int64_t fs_cells = 2 * (int64_t) T.max_bw + 1;
@@ -1541,7 +1539,6 @@ int sp_hmm_batch(sp_ctx *c, int32_t n, const uint8_t *ref_pool, const int64_t *r
     if ((rc = S.order.ensure(4 * (size_t) n))) return rc;
     if ((rc = S.s_pool.ensure(8 * (size_t) (s_total + 2)))) return rc;
     const bool fast = c->hmm_mode == 1;
-    if ((rc = S.rerun_list.ensure(4 * (size_t) (n + 1)))) return rc;
     int64_t fs_cells = 2 * (int64_t) max_bw + 1;
     if (fast && sp_hmmf_class_cells(sp_band_class(max_bw)) > fs_cells) fs_cells = sp_hmmf_class_cells(sp_band_class(max_bw));
     const int64_t fs_stride = 2 * fs_cells;
