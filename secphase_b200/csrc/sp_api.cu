@@ -108,7 +108,7 @@ struct Slot {
     bool safe_caps = false;
     size_t off_gblk_cap = 0, off_gblk_off = 0, off_giv_off = 0;  // plan-derived sections inside h_in / d_in
     // device work tables
-    DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, item_off, row_off, sdbl_off, score,
+    DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, acnt, item_off, row_off, sdbl_off, score,
         fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out, set_base;
     // host results
     PinBuf h_tot, h_gout, h_score, h_info, h_fin, h_qual, h_rerun;
@@ -438,7 +438,7 @@ void sp_destroy(sp_ctx *c) {
     for (int s = 0; s < SP_N_SLOTS; s++) {
         Slot &S = c->slot[s];
         DevBuf *bufs[] = {&S.d_in, &S.ops, &S.imk, &S.info, &S.blk, &S.iv, &S.nb, &S.gpos, &S.ent, &S.res, &S.baq,
-                          &S.gP, &S.gout, &S.gcnt, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
+                          &S.gP, &S.gout, &S.gcnt, &S.acnt, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
                           &S.fin, &S.items, &S.rows, &S.order, &S.bins, &S.class_start, &S.s_pool, &S.fsave,
                           &S.gband, &S.totals, &S.work_counter, &S.qual_out, &S.set_base};
         for (DevBuf *b : bufs) b->release();
@@ -675,6 +675,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b, bool zero_cop
     if ((rc = S.gP.ensure(4 * (G + 1)))) return rc;
     if ((rc = S.gout.ensure(sizeof(SpGroupOut) * (G + 1)))) return rc;
     if ((rc = S.gcnt.ensure(sizeof(SpEmitCounts) * (G + 1)))) return rc;
+    if ((rc = S.acnt.ensure(sizeof(SpEmitCounts) * (A + 1)))) return rc;
     if ((rc = S.item_off.ensure(4 * (G + 2)))) return rc;
     if ((rc = S.row_off.ensure(4 * (G + 2)))) return rc;
     if ((rc = S.sdbl_off.ensure(8 * (G + 2)))) return rc;
@@ -709,7 +710,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b, bool zero_cop
     P.ops = S.ops.as<SpOp>(); P.imk = S.imk.as<SpInitMarker>(); P.info = S.info.as<SpAlnInfo>();
     P.blk = S.blk.as<SpBlock>(); P.iv = S.iv.as<SpIv>(); P.nb = S.nb.as<int32_t>(); P.gpos = S.gpos.as<int32_t>();
     P.ent = S.ent.as<SpEntry>(); P.res = S.res.as<int32_t>(); P.baq = dbg ? S.baq.as<int32_t>() : nullptr;
-    P.gP = S.gP.as<int32_t>(); P.gout = S.gout.as<SpGroupOut>(); P.gcnt = S.gcnt.as<SpEmitCounts>();
+    P.gP = S.gP.as<int32_t>(); P.gout = S.gout.as<SpGroupOut>(); P.gcnt = S.gcnt.as<SpEmitCounts>(); P.acnt = S.acnt.as<SpEmitCounts>();
     P.item_off = S.item_off.as<int32_t>(); P.row_off = S.row_off.as<int32_t>(); P.sdbl_off = S.sdbl_off.as<int64_t>();
     P.score = S.score.as<double>(); P.fin_wide = S.fin_wide.as<int32_t>(); P.fin = S.fin.as<int32_t>();
     P.ref = c->ref.as<uint8_t>(); P.contig_off = c->contig_off.as<int64_t>(); P.n_contigs = c->n_contigs;
@@ -901,7 +902,9 @@ static int run_phase_a(sp_ctx *c, Slot &S) {
     CK(cudaEventRecord(S.ev[EV_WALK], st));
     if (P.G > 0) {
         k_group<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC);
-        S.launches++;
+        k_count<<<(P.A + 127) / 128, 128, 0, st>>>(P, dC);
+        k_group_counts<<<(P.G + 127) / 128, 128, 0, st>>>(P);
+        S.launches += 3;
     }
     k_scan_groups<<<1, 1024, 0, st>>>(P, S.totals.as<SpTotals>());
     S.launches++;
@@ -948,7 +951,7 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
         return rc;
     }
     if (P.G > 0 && T.n_items > 0) {
-        k_emit<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC, S.items.as<SpItem>(), S.rows.as<SpRow>());
+        k_emit<<<(P.A + 127) / 128, 128, 0, st>>>(P, dC, S.items.as<SpItem>(), S.rows.as<SpRow>());
         if (S.full_baq) {  // -w: k_emit laid out the windows only; their per-base rows are filled in parallel
             k_fill_rows<<<(T.n_items * 32 + 255) / 256, 256, 0, st>>>(P, S.items.as<SpItem>(), T.n_items, S.rows.as<SpRow>());
             S.launches++;

@@ -56,6 +56,7 @@ struct SpBatchPtrs {
     int32_t *gP;
     SpGroupOut *gout;
     SpEmitCounts *gcnt;
+    SpEmitCounts *acnt;  // per alignment: what its HMM windows add to the group's counts (k_count)
     int32_t *item_off, *row_off;
     int64_t *sdbl_off;
     double *score;
@@ -143,26 +144,55 @@ __global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__re
     if (P > 0) {
         conf_len = sp_consensus_loop(C, V, P, gpos, W, &margin, &err);
         SP_PROF(1);
-        if (conf_len > 0 || !C.consensus) {
-            scored = true;
-            if (C.baq_flag) {
-                for (int i = 0; i < V.n; i++) {
-                    const int a = V.a0 + i;
-                    sp_emit_alignment<false>(C, V, i, P, ent, W.ab + (int64_t) i * W.cap, W.nb[i],
-                                             B.contig_off[B.tid[a]], 0, cnt, nullptr, nullptr, 0, nullptr, 0, 0);
-                }
-            }
-        }
+        if (conf_len > 0 || !C.consensus) scored = true;  // (the HMM windows are counted per alignment, k_count)
     } else {
         for (int i = 0; i < V.n; i++) W.nb[i] = 0;  // secphase.c:161: no markers, no confident blocks
     }
     SP_PROF(2);
-    B.gcnt[g] = cnt;
+    (void) cnt;
     o.margin_eff = margin;
     o.conf_len = conf_len;
     o.scored = scored ? 1 : 0;
     o.err = err;
     B.gout[g] = o;
+}
+
+// K3b count pass, thread per ALIGNMENT: the HMM windows calc_local_baq would run for this alignment (ptMarker.c:
+// 670-809) -- how many instances / rows / band cells they are.  Alignments of a group are independent here, so the
+// lay-out walk of a group's windows is spread over as many threads as it has alignments (up to ten in the
+// many-secondaries case) instead of running them one after the other in the group's thread.
+__global__ void __launch_bounds__(128) k_count(SpBatchPtrs B, const SpConst *__restrict__ Cp) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= B.A) return;
+    const SpConst &C = *Cp;
+    const int g = B.aln_grp[a];
+    SpEmitCounts cnt;
+    memset(&cnt, 0, sizeof(cnt));
+    if (B.gout[g].scored && C.baq_flag) {
+        SpGroupAlnView V = sp_make_view(B, g);
+        const int i = a - V.a0, cap = B.gblk_cap[g];
+        sp_emit_alignment<false>(C, V, i, B.gP[g], B.ent + B.gent_off[g], B.blk + B.gblk_off[g] + (int64_t) i * cap, B.nb[a],
+                                 B.contig_off[B.tid[a]], 0, cnt, nullptr, nullptr, 0, nullptr, 0, 0);
+    }
+    B.acnt[a] = cnt;
+}
+// per group: the sum over its alignments
+__global__ void __launch_bounds__(128) k_group_counts(SpBatchPtrs B) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B.G) return;
+    SpEmitCounts s;
+    memset(&s, 0, sizeof(s));
+    for (int a = B.grp_aln_off[g]; a < B.grp_aln_off[g + 1]; a++) {
+        const SpEmitCounts c = B.acnt[a];
+        s.n_items += c.n_items;
+        s.n_rows += c.n_rows;
+        s.cells += c.cells;
+        s.s_doubles += c.s_doubles;
+        s.max_bw = max(s.max_bw, c.max_bw);
+        s.max_lq = max(s.max_lq, c.max_lq);
+        for (int k = 0; k < SP_N_CLASSES; k++) { s.class_count[k] += c.class_count[k]; s.class_rows[k] += c.class_rows[k]; }
+    }
+    B.gcnt[g] = s;
 }
 
 // exclusive scans over groups (one CTA of 1024 threads); also accumulates the batch totals
@@ -238,23 +268,28 @@ __global__ void __launch_bounds__(1024) k_scan_groups(SpBatchPtrs B, SpTotals *t
     }
 }
 
-__global__ void __launch_bounds__(64) k_emit(SpBatchPtrs B, const SpConst *__restrict__ Cp, SpItem *items, SpRow *rows) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= B.G) return;
+// K3b emit pass, thread per alignment: places the alignment's instances and rows behind those of the alignments
+// before it in the group (the order the reference runs them, calc_update_baq_all ptMarker.c:811-831)
+__global__ void __launch_bounds__(128) k_emit(SpBatchPtrs B, const SpConst *__restrict__ Cp, SpItem *items, SpRow *rows) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= B.A) return;
     const SpConst &C = *Cp;
-    const SpGroupOut o = B.gout[g];
-    if (!o.scored || !C.baq_flag) return;
+    const int g = B.aln_grp[a];
+    if (!B.gout[g].scored || !C.baq_flag) return;
     SP_PROF_T0();
     SpGroupAlnView V = sp_make_view(B, g);
+    const int i = a - V.a0, cap = B.gblk_cap[g];
     SpEmitCounts cnt;
     memset(&cnt, 0, sizeof(cnt));
-    const int cap = B.gblk_cap[g];
-    for (int i = 0; i < V.n; i++) {
-        const int a = V.a0 + i;
-        sp_emit_alignment<true>(C, V, i, B.gP[g], B.ent + B.gent_off[g], B.blk + B.gblk_off[g] + (int64_t) i * cap,
-                                B.nb[a], B.contig_off[B.tid[a]], 0, cnt, B.res + B.gent_off[g], items,
-                                B.item_off[g], rows, B.row_off[g], B.sdbl_off[g]);
+    for (int k = V.a0; k < a; k++) {  // what the alignments before this one placed
+        const SpEmitCounts c = B.acnt[k];
+        cnt.n_items += c.n_items;
+        cnt.n_rows += c.n_rows;
+        cnt.s_doubles += c.s_doubles;
     }
+    sp_emit_alignment<true>(C, V, i, B.gP[g], B.ent + B.gent_off[g], B.blk + B.gblk_off[g] + (int64_t) i * cap, B.nb[a],
+                            B.contig_off[B.tid[a]], 0, cnt, B.res + B.gent_off[g], items, B.item_off[g], rows,
+                            B.row_off[g], B.sdbl_off[g]);
     SP_PROF(3);
 }
 
