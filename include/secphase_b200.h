@@ -190,7 +190,9 @@ int sp_run_resident(sp_ctx *ctx, int slot);
  * Test switches (rows/off ignored): what = -1 keeps the post-BAQ table of later batches; what = -2 returns
  * how many batches were re-run with the provable table bounds so far (SP_ECAPACITY is only reported when
  * that second run overflows too); what <= -100 clamps the FIRST plan's per-group block workspace to
- * -(what+100) entries so that tests can force that retry. */
+ * -(what+100) entries so that tests can force that retry; what = -3 returns how many alignments of the slot's
+ * last batch the warp-cooperative CIGAR/cs walker left to the serial walker (MD tags, cs text that is not the
+ * run structure of the CIGAR; -1 when SECPHASE_B200_WALK=serial made the serial walker the only one). */
 int64_t sp_debug_table(sp_ctx *ctx, int slot, int what, const int32_t **rows, const int64_t **off);
 
 /* --- the HMM alone, batch form of probaln_glocal(ref,l_ref,query,l_query,iqual,&conf,state,q)

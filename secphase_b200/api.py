@@ -310,6 +310,11 @@ class Secphase:
     def cap_retries(self):
         return int(self._L.sp_debug_table(self._h, 0, -2, None, None))
 
+    def walk_fallbacks(self, slot=0):
+        """Alignments of the slot's last batch that the warp-cooperative walker handed to the serial one
+        (-1 when SECPHASE_B200_WALK=serial selected the serial walker for everything)."""
+        return int(self._L.sp_debug_table(self._h, slot, -3, None, None))
+
     def debug_table(self, what, slot=0):
         rows = C.POINTER(C.c_int32)()
         off = C.POINTER(C.c_int64)()

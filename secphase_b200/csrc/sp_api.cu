@@ -108,7 +108,7 @@ struct Slot {
     bool safe_caps = false;
     size_t off_gblk_cap = 0, off_gblk_off = 0, off_giv_off = 0;  // plan-derived sections inside h_in / d_in
     // device work tables
-    DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, acnt, item_off, row_off, sdbl_off, score,
+    DevBuf ops, imk, info, blk, iv, nb, gpos, ent, res, baq, gP, gout, gcnt, acnt, walk_fb, item_off, row_off, sdbl_off, score,
         fin_wide, fin, items, rows, order, bins, class_start, s_pool, fsave, gband, totals, work_counter, qual_out, set_base;
     // host results
     PinBuf h_tot, h_gout, h_score, h_info, h_fin, h_qual, h_rerun;
@@ -138,6 +138,10 @@ struct Slot {
     std::vector<double> r_score;
 };
 
+#ifndef SP_WALK_WARP_MIN_OPS
+#define SP_WALK_WARP_MIN_OPS 600  // planned op-table size from which an alignment gets a warp of its own (k_walk_warp)
+#endif
+
 struct sp_ctx {
     int device = 0;
     sp_params par;
@@ -153,6 +157,8 @@ struct sp_ctx {
     int test_block_cap = 0;  // tests: first plan clamps every group's block workspace to this (forces the retry)
     int64_t cap_retries = 0;
     bool full_baq = false;  // sp_set_write_qual: --writeBam mode
+    bool walk_serial = false; // SECPHASE_B200_WALK=serial: thread-per-alignment walker only
+    int walk_min_ops = SP_WALK_WARP_MIN_OPS;  // SECPHASE_B200_WALK=warp: 0 (every cs alignment gets a warp)
     bool hmm_merge = false; // SECPHASE_B200_HMM_MERGE=1: one fast launch for all classes (best pipelined, longest single-batch tail)
     int hmm_mode = 1;       // sp_set_hmm_mode: 0 strict (the reference's rounding order), 1 fast + guard band + strict re-run
     bool streams_ready = false;  // ensure_streams
@@ -390,6 +396,11 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
     SP_ATTRF(41); SP_ATTRF(43); SP_ATTRF(45); SP_ATTRF(55); SP_ATTRF(73); SP_ATTRF(97); SP_ATTRF(125);
 #undef SP_ATTRF
     if (const char *e = getenv("SECPHASE_B200_HMM")) c->hmm_mode = strcmp(e, "strict") == 0 ? 0 : 1;
+    if (const char *e = getenv("SECPHASE_B200_WALK")) {
+        c->walk_serial = strcmp(e, "serial") == 0;
+        if (strcmp(e, "warp") == 0) c->walk_min_ops = 0;
+        else if (atoi(e) > 0) c->walk_min_ops = atoi(e);
+    }
     if (const char *e = getenv("SECPHASE_B200_HMM_MERGE")) c->hmm_merge = atoi(e) != 0;
     if (!attr_ok) {
         set_err("sp_create: cudaFuncSetAttribute(k_hmm) failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -438,7 +449,7 @@ void sp_destroy(sp_ctx *c) {
     for (int s = 0; s < SP_N_SLOTS; s++) {
         Slot &S = c->slot[s];
         DevBuf *bufs[] = {&S.d_in, &S.ops, &S.imk, &S.info, &S.blk, &S.iv, &S.nb, &S.gpos, &S.ent, &S.res, &S.baq,
-                          &S.gP, &S.gout, &S.gcnt, &S.acnt, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
+                          &S.gP, &S.gout, &S.gcnt, &S.acnt, &S.walk_fb, &S.item_off, &S.row_off, &S.sdbl_off, &S.score, &S.fin_wide,
                           &S.fin, &S.items, &S.rows, &S.order, &S.bins, &S.class_start, &S.s_pool, &S.fsave,
                           &S.gband, &S.totals, &S.work_counter, &S.qual_out, &S.set_base};
         for (DevBuf *b : bufs) b->release();
@@ -676,6 +687,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b, bool zero_cop
     if ((rc = S.gout.ensure(sizeof(SpGroupOut) * (G + 1)))) return rc;
     if ((rc = S.gcnt.ensure(sizeof(SpEmitCounts) * (G + 1)))) return rc;
     if ((rc = S.acnt.ensure(sizeof(SpEmitCounts) * (A + 1)))) return rc;
+    if ((rc = S.walk_fb.ensure(4 * (A + 2)))) return rc;
     if ((rc = S.item_off.ensure(4 * (G + 2)))) return rc;
     if ((rc = S.row_off.ensure(4 * (G + 2)))) return rc;
     if ((rc = S.sdbl_off.ensure(8 * (G + 2)))) return rc;
@@ -710,7 +722,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b, bool zero_cop
     P.ops = S.ops.as<SpOp>(); P.imk = S.imk.as<SpInitMarker>(); P.info = S.info.as<SpAlnInfo>();
     P.blk = S.blk.as<SpBlock>(); P.iv = S.iv.as<SpIv>(); P.nb = S.nb.as<int32_t>(); P.gpos = S.gpos.as<int32_t>();
     P.ent = S.ent.as<SpEntry>(); P.res = S.res.as<int32_t>(); P.baq = dbg ? S.baq.as<int32_t>() : nullptr;
-    P.gP = S.gP.as<int32_t>(); P.gout = S.gout.as<SpGroupOut>(); P.gcnt = S.gcnt.as<SpEmitCounts>(); P.acnt = S.acnt.as<SpEmitCounts>();
+    P.gP = S.gP.as<int32_t>(); P.gout = S.gout.as<SpGroupOut>(); P.gcnt = S.gcnt.as<SpEmitCounts>(); P.acnt = S.acnt.as<SpEmitCounts>(); P.walk_fb = S.walk_fb.as<int32_t>();
     P.item_off = S.item_off.as<int32_t>(); P.row_off = S.row_off.as<int32_t>(); P.sdbl_off = S.sdbl_off.as<int64_t>();
     P.score = S.score.as<double>(); P.fin_wide = S.fin_wide.as<int32_t>(); P.fin = S.fin.as<int32_t>();
     P.ref = c->ref.as<uint8_t>(); P.contig_off = c->contig_off.as<int64_t>(); P.n_contigs = c->n_contigs;
@@ -896,8 +908,15 @@ static int run_phase_a(sp_ctx *c, Slot &S) {
     CK(cudaMemsetAsync(S.totals.p, 0, sizeof(SpTotals), st));
     CK(cudaMemsetAsync(S.res.p, 0xff, 4 * (size_t) (S.plan.total_ent + 1), st));  // SP_RES_RAW == -1
     if (P.A > 0) {
-        k_walk<<<(P.A + 127) / 128, 128, 0, st>>>(P, dC);
-        S.launches++;
+        if (c->walk_serial) {
+            k_walk<<<(P.A + 127) / 128, 128, 0, st>>>(P, dC);
+            S.launches++;
+        } else {
+            CK(cudaMemsetAsync(S.walk_fb.p, 0, 4, st));
+            k_walk_warp<<<(P.A + 3) / 4, 128, 0, st>>>(P, dC, c->walk_min_ops);
+            k_walk_list<<<(P.A + 127) / 128, 128, 0, st>>>(P, dC);
+            S.launches += 2;
+        }
     }
     CK(cudaEventRecord(S.ev[EV_WALK], st));
     if (P.G > 0) {
@@ -1379,6 +1398,15 @@ int64_t sp_debug_table(sp_ctx *c, int slot, int what, const int32_t **rows_out, 
         return 0;
     }
     if (what == -2) return c->cap_retries;  // batches re-run with the provable bounds so far
+    if (what == -3) {  // alignments of the slot's last batch the warp walker left to the serial one (-1: serial mode)
+        if (c->walk_serial) return -1;
+        if (!c->slot[slot].walk_fb.p) return 0;
+        int32_t n = 0;
+        if (cudaSetDevice(c->device) != cudaSuccess ||
+            cudaMemcpy(&n, c->slot[slot].walk_fb.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return SP_ECUDA;
+        return n;
+    }
     if (!rows_out) return SP_EINVAL;
     if (cudaSetDevice(c->device) != cudaSuccess) return SP_ECUDA;
     Slot &S = c->slot[slot];

@@ -19,6 +19,7 @@
 #include "sp_markers.cuh"
 #include "sp_score.cuh"
 #include "sp_walk.cuh"
+#include "sp_walk_warp.cuh"
 
 #define SP_SORT_LBINS 2048
 
@@ -57,6 +58,7 @@ struct SpBatchPtrs {
     SpGroupOut *gout;
     SpEmitCounts *gcnt;
     SpEmitCounts *acnt;  // per alignment: what its HMM windows add to the group's counts (k_count)
+    int32_t *walk_fb;    // [0] count, [1..] alignments the warp walker left to the serial one (k_walk_warp -> k_walk_list)
     int32_t *item_off, *row_off;
     int64_t *sdbl_off;
     double *score;
@@ -84,9 +86,7 @@ __device__ __forceinline__ SpGroupAlnView sp_make_view(const SpBatchPtrs &B, int
     return V;
 }
 
-__global__ void __launch_bounds__(128) k_walk(SpBatchPtrs B, const SpConst *__restrict__ Cp) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= B.A) return;
+__device__ __forceinline__ void sp_walk_one(const SpBatchPtrs &B, const SpConst *__restrict__ Cp, int a) {
     const int g = B.aln_grp[a];
     const int i = a - B.grp_aln_off[g];
     const int cap = B.gblk_cap[g];
@@ -99,6 +99,47 @@ __global__ void __launch_bounds__(128) k_walk(SpBatchPtrs B, const SpConst *__re
                       (int) (B.imk_off[a + 1] - B.imk_off[a]), cb, cap, &info);
     B.info[a] = info;
     B.nb[a] = info.n_cb;
+}
+
+// thread per alignment: the serial walker (SECPHASE_B200_WALK=serial, and the specification of the warp walker)
+__global__ void __launch_bounds__(128) k_walk(SpBatchPtrs B, const SpConst *__restrict__ Cp) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= B.A) return;
+    sp_walk_one(B, Cp, a);
+}
+
+// warp per alignment (sp_walk_warp.cuh); what it declines (MD tags, text that is not what an aligner writes for
+// this CIGAR) is listed for k_walk_list
+// min_ops: alignments whose op table is planned smaller than this go to the list at once -- with a few tokens per
+// 32 bytes of text and a hundred-odd tokens in all (HiFi) the serial walker executes fewer warp instructions per
+// alignment (32 alignments a warp) than a warp that scans every byte; with thousands of tokens (ONT) it is the
+// other way round by a factor of three to four.
+__global__ void __launch_bounds__(128) k_walk_warp(SpBatchPtrs B, const SpConst *__restrict__ Cp, int min_ops) {
+    const int a = (int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (a >= B.A) return;
+    if ((int) (B.ops_off[a + 1] - B.ops_off[a] - 1) < min_ops) {
+        if ((threadIdx.x & 31) == 0) B.walk_fb[1 + atomicAdd(B.walk_fb, 1)] = a;
+        return;
+    }
+    const int g = B.aln_grp[a];
+    const int i = a - B.grp_aln_off[g];
+    const int cap = B.gblk_cap[g];
+    SpBlock *cb = B.blk + B.gblk_off[g] + (int64_t) i * cap;
+    const bool ok = sp_walk_alignment_warp(Cp->indel_threshold, Cp->min_q, B.flag[a], B.pos[a], B.l_qseq[a], B.n_cigar[a],
+                                           B.cigar_pool + B.cigar_off[a], B.tag_pool, B.tag_off[a], B.tag_off[a + 1],
+                                           B.tag_kind[a], B.qual_pool + B.qual_off[a], B.ops + B.ops_off[a],
+                                           (int) (B.ops_off[a + 1] - B.ops_off[a] - 1), B.imk + B.imk_off[a],
+                                           (int) (B.imk_off[a + 1] - B.imk_off[a]), cb, cap, &B.info[a]);
+    if ((threadIdx.x & 31) == 0) {
+        if (ok) B.nb[a] = B.info[a].n_cb;
+        else B.walk_fb[1 + atomicAdd(B.walk_fb, 1)] = a;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_walk_list(SpBatchPtrs B, const SpConst *__restrict__ Cp) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B.walk_fb[0]) return;
+    sp_walk_one(B, Cp, B.walk_fb[1 + t]);
 }
 
 #ifdef SP_PROFILE_GROUP  // tuning aid: clock64 split of the thread-per-group stages (summed over threads)

@@ -23,6 +23,9 @@
 #include "../../secphase_b200/csrc/sp_plan.h"
 #include "../../secphase_b200/csrc/sp_score.cuh"
 #include "../../secphase_b200/csrc/sp_walk.cuh"
+#define SP_WARP_EMU 1
+#include "warp_emu.h"
+#include "../../secphase_b200/csrc/sp_walk_warp.cuh"
 
 struct HsOut {
     std::vector<int32_t> group;   // [G][SP_GROUP_W]
@@ -275,6 +278,59 @@ int hs_walk_stats(const sp_flat_batch *b, const sp_params *p, int32_t *out /* [A
                           mcap, cb.data(), pl.cb_cap[a], &info);
         out[a * 5 + 0] = info.n_ops; out[a * 5 + 1] = ocap; out[a * 5 + 2] = info.n_imk; out[a * 5 + 3] = mcap;
         out[a * 5 + 4] = info.err;
+    }
+    return 0;
+}
+
+// The warp-cooperative walker (sp_walk_warp.cuh, run on warp_emu.h's 32 coroutine lanes) against the serial walker
+// for every alignment of a batch.  out[0] alignments, out[1] handled by the warp walker (the others fell back),
+// out[2] alignments whose tables differ, out[3] the first of them (-1 none), out[4] what differed there
+// (1 ops, 2 markers, 4 blocks, 8 scalars).
+int hs_walk_warp_check(const sp_flat_batch *b, const sp_params *p, int64_t *out) {
+    SpConst C;
+    sp_fill_const(*p, C);
+    SpPlan pl;
+    int rc = sp_make_plan(b, p->indel_threshold, false, pl);
+    if (rc != SP_OK) return rc;
+    const int64_t tag_bytes = b->tag_off[pl.A];
+    std::vector<uint8_t> tagbuf((size_t) tag_bytes + 64, 0);
+    uint8_t *tag_pool = tagbuf.data();
+    while (((uintptr_t) tag_pool) & 15) tag_pool++;
+    memcpy(tag_pool, b->tag_pool, (size_t) tag_bytes);
+    out[0] = pl.A; out[1] = 0; out[2] = 0; out[3] = -1; out[4] = 0;
+    for (int a = 0; a < pl.A; a++) {
+        const int ocap = (int) (pl.ops_off[a + 1] - pl.ops_off[a] - 1), mcap = (int) (pl.imk_off[a + 1] - pl.imk_off[a]);
+        const int ccap = pl.cb_cap[a];
+        std::vector<SpOp> ops((size_t) ocap + 1), ops2((size_t) ocap + 1);
+        std::vector<SpInitMarker> imk((size_t) mcap + 1), imk2((size_t) mcap + 1);
+        std::vector<SpBlock> cb((size_t) ccap + 1), cb2((size_t) ccap + 1);
+        SpAlnInfo info, info2;
+        memset(&info, 0, sizeof info); memset(&info2, 0, sizeof info2);
+        const int tk = b->tag_kind ? b->tag_kind[a] : 0;
+        sp_walk_alignment(C.indel_threshold, C.min_q, b->flag[a], b->pos[a], b->l_qseq[a], b->n_cigar[a],
+                          b->cigar_pool + b->cigar_off[a], tag_pool, b->tag_off[a], b->tag_off[a + 1], tk,
+                          b->qual_pool + b->qual_off[a], ops.data(), ocap, imk.data(), mcap, cb.data(), ccap, &info);
+        bool handled = false;
+        warp_emu::run_warp([&]() {
+            const bool ok = sp_walk_alignment_warp(C.indel_threshold, C.min_q, b->flag[a], b->pos[a], b->l_qseq[a], b->n_cigar[a],
+                                                   b->cigar_pool + b->cigar_off[a], tag_pool, b->tag_off[a], b->tag_off[a + 1], tk,
+                                                   b->qual_pool + b->qual_off[a], ops2.data(), ocap, imk2.data(), mcap,
+                                                   cb2.data(), ccap, &info2);
+            if (warp_emu::lane_id() == 0) handled = ok;
+        });
+        if (!handled) continue;
+        out[1]++;
+        int diff = 0;
+        if (memcmp(&info, &info2, sizeof info)) diff |= 8;
+        else {
+            if (memcmp(ops.data(), ops2.data(), sizeof(SpOp) * (size_t) (info.n_ops + 1))) diff |= 1;
+            if (memcmp(imk.data(), imk2.data(), sizeof(SpInitMarker) * (size_t) info.n_imk)) diff |= 2;
+            if (memcmp(cb.data(), cb2.data(), sizeof(SpBlock) * (size_t) info.n_cb)) diff |= 4;
+        }
+        if (diff) {
+            if (out[3] < 0) { out[3] = a; out[4] = diff; }
+            out[2]++;
+        }
     }
     return 0;
 }

@@ -200,3 +200,17 @@ def plan_signature(batch, indel_threshold, n_threads, safe_caps=False):
     rc = C.c_int()
     h = lib().hs_plan_sig(C.byref(cb), indel_threshold, 1 if safe_caps else 0, n_threads, C.byref(rc))
     return rc.value, int(h)
+
+
+def walk_warp_check(batch, params):
+    """Warp-cooperative walker (32 emulated lanes) vs the serial walker over every alignment of the batch:
+    dict(alignments, handled, different, first, what)."""
+    L = lib()
+    L.hs_walk_warp_check.argtypes = [C.POINTER(CFlatBatch), C.POINTER(SpParams), C.POINTER(C.c_int64)]
+    L.hs_walk_warp_check.restype = C.c_int
+    cb = batch.as_c()
+    out = (C.c_int64 * 5)()
+    rc = L.hs_walk_warp_check(C.byref(cb), C.byref(params), out)
+    if rc != 0:
+        raise RuntimeError(f"hs_walk_warp_check rc={rc}")
+    return dict(alignments=out[0], handled=out[1], different=out[2], first=out[3], what=out[4])

@@ -336,3 +336,43 @@ def test_rng_matches_glibc(sp):
         eng.rng_seed(1)
         for _ in range(1000):
             assert eng.rng_next() == libc.rand()
+
+
+def test_warp_walker_and_serial_walker(sp, oracle, monkeypatch):
+    """K1 has two forms: a warp per alignment (sp_walk_warp.cuh; what an aligner writes) and a thread per alignment
+    (sp_walk.cuh; everything, and whatever the first declines).  Both against the reference's tables, and the
+    hand-over between them: MD tags and CIGARs mixing M with =/X go to the serial walker, nothing else does."""
+    cases = [("ont", "ont", 24, dict(locus_len=400000)),
+             ("hifi", "hifi", 48, dict(locus_len=300000, eqx=1, n_rate=1e-4, clip_prob=0.8)),
+             ("ont", "ont", 40, dict(locus_len=300000, len_mean=8000, len_sd=3000, len_min=1500, clip_prob=0.9, hard_clip_prob=0.9)),
+             ("hifi", "hifi", 40, dict(locus_len=300000, use_md=1)),
+             ("stress", "hifi", 12, dict(locus_len=300000))]
+    for mode in ("warp", "serial"):
+        monkeypatch.setenv("SECPHASE_B200_WALK", mode)   # ("warp": also for alignments the default leaves to the serial walker)
+        for k, (spreset, ppreset, ng, over) in enumerate(cases):
+            s, b, codes, off = make_case(spreset, ng, **over)
+            exp = oracle.run(b, oracle.preset_params(ppreset), oracle_refseq(oracle, s))
+            A = len(b.n_cigar)
+            with sp.Secphase(ppreset) as eng:
+                eng.set_reference_codes(codes, off)
+                got = eng.run_debug(b)
+                fb = eng.walk_fallbacks()
+                assert not compare_results(exp, got, label=f"cuda-{mode}-walk")
+                assert fb == (-1 if mode == "serial" else A if over.get("use_md") else 0)
+                if k == 1:
+                    # '=' ops rewritten as 'M' next to '=' / 'X' ops: same alignment, but no longer the token
+                    # structure the warp walker expects -> handed to the serial walker, same tables
+                    b2 = b.group_slice(0, b.n_groups)
+                    b2.cigar_pool = b2.cigar_pool.copy()
+                    changed = set()
+                    for a in range(0, A, 3):
+                        c0, nc = int(b2.cigar_off[a]), int(b2.n_cigar[a])
+                        eq = [j for j in range(c0, c0 + nc) if (int(b2.cigar_pool[j]) & 15) == 7]
+                        if len(eq) > 1:
+                            j = eq[len(eq) // 2]
+                            b2.cigar_pool[j] = int(b2.cigar_pool[j]) & ~15
+                            changed.add(a)
+                    eng.rng_seed(1)
+                    got2 = eng.run_debug(b2)
+                    assert not compare_results(exp, got2, label=f"cuda-{mode}-walk-mixed-cigar")
+                    assert eng.walk_fallbacks() == (-1 if mode == "serial" else len(changed)) and len(changed) > 3

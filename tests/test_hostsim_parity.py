@@ -213,3 +213,54 @@ def test_fast_hmm_pipeline_bit_exact_vs_oracle(hostsim, oracle, name, spreset, p
     assert f["instances"] > 0.5 * len(x["items"])
     assert f["rerun"] <= 0.01 * f["instances"] + 2
     assert f["max_abs_drift_ulp"] <= 16 and f["max_rel_drift"] <= 1e-10
+
+
+@pytest.mark.parametrize("name,spreset,ppreset,ng,over", CASES, ids=[c[0] for c in CASES])
+def test_warp_walker_equals_serial_walker(hostsim, oracle, name, spreset, ppreset, ng, over):
+    """sp_walk_warp.cuh (the 32 lanes emulated by tests/hostsim/warp_emu.h) writes the tables of sp_walk.cuh --
+    ops, extents, initial markers, confident blocks -- for every alignment it accepts, and accepts everything the
+    generator writes with cs tags."""
+    s, b, codes, off = make_case(spreset, min(ng, 12), **over)
+    r = hostsim.walk_warp_check(b, hostsim.params_from_oracle(oracle.preset_params(ppreset)))
+    assert r["different"] == 0, r
+    assert r["handled"] == (0 if over.get("use_md") else r["alignments"]), r
+
+
+def test_warp_walker_declines_or_agrees_on_damaged_input(hostsim, oracle):
+    """Damaged cs text and CIGARs (substituted and swapped bytes, changed lengths and ops, zero-length ops): the
+    warp walker either hands the alignment to the serial walker or writes exactly the serial walker's tables."""
+    rng = np.random.default_rng(11)
+    alpha = np.frombuffer(b":*+-acgtn0123456789Z^ ", dtype=np.uint8)
+    handled = total = 0
+    for spreset, ppreset, over in (("hifi", "hifi", dict(locus_len=300000)),
+                                   ("hifi", "hifi", dict(locus_len=300000, eqx=1, clip_prob=0.8)),
+                                   ("ont", "ont", dict(locus_len=300000, len_mean=3000, len_sd=1000, len_min=800, clip_prob=0.9,
+                                                       hard_clip_prob=0.9))):
+        s, b0, codes, off = make_case(spreset, 12, **over)
+        P = hostsim.params_from_oracle(oracle.preset_params(ppreset))
+        for it in range(12):
+            b = b0.group_slice(0, b0.n_groups)
+            b.tag_pool = b.tag_pool.copy()
+            b.cigar_pool = b.cigar_pool.copy()
+            for a in range(len(b.n_cigar)):
+                mode = int(rng.integers(0, 5))
+                t0, t1 = int(b.tag_off[a]), int(b.tag_off[a + 1])
+                c0, nc = int(b.cigar_off[a]), int(b.n_cigar[a])
+                if mode == 0 and t1 > t0:
+                    for _ in range(int(rng.integers(1, 4))):
+                        b.tag_pool[rng.integers(t0, t1)] = alpha[rng.integers(0, len(alpha))]
+                elif mode == 1:
+                    k = c0 + int(rng.integers(0, nc))
+                    v = int(b.cigar_pool[k])
+                    b.cigar_pool[k] = (max(0, (v >> 4) + int(rng.integers(-2, 3))) << 4) | (v & 15)
+                elif mode == 2:
+                    k = c0 + int(rng.integers(0, nc))
+                    b.cigar_pool[k] = (int(b.cigar_pool[k]) & ~15) | int(rng.choice([0, 1, 2, 4, 5, 7, 8]))
+                elif mode == 3 and t1 - t0 > 4:
+                    i, j = rng.integers(t0, t1, 2)
+                    b.tag_pool[i], b.tag_pool[j] = b.tag_pool[j], b.tag_pool[i]
+            r = hostsim.walk_warp_check(b, P)
+            assert r["different"] == 0, (spreset, it, r)
+            handled += r["handled"]
+            total += r["alignments"]
+    assert 0 < handled < total

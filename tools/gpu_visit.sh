@@ -51,6 +51,32 @@ stage)
     timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --hmm $m >> $out/${tag}_stage.json 2>> $out/${tag}_stage.err
   done
   cat $out/${tag}_stage.json ;;
+prof)  # clock64 split of k_group / k_emit (lib/variants/lib_prof.so = -DSP_PROFILE_GROUP)
+  for p in stress ont; do
+    SECPHASE_B200_LIB=secphase_b200/lib/variants/lib_prof.so timeout 300 python tools/stage_bench.py --preset $p --groups 2048 --iters 1 >> $out/${tag}_prof.json 2>> $out/${tag}_prof.err
+  done
+  cat $out/${tag}_prof.err | tail -5 ;;
+ontsms)  # ONT bench line vs the SM split (integer stages | HMM)
+  for n in ${SMS_LIST:-16 24 32 40}; do
+    ( SECPHASE_B200_INT_SMS=$n timeout 300 python bench.py --preset ont --no-cpu-baseline --no-per-config --steps 6 ) >> $out/${tag}_ontsms.json 2>> $out/${tag}_ontsms.err
+  done
+  python - <<EOF
+import json
+for l in open('$out/${tag}_ontsms.json'):
+    try: d=json.loads(l)
+    except Exception: continue
+    print(d['config'].get('sm_partition'), round(d['value']), round(d['e2e']['value']), d['roofline']['kernel_ms_per_step'], d.get('stage_ms_isolated'))
+EOF
+  ;;
+stagew)  # fast-arithmetic stage times with a warp per alignment in K1 for every alignment (default: only long op tables)
+  for p in ont stress; do
+    SECPHASE_B200_WALK=warp timeout 300 python tools/stage_bench.py --preset $p --groups 2048 >> $out/${tag}_stagew.json 2>> $out/${tag}_stagew.err
+    timeout 300 python tools/stage_bench.py --preset $p --groups 2048 >> $out/${tag}_stagew.json 2>> $out/${tag}_stagew.err
+  done
+  SECPHASE_B200_WALK=warp timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 >> $out/${tag}_stagew.json 2>> $out/${tag}_stagew.err
+  timeout 300 python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 >> $out/${tag}_stagew.json 2>> $out/${tag}_stagew.err
+  timeout 300 python tools/stage_bench.py --preset ont --groups 10240 --locus-len 5000000 >> $out/${tag}_stagew.json 2>> $out/${tag}_stagew.err
+  cut -c1-400 $out/${tag}_stagew.json ;;
 stagehifi)  # HiFi bench-size stage times: fast (default lib and every lib under lib/variants), then strict
   for lib in "" secphase_b200/lib/variants/*.so; do
     [ -n "$lib" ] && [ ! -f "$lib" ] && continue
