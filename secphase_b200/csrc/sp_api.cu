@@ -125,6 +125,8 @@ struct Slot {
     // and enqueues phase B (emit, sort, HMM, score, result copies).  phase: 0 none, 1 A enqueued,
     // 2 B enqueued (or failed: b_rc/b_err), guarded by sp_ctx::mu.
     cudaEvent_t ev_a = nullptr;
+    cudaStream_t stream_hi = nullptr;  // phase B's integer kernels: same SMs as `stream`, scheduled ahead of the next batches' phase A
+    cudaEvent_t ev_b = nullptr;        // end of phase B on stream_hi; `stream` waits for it
     int phase = 0;
     int b_rc = 0;
     std::string b_err;
@@ -261,16 +263,21 @@ static void partition_sms(sp_ctx *c, int want_int) {
 }
 
 // a non-blocking stream inside green context g (or an ordinary one when the device is not partitioned)
-static bool make_stream(sp_ctx *c, CUgreenCtx g, cudaStream_t *out) {
+static bool make_stream(sp_ctx *c, CUgreenCtx g, cudaStream_t *out, bool high_priority = false) {
+    int prio = 0;
+    if (high_priority) {
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) prio = greatest;
+    }
     if (c->partitioned && g) {
         CUstream s = nullptr;
-        if (g_green_stream_create(&s, g, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS) {
+        if (g_green_stream_create(&s, g, CU_STREAM_NON_BLOCKING, prio) == CUDA_SUCCESS) {
             *out = reinterpret_cast<cudaStream_t>(s);
             return true;
         }
         return false;
     }
-    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking) == cudaSuccess;
+    return cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, prio) == cudaSuccess;
 }
 
 // The SM partition and the streams inside it are created at the first batch, because the right split
@@ -290,6 +297,10 @@ static int ensure_streams(sp_ctx *c, const sp_flat_batch *hint) {
     for (int s = 0; s < SP_N_SLOTS && ok; s++) {
         Slot &S = c->slot[s];
         ok = ok && make_stream(c, c->g_int, &S.stream);
+        // With several batches in flight the integer SMs are kept busy by the walk/group kernels of the batches
+        // behind; a batch's emit/sort (which gate its HMM launches) and score kernels must not queue behind them,
+        // or the HMM SMs idle: they go to a stream of the highest priority.  SECPHASE_B200_NO_PRIORITY=1: one stream.
+        if (!getenv("SECPHASE_B200_NO_PRIORITY")) ok = ok && make_stream(c, c->g_int, &S.stream_hi, true);
         for (int k = 0; k < SP_N_AUX && ok; k++) ok = ok && make_stream(c, c->g_hmm, &S.aux[k]);
     }
     if (!ok) {
@@ -413,6 +424,7 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
         for (int k = 0; k < EV_N; k++) ok = ok && cudaEventCreate(&S.ev[k]) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&S.ev_a, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&S.ev_b, cudaEventDisableTiming) == cudaSuccess;
         for (int k = 0; k < SP_N_AUX && ok; k++)
             ok = ok && cudaEventCreateWithFlags(&S.ev_join[k], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -440,10 +452,12 @@ void sp_destroy(sp_ctx *c) {
     cudaDeviceSynchronize();
 #ifdef SP_PROFILE_GROUP
     {
-        unsigned long long h[8] = {};
+        unsigned long long h[16] = {};
         cudaMemcpyFromSymbol(h, sp_prof, sizeof(h));
         fprintf(stderr, "[secphase_b200:prof] thread-cycles: k_group markers %llu, consensus %llu, emit-count %llu; k_emit %llu\n",
                 h[0], h[1], h[2], h[3]);
+        fprintf(stderr, "[secphase_b200:prof] consensus rounds: sort+intersect blocks %llu, flank lists %llu, intersect flank %llu, "
+                        "project %llu, sort %llu (+needs_to_find_blocks outside)\n", h[8], h[9], h[10], h[11], h[12]);
     }
 #endif
     for (int s = 0; s < SP_N_SLOTS; s++) {
@@ -459,6 +473,8 @@ void sp_destroy(sp_ctx *c) {
             if (S.ev[k]) cudaEventDestroy(S.ev[k]);
         if (S.ev_fork) cudaEventDestroy(S.ev_fork);
         if (S.ev_a) cudaEventDestroy(S.ev_a);
+        if (S.ev_b) cudaEventDestroy(S.ev_b);
+        if (S.stream_hi) cudaStreamDestroy(S.stream_hi);
         for (int k = 0; k < SP_N_AUX; k++) {
             if (S.ev_join[k]) cudaEventDestroy(S.ev_join[k]);
             if (S.aux[k]) cudaStreamDestroy(S.aux[k]);
@@ -937,7 +953,9 @@ static int run_phase_a(sp_ctx *c, Slot &S) {
 
 // Phase B, enqueued by the launcher thread once ev_a has fired: emit, sort, HMM, score.
 static int run_phase_b(sp_ctx *c, Slot &S) {
-    cudaStream_t st = S.stream;
+    // (phase A is complete when this runs, so the high-priority stream needs no dependency on `stream`;
+    // `stream` -- results, the next use of the slot -- waits for the end of phase B below)
+    cudaStream_t st = S.stream_hi ? S.stream_hi : S.stream;
     const SpBatchPtrs &P = S.P;
     const SpConst *dC = c->dC.as<SpConst>();
     CK(cudaEventSynchronize(S.ev_a));
@@ -1013,6 +1031,10 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
         S.launches++;
     }
     CK(cudaEventRecord(S.ev[EV_SCORE], st));
+    if (st != S.stream) {
+        CK(cudaEventRecord(S.ev_b, st));
+        CK(cudaStreamWaitEvent(S.stream, S.ev_b, 0));
+    }
     CK(cudaGetLastError());
     return SP_OK;
 }

@@ -15,6 +15,17 @@
 #include "sp_markers.cuh"
 #include "sp_walk.cuh"
 
+#if defined(SP_PROFILE_GROUP) && defined(__CUDACC__)  // tuning aid (see sp_kernels.cuh): [0..7] stages, [8..15] inside the consensus rounds
+__device__ unsigned long long sp_prof[16];
+#endif
+#if defined(SP_PROFILE_GROUP) && defined(__CUDA_ARCH__)
+#define SP_PROFB_T0() long long profb_t = clock64()
+#define SP_PROFB(k) do { long long t_ = clock64(); atomicAdd(&sp_prof[8 + (k)], (unsigned long long) (t_ - profb_t)); profb_t = t_; } while (0)
+#else
+#define SP_PROFB_T0() ((void) 0)
+#define SP_PROFB(k) ((void) 0)
+#endif
+
 struct SpIv {  // interval in read-forward coordinates
     int32_t s, e;
 };
@@ -102,10 +113,133 @@ struct SpBlockWork {
     int cap;
 };
 
+// find_flanking_blocks (ptMarker.c:446-484) for one alignment: the windows of +-margin around the group's marker
+// positions, clipped to the alignment and merged.  Returns the list length (<= cap).
+SP_HD int sp_flank_list(const SpAlnInfo &ai, int n, int P, const int32_t *gpos, int margin, SpIv *flank, int cap, int *err) {
+    int nf = 0;
+    if (P > 0) {
+        int start = sp_max(ai.rds_f, gpos[0] - margin);
+        int end = sp_min(ai.rde_f, gpos[0] + margin);
+        // The marker list holds n entries per position (ptMarker.c:455-476 iterates all of them).
+        // After the first entry of a position `end` equals that position's own clipped end, so the
+        // other n-1 entries are no-ops whenever the clipped interval is non-degenerate (cs < ce);
+        // only degenerate ones (cs >= ce) are replayed entry by entry.
+        for (int pi = 0; pi < P; pi++) {
+            const int p = gpos[pi];
+            const int cs = sp_max(ai.rds_f, p - margin);
+            const int ce = sp_min(ai.rde_f, p + margin);
+            const int reps = (cs < ce) ? 1 : n;
+            for (int r = (pi == 0 ? 1 : 0); r < (pi == 0 ? sp_max(reps, 1) : reps); r++) {
+                if (cs < end) {
+                    end = ce;
+                } else {
+                    if (nf < cap) { flank[nf].s = start; flank[nf].e = end; } else *err |= SP_GERR_BLOCK_CAP;
+                    nf++;
+                    start = cs;
+                    end = ce;
+                }
+            }
+        }
+        if (nf < cap) { flank[nf].s = start; flank[nf].e = end; } else *err |= SP_GERR_BLOCK_CAP;
+        nf++;
+        if (nf > cap) nf = cap;
+    }
+    return nf;
+}
+
+// The projection of correct_conf_blocks (ptMarker.c:528-643) for alignment i of the group: the consensus blocks
+// cur[0..nc) (read-forward coordinates) in the alignment's seq/ref coordinates, written to `out` in SEQ order.
+// Returns the list length (<= cap).
+SP_HD int sp_project_blocks(const SpGroupAlnView &G, int i, const SpIv *cur, int nc, int indel_threshold, SpBlock *out,
+                            int cap, int *err) {
+    const int a = G.a0 + i;
+    const bool rev = (G.flag[a] & SP_FREVERSE) != 0;
+    const SpOp *ops = G.ops + G.ops_off[a];
+    const int n_ops = G.info[a].n_ops;
+    int m = 0;
+    int j = rev ? nc - 1 : 0;
+    bool have = true, del_flag = false;
+    int b_s, b_e;
+    int rfs = 0, rfe = 0, sqs = 0, sqe = 0;  // the reference leaves these uninitialised
+    if (rev) { b_s = -cur[j].e; b_e = -cur[j].s; } else { b_s = cur[j].s; b_e = cur[j].e; }
+    for (int o = 0; o < n_ops; o++) {
+        // Ops that cannot touch the current block are jumped over with a binary search in the op
+        // table instead of being visited (the reference walks every op of the record in every
+        // round of the x0.8 loop, ptMarker.c:545-641).  In walking coordinates an op spans
+        // [w[o], w[o+1]-1]; with del_flag clear, an op matters only if it ends at or after b_s-1
+        // (it may contain b_s, or be a deletion sitting at b_s) and, once ops start past b_s,
+        // only if it reaches b_e (the emitting branch).  Everything skipped would at most have
+        // cleared del_flag, which is already clear.
+        if (!del_flag) {
+            const int w0 = rev ? -ops[o].rdx : ops[o].rdx;
+            const int target = (w0 > b_s) ? b_e + 1 : b_s;
+            // (bisecting the whole remaining table beats galloping from o here: the first levels of the search hit
+            // the same few entries every time and stay in L1; measured, profiles/r02_prof_group_gallop_v29.txt)
+            int lo = o, hi = n_ops;  // first idx in [o, n_ops) with w[idx+1] >= target
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const int w1 = rev ? -ops[mid + 1].rdx : ops[mid + 1].rdx;
+                if (w1 >= target) hi = mid; else lo = mid + 1;
+            }
+            o = lo;
+            if (o >= n_ops) break;
+        }
+        const SpOpView v = sp_op_view(ops, o, rev);
+        int c_s, c_e;
+        if (rev) { c_s = -v.rde_f; c_e = -v.rds_f; } else { c_s = v.rds_f; c_e = v.rde_f; }
+        if (sp_op_is_match(v.op) || v.op == SP_CINS) {
+            const bool ins = v.op == SP_CINS;
+            while (have && b_e <= c_e) {
+                if (c_s <= b_s && !(del_flag && c_s == b_s)) {
+                    rfs = ins ? v.rfs : v.rfs + (b_s - c_s);
+                    sqs = v.sqs + (b_s - c_s);
+                }
+                rfe = ins ? v.rfe : v.rfs + (b_e - c_s);
+                sqe = v.sqs + (b_e - c_s);
+                if (m < cap) {
+                    SpBlock nb;
+                    nb.rfs = rfs; nb.rfe = rfe; nb.sqs = sqs; nb.sqe = sqe;
+                    nb.rds_f = cur[j].s; nb.rde_f = cur[j].e;
+                    out[m] = nb;
+                } else {
+                    *err |= SP_GERR_BLOCK_CAP;
+                }
+                m++;
+                if (rev && j > 0) {
+                    j--;
+                    b_s = -cur[j].e; b_e = -cur[j].s;
+                } else if (!rev && j < nc - 1) {
+                    j++;
+                    b_s = cur[j].s; b_e = cur[j].e;
+                } else {
+                    have = false;
+                }
+            }
+            if (!have) break;
+            if (c_s <= b_s && b_s <= c_e && !(del_flag && c_s == b_s)) {
+                rfs = ins ? v.rfs : v.rfs + (b_s - c_s);
+                sqs = v.sqs + (b_s - c_s);
+            }
+            del_flag = false;
+        } else if (v.op == SP_CDEL) {
+            // 615-625 only writes prev_block->rfe of the temporary consensus list (no effect, Q6)
+            if (have && b_s == c_s && v.len <= indel_threshold) {
+                del_flag = true;
+                rfs = v.rfs;
+                sqs = v.sqs;
+            }
+        }
+    }
+    if (m > cap) m = cap;
+    sp_sort_blocks_by_sqs(out, m);
+    return m;
+}
+
 // correct_conf_blocks (ptMarker.c:495-647) preceded by set_flanking_blocks (487-492).
 SP_HD int sp_correct_conf_blocks(const SpGroupAlnView &G, int P, const int32_t *gpos, int margin,
                                  int indel_threshold, SpBlockWork &W, int *err) {
     const int n = G.n, cap = W.cap;
+    SP_PROFB_T0();
     // --- intersect the alignments' confident blocks (495-507)
     sp_sort_blocks_by_rds(W.ab, W.nb[0]);
     SpIv *cur = W.cons_a, *nxt = W.cons_b;
@@ -121,40 +255,15 @@ SP_HD int sp_correct_conf_blocks(const SpGroupAlnView &G, int P, const int32_t *
                           W.nb[i], nxt, cap, err);
         SpIv *t = cur; cur = nxt; nxt = t;
     }
-    // --- intersect with every alignment's flanking blocks (508-514; find_flanking_blocks 446-484)
+    SP_PROFB(0);
+    // --- intersect with every alignment's flanking blocks (508-514)
     for (int i = 0; i < n; i++) {
-        const SpAlnInfo &ai = G.info[G.a0 + i];
-        int nf = 0;
-        if (P > 0) {
-            int start = sp_max(ai.rds_f, gpos[0] - margin);
-            int end = sp_min(ai.rde_f, gpos[0] + margin);
-            // The marker list holds n entries per position (ptMarker.c:455-476 iterates all of them).
-            // After the first entry of a position `end` equals that position's own clipped end, so the
-            // other n-1 entries are no-ops whenever the clipped interval is non-degenerate (cs < ce);
-            // only degenerate ones (cs >= ce) are replayed entry by entry.
-            for (int pi = 0; pi < P; pi++) {
-                const int p = gpos[pi];
-                const int cs = sp_max(ai.rds_f, p - margin);
-                const int ce = sp_min(ai.rde_f, p + margin);
-                const int reps = (cs < ce) ? 1 : n;
-                for (int r = (pi == 0 ? 1 : 0); r < (pi == 0 ? sp_max(reps, 1) : reps); r++) {
-                    if (cs < end) {
-                        end = ce;
-                    } else {
-                        if (nf < cap) { W.flank[nf].s = start; W.flank[nf].e = end; } else *err |= SP_GERR_BLOCK_CAP;
-                        nf++;
-                        start = cs;
-                        end = ce;
-                    }
-                }
-            }
-            if (nf < cap) { W.flank[nf].s = start; W.flank[nf].e = end; } else *err |= SP_GERR_BLOCK_CAP;
-            nf++;
-            if (nf > cap) nf = cap;
-        }
+        const int nf = sp_flank_list(G.info[G.a0 + i], n, P, gpos, margin, W.flank, cap, err);
+        SP_PROFB(1);
         const SpIv *fl = W.flank;
         nc = sp_intersect(cur, nc, [&](int j) { return fl[j]; }, nf, nxt, cap, err);
         SpIv *t = cur; cur = nxt; nxt = t;
+        SP_PROFB(2);
     }
     if (nc == 0) {  // 515-523
         for (int i = 0; i < n; i++) W.nb[i] = 0;
@@ -162,86 +271,8 @@ SP_HD int sp_correct_conf_blocks(const SpGroupAlnView &G, int P, const int32_t *
     }
     // --- project the consensus blocks into each alignment's seq/ref coordinates (528-643)
     for (int i = 0; i < n; i++) {
-        const int a = G.a0 + i;
-        const bool rev = (G.flag[a] & SP_FREVERSE) != 0;
-        const SpOp *ops = G.ops + G.ops_off[a];
-        const int n_ops = G.info[a].n_ops;
-        SpBlock *out = W.ab + (int64_t) i * cap;
-        int m = 0;
-        int j = rev ? nc - 1 : 0;
-        bool have = true, del_flag = false;
-        int b_s, b_e;
-        int rfs = 0, rfe = 0, sqs = 0, sqe = 0;  // the reference leaves these uninitialised
-        if (rev) { b_s = -cur[j].e; b_e = -cur[j].s; } else { b_s = cur[j].s; b_e = cur[j].e; }
-        for (int o = 0; o < n_ops; o++) {
-            // Ops that cannot touch the current block are jumped over with a binary search in the op
-            // table instead of being visited (the reference walks every op of the record in every
-            // round of the x0.8 loop, ptMarker.c:545-641).  In walking coordinates an op spans
-            // [w[o], w[o+1]-1]; with del_flag clear, an op matters only if it ends at or after b_s-1
-            // (it may contain b_s, or be a deletion sitting at b_s) and, once ops start past b_s,
-            // only if it reaches b_e (the emitting branch).  Everything skipped would at most have
-            // cleared del_flag, which is already clear.
-            if (!del_flag) {
-                const int w0 = rev ? -ops[o].rdx : ops[o].rdx;
-                const int target = (w0 > b_s) ? b_e + 1 : b_s;
-                int lo = o, hi = n_ops;  // first idx in [o, n_ops) with w[idx+1] >= target
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    const int w1 = rev ? -ops[mid + 1].rdx : ops[mid + 1].rdx;
-                    if (w1 >= target) hi = mid; else lo = mid + 1;
-                }
-                o = lo;
-                if (o >= n_ops) break;
-            }
-            const SpOpView v = sp_op_view(ops, o, rev);
-            int c_s, c_e;
-            if (rev) { c_s = -v.rde_f; c_e = -v.rds_f; } else { c_s = v.rds_f; c_e = v.rde_f; }
-            if (sp_op_is_match(v.op) || v.op == SP_CINS) {
-                const bool ins = v.op == SP_CINS;
-                while (have && b_e <= c_e) {
-                    if (c_s <= b_s && !(del_flag && c_s == b_s)) {
-                        rfs = ins ? v.rfs : v.rfs + (b_s - c_s);
-                        sqs = v.sqs + (b_s - c_s);
-                    }
-                    rfe = ins ? v.rfe : v.rfs + (b_e - c_s);
-                    sqe = v.sqs + (b_e - c_s);
-                    if (m < cap) {
-                        SpBlock nb;
-                        nb.rfs = rfs; nb.rfe = rfe; nb.sqs = sqs; nb.sqe = sqe;
-                        nb.rds_f = cur[j].s; nb.rde_f = cur[j].e;
-                        out[m] = nb;
-                    } else {
-                        *err |= SP_GERR_BLOCK_CAP;
-                    }
-                    m++;
-                    if (rev && j > 0) {
-                        j--;
-                        b_s = -cur[j].e; b_e = -cur[j].s;
-                    } else if (!rev && j < nc - 1) {
-                        j++;
-                        b_s = cur[j].s; b_e = cur[j].e;
-                    } else {
-                        have = false;
-                    }
-                }
-                if (!have) break;
-                if (c_s <= b_s && b_s <= c_e && !(del_flag && c_s == b_s)) {
-                    rfs = ins ? v.rfs : v.rfs + (b_s - c_s);
-                    sqs = v.sqs + (b_s - c_s);
-                }
-                del_flag = false;
-            } else if (v.op == SP_CDEL) {
-                // 615-625 only writes prev_block->rfe of the temporary consensus list (no effect, Q6)
-                if (have && b_s == c_s && v.len <= indel_threshold) {
-                    del_flag = true;
-                    rfs = v.rfs;
-                    sqs = v.sqs;
-                }
-            }
-        }
-        if (m > cap) m = cap;
-        sp_sort_blocks_by_sqs(out, m);
-        W.nb[i] = m;
+        W.nb[i] = sp_project_blocks(G, i, cur, nc, indel_threshold, W.ab + (int64_t) i * cap, cap, err);
+        SP_PROFB(3);
     }
     return nc;
 }

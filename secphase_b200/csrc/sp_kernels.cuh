@@ -143,7 +143,6 @@ __global__ void __launch_bounds__(128) k_walk_list(SpBatchPtrs B, const SpConst 
 }
 
 #ifdef SP_PROFILE_GROUP  // tuning aid: clock64 split of the thread-per-group stages (summed over threads)
-__device__ unsigned long long sp_prof[8];
 #define SP_PROF_T0() long long prof_t = clock64()
 #define SP_PROF(k) do { long long t_ = clock64(); atomicAdd(&sp_prof[k], (unsigned long long) (t_ - prof_t)); prof_t = t_; } while (0)
 #else

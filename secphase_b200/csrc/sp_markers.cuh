@@ -33,7 +33,11 @@ struct SpGroupAlnView {  // what K2..K5 need to know about the alignments of one
 SP_HD int sp_group_markers(const SpGroupAlnView &G, int32_t *gpos, SpEntry *entries, int pos_cap, int32_t *counts,
                            int *err) {
     const int n = G.n;
-    int cur[SP_MAX_ALN_PER_GROUP_C];
+    // per alignment: cursor into its initial markers (walked in ascending read_pos_f) and the position under the
+    // cursor (the heads are compared n times per position).  The op that holds a position is found by bisecting the
+    // whole op table every time: galloping from the previous hit was measured slower (the first levels of the
+    // bisection stay in L1; profiles/r02_prof_group_gallop_v29.txt).
+    int cur[SP_MAX_ALN_PER_GROUP_C], head[SP_MAX_ALN_PER_GROUP_C];
     int n_init = 0;
     for (int i = 0; i < n; i++) {
         const int a = G.a0 + i;
@@ -41,31 +45,26 @@ SP_HD int sp_group_markers(const SpGroupAlnView &G, int32_t *gpos, SpEntry *entr
         const int cnt = G.info[a].n_imk;
         n_init += cnt;
         cur[i] = rev ? cnt - 1 : 0;  // walk every list in ascending read_pos_f
+        head[i] = (cur[i] >= 0 && cur[i] < cnt) ? G.imk[G.imk_off[a] + cur[i]].read_pos_f : 0x7fffffff;
     }
     int P = 0, n_after_allmm = 0, n_filled = 0;
     for (;;) {
         // smallest head position
         int p = 0x7fffffff;
-        for (int i = 0; i < n; i++) {
-            const int a = G.a0 + i;
-            const int cnt = G.info[a].n_imk;
-            if (cur[i] >= 0 && cur[i] < cnt) {
-                int q = G.imk[G.imk_off[a] + cur[i]].read_pos_f;
-                if (q < p) p = q;
-            }
-        }
+        for (int i = 0; i < n; i++) p = head[i] < p ? head[i] : p;
         if (p == 0x7fffffff) break;
         // which alignments mismatch at p
         int occ = 0;
         int has[SP_MAX_ALN_PER_GROUP_C];
         for (int i = 0; i < n; i++) {
-            const int a = G.a0 + i;
-            const int cnt = G.info[a].n_imk;
             has[i] = -1;
-            if (cur[i] >= 0 && cur[i] < cnt && G.imk[G.imk_off[a] + cur[i]].read_pos_f == p) {
+            if (head[i] == p) {
+                const int a = G.a0 + i;
+                const int cnt = G.info[a].n_imk;
                 has[i] = cur[i];
                 occ++;
                 cur[i] += ((G.flag[a] & SP_FREVERSE) != 0) ? -1 : 1;
+                head[i] = (cur[i] >= 0 && cur[i] < cnt) ? G.imk[G.imk_off[a] + cur[i]].read_pos_f : 0x7fffffff;
             }
         }
         if (occ == n) continue;  // mismatch in every alignment: a read error (ptMarker.c:223-225)

@@ -446,3 +446,4 @@ SP_HD int sp_find_op_by_read_pos(const SpOp *ops, int n_ops, bool rev, int p) {
     if (v.rds_f <= p && p <= v.rde_f) return j;
     return -1;
 }
+

@@ -233,7 +233,8 @@ SP_WDN bool sp_walk_alignment_warp(int indel_threshold, int min_q, int flag, int
     //   coordinates (prefix sums), the check against the CIGAR, initial markers (ptMarker.c:50-70), confident
     //   blocks (ptMarker.c:328-395)
     const int T = lead_h + trail_h + l_qseq;  // cigar_it.c:41-42
-    int c_sq = 0, c_rf = 0, c_rd = 0;         // running totals
+    int c_sq = 0, c_rf = 0;                   // running totals (read bases = SEQ bases + hard clips passed)
+    const int lh = (cigar[0] & 15) == SP_CHARD ? lead_h : 0;
     int first_match = 0x7fffffff;
     int run_c = 0, gap_from = lead_s;         // M/I/D CIGARs: runs matched so far, SEQ offset after the last indel
     int n_imk = 0, n_cb = 0, err = 0;
@@ -247,8 +248,8 @@ SP_WDN bool sp_walk_alignment_warp(int indel_threshold, int min_q, int flag, int
         const int op = (int) (ol & 15), len = (int) (ol >> 4);
         const int smk = on ? sp_op_step_mask(op) : 0;
         const int sq = (smk & 1) ? len : 0, rf = (smk & 2) ? len : 0, rd = (smk & 4) ? len : 0;
-        const int i_sq = c_sq + sp_warp_incl_scan(sq, lane), i_rf = c_rf + sp_warp_incl_scan(rf, lane),
-                  i_rd = c_rd + sp_warp_incl_scan(rd, lane);
+        const int i_sq = c_sq + sp_warp_incl_scan(sq, lane), i_rf = c_rf + sp_warp_incl_scan(rf, lane);
+        const int i_rd = i_sq + lh + ((on && op == SP_CHARD && k >= n_lead) ? len : 0);
         SpOp o;
         o.oplen = ol;
         o.sqs = i_sq - sq;
@@ -290,7 +291,15 @@ SP_WDN bool sp_walk_alignment_warp(int indel_threshold, int min_q, int flag, int
                 else
                     for (int j = 0; j < len; j++) cnt += (int) qual[o.sqs + j] >= min_q;
             }
-            const int incl = sp_warp_incl_scan(cnt, lane);
+            int incl, total;
+            if (!__any_sync(SP_FULL, cnt > 1)) {  // (one base per '*' token is the rule)
+                const uint32_t bm = __ballot_sync(SP_FULL, cnt == 1);
+                incl = __popc(bm & (lt | (1u << lane)));
+                total = __popc(bm);
+            } else {
+                incl = sp_warp_incl_scan(cnt, lane);
+                total = __shfl_sync(SP_FULL, incl, 31);
+            }
             if (cnt) {
                 int w = n_imk + incl - cnt;
                 for (int j = 0; j < len; j++) {
@@ -309,7 +318,7 @@ SP_WDN bool sp_walk_alignment_warp(int indel_threshold, int min_q, int flag, int
                     w++;
                 }
             }
-            n_imk += __shfl_sync(SP_FULL, incl, 31);
+            n_imk += total;
         }
         // ---- confident blocks
         {
@@ -340,8 +349,8 @@ SP_WDN bool sp_walk_alignment_warp(int indel_threshold, int min_q, int flag, int
         }
         c_sq = __shfl_sync(SP_FULL, i_sq, 31);
         c_rf = __shfl_sync(SP_FULL, i_rf, 31);
-        c_rd = __shfl_sync(SP_FULL, i_rd, 31);
     }
+    const int c_rd = c_sq + lh + trail_h;
     if (!eqx) {  // the M run after the last indel, and the run count
         const int gap = (c_sq - trail_s) - gap_from;
         if (gap > 0) {

@@ -52,13 +52,14 @@ stage)
   done
   cat $out/${tag}_stage.json ;;
 prof)  # clock64 split of k_group / k_emit (lib/variants/lib_prof.so = -DSP_PROFILE_GROUP)
-  for p in stress ont; do
-    SECPHASE_B200_LIB=secphase_b200/lib/variants/lib_prof.so timeout 300 python tools/stage_bench.py --preset $p --groups 2048 --iters 1 >> $out/${tag}_prof.json 2>> $out/${tag}_prof.err
-  done
-  cat $out/${tag}_prof.err | tail -5 ;;
-ontsms)  # ONT bench line vs the SM split (integer stages | HMM)
+  for p in stress ont; do for v in ${PROF_LIBS:-prof}; do
+    echo "variant $v preset $p" >> $out/${tag}_prof.err
+    SECPHASE_B200_LIB=secphase_b200/lib/variants/lib_$v.so timeout 300 python tools/stage_bench.py --preset $p --groups 2048 --iters 3 >> $out/${tag}_prof.json 2>> $out/${tag}_prof.err
+  done; done
+  cat $out/${tag}_prof.err | tail -24; cut -c1-330 $out/${tag}_prof.json ;;
+ontsms)  # bench line of one config (PRESET, default ont) vs the SM split (integer stages | HMM)
   for n in ${SMS_LIST:-16 24 32 40}; do
-    ( SECPHASE_B200_INT_SMS=$n timeout 300 python bench.py --preset ont --no-cpu-baseline --no-per-config --steps 6 ) >> $out/${tag}_ontsms.json 2>> $out/${tag}_ontsms.err
+    ( SECPHASE_B200_INT_SMS=$n timeout 300 python bench.py --preset ${PRESET:-ont} --no-cpu-baseline --no-per-config --steps 6 ) >> $out/${tag}_ontsms.json 2>> $out/${tag}_ontsms.err
   done
   python - <<EOF
 import json
