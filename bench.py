@@ -663,7 +663,7 @@ def main():
     # ---- the other BASELINE configs (N=1 default run only) ------------------------------------
     if rank == 0 and world == 1 and args.preset == "hifi" and not args.no_per_config and not args.no_cpu_baseline:
         per = {}
-        plan = [("hifi_small", 10, 3), ("ont", 6, 3), ("wg_offsets", 6, 3), ("stress", 6, 3)]
+        plan = [("hifi_small", 20, 3), ("ont", 15, 3), ("wg_offsets", 15, 3), ("stress", 9, 3)]  # (steps, warm-up): enough steps that the pipeline fill -- one integer phase with idle HMM SMs -- is a few per cent
         for name, k_steps, k_warm in plan:
             t_c = time.perf_counter()
             try:

@@ -159,6 +159,8 @@ struct sp_ctx {
     int test_block_cap = 0;  // tests: first plan clamps every group's block workspace to this (forces the retry)
     int64_t cap_retries = 0;
     bool full_baq = false;  // sp_set_write_qual: --writeBam mode
+    int group_mode = 0;  // SECPHASE_B200_GROUP: 0 default (lanes for groups of <= 4 alignments), 1 serial: thread per group, 2 lanes for all
+    int score_mode = 0;  // SECPHASE_B200_SCORE: the same for K5
     bool walk_serial = false; // SECPHASE_B200_WALK=serial: thread-per-alignment walker only
     int walk_min_ops = SP_WALK_WARP_MIN_OPS;  // SECPHASE_B200_WALK=warp: 0 (every cs alignment gets a warp)
     bool hmm_merge = false; // SECPHASE_B200_HMM_MERGE=1: one fast launch for all classes (best pipelined, longest single-batch tail)
@@ -284,12 +286,13 @@ static bool make_stream(sp_ctx *c, CUgreenCtx g, cudaStream_t *out, bool high_pr
 // depends on the data: the integer stages (walk / group / emit) are thread-per-alignment latency
 // chains whose cost grows with the cs/MD text, the HMM with the band cells.  HiFi read groups carry
 // ~3 KB of tag text and are best served by 8 SMs of integer work against 140 of HMM; ONT groups carry
-// ~17 KB and want 24 (measured: profiles/r01_sm_partition_sweep_v13.json).  SECPHASE_B200_INT_SMS=<n>
+// ~17 KB and want 32 (measured: profiles/r01_sm_partition_sweep_v13.json; with the warp-per-alignment walker,
+// whose time falls with the SMs it gets: profiles/r02_bench_sm_split_group_lanes_v30.txt).  SECPHASE_B200_INT_SMS=<n>
 // overrides (0 = no partition); the driver rounds the request up to its own granularity.
 static int ensure_streams(sp_ctx *c, const sp_flat_batch *hint) {
     if (c->streams_ready) return SP_OK;
     int want = 8;
-    if (hint && hint->n_groups > 0 && hint->tag_off[hint->n_alns] / hint->n_groups > 8192) want = 24;
+    if (hint && hint->n_groups > 0 && hint->tag_off[hint->n_alns] / hint->n_groups > 8192) want = 32;
     if (const char *e = getenv("SECPHASE_B200_INT_SMS")) want = atoi(e);
     if (want >= c->sm_count) want = 0;
     partition_sms(c, want);
@@ -407,6 +410,9 @@ sp_ctx *sp_create(const sp_params *p, int cuda_device) {
     SP_ATTRF(41); SP_ATTRF(43); SP_ATTRF(45); SP_ATTRF(55); SP_ATTRF(73); SP_ATTRF(97); SP_ATTRF(125);
 #undef SP_ATTRF
     if (const char *e = getenv("SECPHASE_B200_HMM")) c->hmm_mode = strcmp(e, "strict") == 0 ? 0 : 1;
+    if (const char *e = getenv("SECPHASE_B200_GROUP")) c->group_mode = strcmp(e, "serial") == 0 ? 1 : strcmp(e, "lanes") == 0 ? 2 : 0;
+    c->score_mode = c->group_mode;
+    if (const char *e = getenv("SECPHASE_B200_SCORE")) c->score_mode = strcmp(e, "serial") == 0 ? 1 : strcmp(e, "lanes") == 0 ? 2 : 0;
     if (const char *e = getenv("SECPHASE_B200_WALK")) {
         c->walk_serial = strcmp(e, "serial") == 0;
         if (strcmp(e, "warp") == 0) c->walk_min_ops = 0;
@@ -561,7 +567,7 @@ struct Section {
     size_t off, bytes;
 };
 struct InLayout {
-    Section grp_aln_off, flag, tid, pos, l_qseq, n_cigar, tag_kind, aln_grp, gblk_cap;
+    Section grp_aln_off, flag, tid, pos, l_qseq, n_cigar, tag_kind, aln_grp, gblk_cap, glist;
     Section cigar_off, tag_off, seq_off, qual_off, ops_off, imk_off, gpos_off, gent_off, gblk_off, giv_off;
     Section cigar_pool, tag_pool, seq_pool, qual_pool;
     size_t total;
@@ -587,7 +593,7 @@ static InLayout make_layout(const sp_flat_batch *b, const SpPlan &pl) {
     const size_t G = (size_t) pl.G, A = (size_t) pl.A;
     add(L.grp_aln_off, 4 * (G + 1));
     add(L.flag, 4 * A); add(L.tid, 4 * A); add(L.pos, 4 * A); add(L.l_qseq, 4 * A); add(L.n_cigar, 4 * A);
-    add(L.tag_kind, 4 * A); add(L.aln_grp, 4 * A); add(L.gblk_cap, 4 * G);
+    add(L.tag_kind, 4 * A); add(L.aln_grp, 4 * A); add(L.gblk_cap, 4 * G); add(L.glist, 4 * G);
     add(L.cigar_off, 8 * (A + 1)); add(L.tag_off, 8 * (A + 1)); add(L.seq_off, 8 * (A + 1)); add(L.qual_off, 8 * (A + 1));
     add(L.ops_off, 8 * (A + 1)); add(L.imk_off, 8 * (A + 1));
     add(L.gpos_off, 8 * (G + 1)); add(L.gent_off, 8 * (G + 1)); add(L.gblk_off, 8 * (G + 1)); add(L.giv_off, 8 * (G + 1));
@@ -634,7 +640,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b, bool zero_cop
     put(L.grp_aln_off, b->grp_aln_off);
     put(L.flag, b->flag); put(L.tid, b->tid); put(L.pos, b->pos); put(L.l_qseq, b->l_qseq); put(L.n_cigar, b->n_cigar);
     if (b->tag_kind) put(L.tag_kind, b->tag_kind); else memset(h + L.tag_kind.off, 0, L.tag_kind.bytes);
-    put(L.aln_grp, pl.aln_grp.data()); put(L.gblk_cap, pl.gblk_cap.data());
+    put(L.aln_grp, pl.aln_grp.data()); put(L.gblk_cap, pl.gblk_cap.data()); put(L.glist, pl.glist.data());
     put(L.cigar_off, b->cigar_off); put(L.tag_off, b->tag_off); put(L.seq_off, b->seq_off); put(L.qual_off, b->qual_off);
     put(L.ops_off, pl.ops_off.data()); put(L.imk_off, pl.imk_off.data());
     put(L.gpos_off, pl.gpos_off.data()); put(L.gent_off, pl.gent_off.data());
@@ -727,7 +733,7 @@ static int stage_batch(sp_ctx *c, Slot &S, const sp_flat_batch *b, bool zero_cop
 #define DP(T, sec) reinterpret_cast<const T *>(d + L.sec.off)
     P.grp_aln_off = DP(int32_t, grp_aln_off); P.flag = DP(int32_t, flag); P.tid = DP(int32_t, tid);
     P.pos = DP(int32_t, pos); P.l_qseq = DP(int32_t, l_qseq); P.n_cigar = DP(int32_t, n_cigar);
-    P.tag_kind = DP(int32_t, tag_kind); P.aln_grp = DP(int32_t, aln_grp); P.gblk_cap = DP(int32_t, gblk_cap);
+    P.tag_kind = DP(int32_t, tag_kind); P.aln_grp = DP(int32_t, aln_grp); P.gblk_cap = DP(int32_t, gblk_cap); P.glist = DP(int32_t, glist);
     P.cigar_off = DP(int64_t, cigar_off); P.tag_off = DP(int64_t, tag_off); P.seq_off = DP(int64_t, seq_off);
     P.qual_off = DP(int64_t, qual_off); P.ops_off = DP(int64_t, ops_off); P.imk_off = DP(int64_t, imk_off);
     P.gpos_off = DP(int64_t, gpos_off); P.gent_off = DP(int64_t, gent_off); P.gblk_off = DP(int64_t, gblk_off);
@@ -936,10 +942,30 @@ static int run_phase_a(sp_ctx *c, Slot &S) {
     }
     CK(cudaEventRecord(S.ev[EV_WALK], st));
     if (P.G > 0) {
-        k_group<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC);
+        // K2 + K3: a lane per alignment for read groups of up to four alignments (2 or 4 lanes a group); a thread per
+        // group for the rest -- with 16 lanes a group the chains are shorter still, but the few SMs of the integer
+        // partition then run out of issue slots (stress: 62 ms against 47 per 8192 groups on 8 SMs, profiles/
+        // r02_bench_sm_split_group_lanes_v30.txt).  SECPHASE_B200_GROUP=serial|lanes forces one form for all.
+        const int32_t *gn = S.plan.glist_n;
+        const int lanes_to = c->group_mode == 1 ? 0 : c->group_mode == 2 ? 3 : 2;  // lane classes below this one get lanes
+        int first = 0;
+        for (int cls = 0; cls < 3; cls++) {
+            const int cnt = gn[cls];
+            if (cnt > 0) {
+                if (cls < lanes_to) {
+                    if (cls == 0) k_group_lanes<2><<<(cnt * 2 + 127) / 128, 128, 0, st>>>(P, dC, first, cnt);
+                    else if (cls == 1) k_group_lanes<4><<<(cnt * 4 + 127) / 128, 128, 0, st>>>(P, dC, first, cnt);
+                    else k_group_lanes<16><<<(cnt * 16 + 127) / 128, 128, 0, st>>>(P, dC, first, cnt);
+                } else {
+                    k_group<<<(cnt + 63) / 64, 64, 0, st>>>(P, dC, first, cnt);
+                }
+                S.launches++;
+            }
+            first += cnt;
+        }
         k_count<<<(P.A + 127) / 128, 128, 0, st>>>(P, dC);
         k_group_counts<<<(P.G + 127) / 128, 128, 0, st>>>(P);
-        S.launches += 3;
+        S.launches += 2;
     }
     k_scan_groups<<<1, 1024, 0, st>>>(P, S.totals.as<SpTotals>());
     S.launches++;
@@ -1026,9 +1052,25 @@ static int run_phase_b(sp_ctx *c, Slot &S) {
         }
     }
     if (P.G > 0) {
-        k_score<<<(P.G + 63) / 64, 64, 0, st>>>(P, dC, S.rows.as<SpRow>(), c->par.prim_margin_score,
-                                                (double) c->par.min_score, S.totals.as<SpTotals>());
-        S.launches++;
+        const int32_t *gn = S.plan.glist_n;
+        const double pm = c->par.prim_margin_score, ms = (double) c->par.min_score;
+        // K5: a lane per alignment for every group size (16 lanes for groups of more than four alignments: 13.1 -> 4.6 ms
+        // per 8192 stress groups on the 8 integer SMs); SECPHASE_B200_SCORE=serial: a thread per group
+        const int lanes_to = c->score_mode == 1 ? 0 : 3;
+        int first = 0;
+        for (int cls = 0; cls < 3; cls++) {
+            const int cnt = gn[cls];
+            if (cnt > 0) {
+                SpRow *rw = S.rows.as<SpRow>();
+                SpTotals *tt = S.totals.as<SpTotals>();
+                if (cls >= lanes_to) k_score<<<(cnt + 63) / 64, 64, 0, st>>>(P, dC, rw, pm, ms, tt, first, cnt);
+                else if (cls == 0) k_score_lanes<2><<<(cnt * 2 + 127) / 128, 128, 0, st>>>(P, dC, rw, pm, ms, tt, first, cnt);
+                else if (cls == 1) k_score_lanes<4><<<(cnt * 4 + 127) / 128, 128, 0, st>>>(P, dC, rw, pm, ms, tt, first, cnt);
+                else k_score_lanes<16><<<(cnt * 16 + 127) / 128, 128, 0, st>>>(P, dC, rw, pm, ms, tt, first, cnt);
+                S.launches++;
+            }
+            first += cnt;
+        }
     }
     CK(cudaEventRecord(S.ev[EV_SCORE], st));
     if (st != S.stream) {

@@ -20,6 +20,7 @@
 #include "sp_score.cuh"
 #include "sp_walk.cuh"
 #include "sp_walk_warp.cuh"
+#include "sp_group_warp.cuh"
 
 #define SP_SORT_LBINS 2048
 
@@ -38,7 +39,7 @@ struct SpTotals {  // device-side counters of one batch, read back once mid-pipe
 struct SpBatchPtrs {
     int32_t G, A;
     // uploaded
-    const int32_t *grp_aln_off, *flag, *tid, *pos, *l_qseq, *n_cigar, *tag_kind, *aln_grp, *gblk_cap;
+    const int32_t *grp_aln_off, *flag, *tid, *pos, *l_qseq, *n_cigar, *tag_kind, *aln_grp, *gblk_cap, *glist;
     const int64_t *cigar_off, *tag_off, *seq_off, *qual_off, *ops_off, *imk_off, *gpos_off, *gent_off, *gblk_off,
         *giv_off;
     const uint32_t *cigar_pool;
@@ -150,9 +151,11 @@ __global__ void __launch_bounds__(128) k_walk_list(SpBatchPtrs B, const SpConst 
 #define SP_PROF(k) ((void) 0)
 #endif
 
-__global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__restrict__ Cp) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= B.G) return;
+// thread per read group: groups glist[first .. first + count) (the whole batch: first 0, count G)
+__global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__restrict__ Cp, int first, int count) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= count) return;
+    const int g = B.glist[first + slot];
     SP_PROF_T0();
     const SpConst &C = *Cp;
     SpGroupAlnView V = sp_make_view(B, g);
@@ -195,6 +198,27 @@ __global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__re
     o.scored = scored ? 1 : 0;
     o.err = err;
     B.gout[g] = o;
+}
+
+// K2 + K3 with a lane per alignment (sp_group_warp.cuh): WID lanes per read group, the groups of one lane class
+// (glist[first .. first + count)).
+template <int WID>
+__global__ void __launch_bounds__(128) k_group_lanes(SpBatchPtrs B, const SpConst *__restrict__ Cp, int first, int count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((t & ~31) / WID >= count) return;  // (whole warps only)
+    const int slot = t / WID;
+    const bool has = slot < count;
+    const int g = has ? B.glist[first + slot] : 0;
+    SpGroupAlnView V = sp_make_view(B, g);
+    SpBlockWork W;
+    W.cap = B.gblk_cap[g];
+    W.ab = B.blk + B.gblk_off[g];
+    W.nb = B.nb + V.a0;
+    W.cons_a = B.iv + B.giv_off[g];
+    W.cons_b = W.cons_a + W.cap;
+    W.flank = W.cons_b + W.cap;
+    sp_group_lanes<WID>(*Cp, V, has, B.gpos + B.gpos_off[g], B.ent + B.gent_off[g], (int) (B.gpos_off[g + 1] - B.gpos_off[g]), W,
+                        &B.gout[g], &B.gP[g]);
 }
 
 // K3b count pass, thread per ALIGNMENT: the HMM windows calc_local_baq would run for this alignment (ptMarker.c:
@@ -620,9 +644,10 @@ __global__ void __launch_bounds__(1024) k_fs_sets(SpSetPlan pl, const SpItem *__
 }
 
 __global__ void __launch_bounds__(64) k_score(SpBatchPtrs B, const SpConst *__restrict__ Cp, const SpRow *rows,
-                                              double prim_margin, double min_score, SpTotals *tot) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= B.G) return;
+                                              double prim_margin, double min_score, SpTotals *tot, int first, int count) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= count) return;
+    const int g = B.glist[first + slot];
     const SpConst &C = *Cp;
     SpGroupAlnView V = sp_make_view(B, g);
     SpGroupOut o = B.gout[g];
@@ -642,6 +667,37 @@ __global__ void __launch_bounds__(64) k_score(SpBatchPtrs B, const SpConst *__re
 
 // ---- --writeBam: BAQ-modified quality arrays (full_baq mode) --------------------------------
 // thread per HMM row: fully parallel, one byte read + one byte written per base of every window
+// K5 with a lane per alignment (sp_score_lanes), the groups of one lane class
+template <int WID>
+__global__ void __launch_bounds__(128) k_score_lanes(SpBatchPtrs B, const SpConst *__restrict__ Cp, const SpRow *rows,
+                                                     double prim_margin, double min_score, SpTotals *tot, int first, int count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((t & ~31) / WID >= count) return;  // (whole warps only)
+    const int slot = t / WID, sub = threadIdx.x & (WID - 1), gbase = (threadIdx.x & 31) - sub;
+    const bool has = slot < count;
+    const int g = has ? B.glist[first + slot] : 0;
+    SpGroupAlnView V = sp_make_view(B, g);
+    SpGroupOut o = B.gout[g];
+    int32_t *wide = B.fin_wide + B.gent_off[g] * 6;
+    const int nf = sp_score_lanes<WID>(*Cp, V, has, B.gP[g], B.gpos + B.gpos_off[g], B.ent + B.gent_off[g], B.res + B.gent_off[g],
+                                       rows, o.scored != 0, B.score + V.a0, wide, B.baq ? B.baq + B.gent_off[g] : nullptr);
+    __syncwarp();
+    int off = 0;
+    if (has && sub == 0) {
+        o.n_final = nf;
+        sp_select(V, B.score + V.a0, prim_margin, min_score, &o);
+        off = atomicAdd(&tot->fin_rows, nf);
+        o.fin_off = off;
+        if (o.err) atomicOr(&tot->err, o.err);
+        B.gout[g] = o;
+    }
+    off = __shfl_sync(SP_FULL, off, gbase);
+    if (has) {
+        int32_t *dst = B.fin + (int64_t) off * 6;
+        for (int k = sub; k < nf * 6; k += WID) dst[k] = wide[k];
+    }
+}
+
 __global__ void __launch_bounds__(256) k_baq_rows(const SpConst *__restrict__ Cp, const SpItem *__restrict__ items,
                                                   const SpRow *__restrict__ rows, int n_rows,
                                                   const int64_t *__restrict__ qual_off,

@@ -33,7 +33,9 @@ struct SpPlan {
     std::vector<int64_t> gpos_off;  // [G+1] positions
     std::vector<int64_t> gent_off;  // [G+1] entries (n per position)
     std::vector<int64_t> gblk_off;  // [G+1] SpBlock workspace: n lists of gblk_cap[g]
-    std::vector<int64_t> giv_off;   // [G+1] SpIv workspace: 3 lists of gblk_cap[g]
+    std::vector<int64_t> giv_off;   // [G+1] SpIv workspace: 2 + n lists of gblk_cap[g] (two consensus lists, a flank list per alignment)
+    std::vector<int32_t> glist;     // [G] the groups ordered by lane class (sp_group_lane_class): k_group_lanes<2|4|16>
+    int32_t glist_n[3] = {0, 0, 0}; // groups per lane class
     std::vector<int32_t> gblk_cap;  // [G]
     std::vector<int64_t> g_msum, g_cbsum;  // [G] the bounds gblk_cap was derived from (sp_plan_block_caps)
     int64_t total_ops = 0, total_imk = 0, total_pos = 0, total_ent = 0, total_blk = 0, total_iv = 0;
@@ -105,7 +107,7 @@ inline int sp_plan_block_caps(SpPlan &pl, const int32_t *grp_aln_off, bool safe_
         pl.gblk_off[(size_t) g] = blk;
         blk += cap * n;
         pl.giv_off[(size_t) g] = iv;
-        iv += cap * 3;
+        iv += cap * (2 + n);
     }
     pl.gblk_off[(size_t) pl.G] = blk;
     pl.giv_off[(size_t) pl.G] = iv;
@@ -113,6 +115,9 @@ inline int sp_plan_block_caps(SpPlan &pl, const int32_t *grp_aln_off, bool safe_
     pl.total_iv = iv;
     return SP_OK;
 }
+
+// lanes a read group of n alignments gets in k_group_lanes: 2, 4 or 16 (classes 0, 1, 2)
+inline int sp_group_lane_class(int n) { return n <= 2 ? 0 : n <= 4 ? 1 : 2; }
 
 // returns SP_OK or a negative error.  n_threads > 1: the per-alignment text scan runs on that many threads.
 inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_caps, SpPlan &pl, int n_threads = 1,
@@ -136,6 +141,15 @@ inline int sp_make_plan(const sp_flat_batch *b, int indel_threshold, bool safe_c
         const int a0 = b->grp_aln_off[g], a1 = b->grp_aln_off[g + 1];
         const int n = a1 - a0;
         if (n < 1 || n > SP_MAX_ALN_PER_GROUP || a0 < 0 || a1 > A) return SP_EINVAL;
+    }
+    {
+        pl.glist.assign((size_t) G, 0);
+        int32_t start[3] = {0, 0, 0};
+        pl.glist_n[0] = pl.glist_n[1] = pl.glist_n[2] = 0;
+        for (int g = 0; g < G; g++) pl.glist_n[sp_group_lane_class(b->grp_aln_off[g + 1] - b->grp_aln_off[g])]++;
+        start[1] = pl.glist_n[0];
+        start[2] = pl.glist_n[0] + pl.glist_n[1];
+        for (int g = 0; g < G; g++) pl.glist[(size_t) start[sp_group_lane_class(b->grp_aln_off[g + 1] - b->grp_aln_off[g])]++] = g;
     }
     std::vector<SpAlnCounts> cnt((size_t) A);
     if (n_threads > 1 && A >= 4 * n_threads) {

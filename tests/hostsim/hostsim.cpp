@@ -26,6 +26,7 @@
 #define SP_WARP_EMU 1
 #include "warp_emu.h"
 #include "../../secphase_b200/csrc/sp_walk_warp.cuh"
+#include "../../secphase_b200/csrc/sp_group_warp.cuh"
 
 struct HsOut {
     std::vector<int32_t> group;   // [G][SP_GROUP_W]
@@ -106,7 +107,12 @@ static int hs_hmmf_dispatch(const SpConst &C, const SpHmmIn &in, int bwv, double
     }
 }
 
+static int g_group_lanes = 0;  // hs_set_group_lanes: K2 + K3 through sp_group_warp.cuh on the emulated warp
+
 extern "C" {
+
+void hs_set_group_lanes(int on) { g_group_lanes = on; }
+
 
 HsOut *hs_out_create() { return new HsOut(); }
 void hs_out_destroy(HsOut *o) { delete o; }
@@ -415,25 +421,7 @@ int hs_run3(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         return V;
     };
     out->mk_off[0].push_back(0);
-    // K2 + K3 (consensus + count pass): one "thread" per group
-    for (int g = 0; g < G; g++) {
-        SpGroupAlnView V = view(g);
-        SpGroupOut &o = gout[g];
-        memset(&o, 0, sizeof(o));
-        int err = 0;
-        for (int i = 0; i < V.n; i++) err |= info[V.a0 + i].err;
-        int32_t counts[4];
-        int P = sp_group_markers(V, gpos.data() + pl.gpos_off[g], ent.data() + pl.gent_off[g],
-                                 (int) (pl.gpos_off[g + 1] - pl.gpos_off[g]), counts, &err);
-        gP[g] = P;
-        o.n_init = counts[0]; o.n_after_allmm = counts[1]; o.n_filled = counts[2]; o.n_after_ins = counts[3];
-        for (int pi = 0; pi < P; pi++)
-            for (int i = 0; i < V.n; i++) {
-                const SpEntry &e = ent[pl.gent_off[g] + (int64_t) pi * V.n + i];
-                int32_t row[6] = {i, gpos[pl.gpos_off[g] + pi], e.base_idx, e.q, e.flags & 1, e.ref_pos};
-                out->mk[0].insert(out->mk[0].end(), row, row + 6);
-            }
-        out->mk_off[0].push_back((int64_t) out->mk[0].size() / 6);
+    auto work = [&](int g, const SpGroupAlnView &V) {
         SpBlockWork W;
         W.cap = pl.gblk_cap[g];
         W.ab = blk.data() + pl.gblk_off[g];
@@ -441,12 +429,70 @@ int hs_run3(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         W.cons_a = iv.data() + pl.giv_off[g];
         W.cons_b = W.cons_a + W.cap;
         W.flank = W.cons_b + W.cap;
+        return W;
+    };
+    // K2 + K3 with a lane per alignment (sp_group_warp.cuh on the emulated warp), as k_group_lanes<2|4|16> runs them
+    std::vector<SpGroupOut> lane_out((size_t) G);
+    if (g_group_lanes) {
+        int first = 0;
+        for (int cls = 0; cls < 3; cls++) {
+            const int wid = cls == 0 ? 2 : cls == 1 ? 4 : 16, count = pl.glist_n[cls], per_warp = 32 / wid;
+            for (int w0 = 0; w0 < count; w0 += per_warp) {
+                warp_emu::run_warp([&]() {
+                    const int slot = w0 + warp_emu::lane_id() / wid;
+                    const bool has = slot < count;
+                    const int g = has ? pl.glist[(size_t) (first + slot)] : 0;
+                    SpGroupAlnView V = view(g);
+                    SpBlockWork W = work(g, V);
+                    int32_t *gp = gpos.data() + pl.gpos_off[g];
+                    SpEntry *en = ent.data() + pl.gent_off[g];
+                    const int pc = (int) (pl.gpos_off[g + 1] - pl.gpos_off[g]);
+                    if (wid == 2) sp_group_lanes<2>(C, V, has, gp, en, pc, W, &lane_out[g], &gP[g]);
+                    else if (wid == 4) sp_group_lanes<4>(C, V, has, gp, en, pc, W, &lane_out[g], &gP[g]);
+                    else sp_group_lanes<16>(C, V, has, gp, en, pc, W, &lane_out[g], &gP[g]);
+                });
+            }
+            first += count;
+        }
+    }
+    // K2 + K3 (consensus + count pass): one "thread" per group
+    for (int g = 0; g < G; g++) {
+        SpGroupAlnView V = view(g);
+        SpGroupOut &o = gout[g];
+        memset(&o, 0, sizeof(o));
+        int err = 0;
+        int P;
+        if (g_group_lanes) {
+            o = lane_out[g];
+            P = gP[g];
+            err = o.err;
+        } else {
+            for (int i = 0; i < V.n; i++) err |= info[V.a0 + i].err;
+            int32_t counts[4];
+            P = sp_group_markers(V, gpos.data() + pl.gpos_off[g], ent.data() + pl.gent_off[g],
+                                 (int) (pl.gpos_off[g + 1] - pl.gpos_off[g]), counts, &err);
+            gP[g] = P;
+            o.n_init = counts[0]; o.n_after_allmm = counts[1]; o.n_filled = counts[2]; o.n_after_ins = counts[3];
+        }
+        for (int pi = 0; pi < P; pi++)
+            for (int i = 0; i < V.n; i++) {
+                const SpEntry &e = ent[pl.gent_off[g] + (int64_t) pi * V.n + i];
+                int32_t row[6] = {i, gpos[pl.gpos_off[g] + pi], e.base_idx, e.q, e.flags & 1, e.ref_pos};
+                out->mk[0].insert(out->mk[0].end(), row, row + 6);
+            }
+        out->mk_off[0].push_back((int64_t) out->mk[0].size() / 6);
+        SpBlockWork W = work(g, V);
         int margin = C.flank_margin, conf_len = 1;
         bool scored = false;
         SpEmitCounts cnt;
         memset(&cnt, 0, sizeof(cnt));
-        if (P > 0) {
+        if (g_group_lanes) {
+            margin = o.margin_eff;
+            conf_len = o.conf_len;
+        } else if (P > 0) {
             conf_len = sp_consensus_loop(C, V, P, gpos.data() + pl.gpos_off[g], W, &margin, &err);
+        }
+        if (P > 0) {
             if (conf_len > 0 || !C.consensus) {
                 scored = true;
                 if (C.baq_flag) {
@@ -464,6 +510,7 @@ int hs_run3(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
         gcnt[g] = cnt;
         o.margin_eff = margin;
         o.conf_len = conf_len;
+        if (g_group_lanes && (o.scored != (scored ? 1 : 0))) err |= 0x4000;  // (the lanes' own verdict must agree)
         o.scored = scored ? 1 : 0;
         o.err = err;
     }
@@ -594,13 +641,41 @@ int hs_run3(const sp_flat_batch *b, const sp_params *p, const uint8_t *ref_codes
     out->mk_off[1].push_back(0);
     out->mk_off[2].push_back(0);
     out->block_off.push_back(0);
+    std::vector<int> lane_nf((size_t) G, 0);
+    if (g_group_lanes) {  // K5 as k_score_lanes<2|4|16> runs it
+        int first = 0;
+        for (int cls = 0; cls < 3; cls++) {
+            const int wid = cls == 0 ? 2 : cls == 1 ? 4 : 16, count = pl.glist_n[cls], per_warp = 32 / wid;
+            for (int w0 = 0; w0 < count; w0 += per_warp) {
+                warp_emu::run_warp([&]() {
+                    const int slot = w0 + warp_emu::lane_id() / wid;
+                    const bool has = slot < count;
+                    const int g = has ? pl.glist[(size_t) (first + slot)] : 0;
+                    SpGroupAlnView V = view(g);
+                    const int32_t *gp = gpos.data() + pl.gpos_off[g];
+                    const SpEntry *en = ent.data() + pl.gent_off[g];
+                    const int32_t *rs = res.data() + pl.gent_off[g];
+                    double *sc = score.data() + V.a0;
+                    int32_t *fn = fin.data() + pl.gent_off[g] * 6, *bq = baq.data() + pl.gent_off[g];
+                    const bool scd = gout[g].scored != 0;
+                    int nf;
+                    if (wid == 2) nf = sp_score_lanes<2>(C, V, has, gP[g], gp, en, rs, rows.data(), scd, sc, fn, bq);
+                    else if (wid == 4) nf = sp_score_lanes<4>(C, V, has, gP[g], gp, en, rs, rows.data(), scd, sc, fn, bq);
+                    else nf = sp_score_lanes<16>(C, V, has, gP[g], gp, en, rs, rows.data(), scd, sc, fn, bq);
+                    if (has && warp_emu::lane_id() % wid == 0) lane_nf[(size_t) g] = nf;
+                });
+            }
+            first += count;
+        }
+    }
     for (int g = 0; g < G; g++) {
         SpGroupAlnView V = view(g);
         SpGroupOut &o = gout[g];
         const int P = gP[g];
-        int nf = sp_score_group(C, V, P, gpos.data() + pl.gpos_off[g], ent.data() + pl.gent_off[g],
-                                res.data() + pl.gent_off[g], rows.data(), o.scored != 0, score.data() + V.a0,
-                                fin.data() + pl.gent_off[g] * 6, baq.data() + pl.gent_off[g]);
+        int nf = g_group_lanes ? lane_nf[(size_t) g]
+                               : sp_score_group(C, V, P, gpos.data() + pl.gpos_off[g], ent.data() + pl.gent_off[g],
+                                                res.data() + pl.gent_off[g], rows.data(), o.scored != 0, score.data() + V.a0,
+                                                fin.data() + pl.gent_off[g] * 6, baq.data() + pl.gent_off[g]);
         o.n_final = nf;
         sp_select(V, score.data() + V.a0, p->prim_margin_score, (double) p->min_score, &o);
         int best = sp_finalize_best(rng, V.n, score.data() + V.a0, o.prim_idx, o.max_idx, o.tie_mask,

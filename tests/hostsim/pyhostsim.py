@@ -98,11 +98,13 @@ def params_from_oracle(op):
     return SpParams(**{k: getattr(op, k) for k, _ in SpParams._fields_})
 
 
-def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1, full_baq=False, hmm_mode=0):
+def run(batch, params, ref_codes, contig_off, safe_caps=False, seed=1, full_baq=False, hmm_mode=0, group_lanes=False):
     """hmm_mode: 0 strict kernels; 1 fast kernel + guard-band re-run (the product's default); 2 = 1 and every
-    fast instance cross-checked against the strict kernel (r["fast"] statistics, err bit 0x200 on a miss)."""
+    fast instance cross-checked against the strict kernel (r["fast"] statistics, err bit 0x200 on a miss).
+    group_lanes: stages K2 + K3 in their lane-per-alignment form (sp_group_warp.cuh) on the emulated warp."""
     L = lib()
     out = L.hs_out_create()
+    L.hs_set_group_lanes(1 if group_lanes else 0)
     try:
         cb = batch.as_c()
         ref_codes = np.ascontiguousarray(ref_codes, np.uint8)

@@ -80,7 +80,9 @@ inline void run_warp(const std::function<void()> &body) {
         }
         if (n_wait == 0) break;
         if (n_done != 0) {
-            fprintf(stderr, "warp_emu: %d lane(s) returned while %d wait at a full-mask intrinsic\n", n_done, n_wait);
+            fprintf(stderr, "warp_emu: %d lane(s) returned while %d wait at a full-mask intrinsic; rendezvous passed per lane:", n_done, n_wait);
+            for (int l = 0; l < 32; l++) fprintf(stderr, " %u%s", w->gen[l], w->done[l] ? "r" : "");
+            fprintf(stderr, "\n");
             abort();
         }
         // all 32 wait at (what must be) the same rendezvous
@@ -119,6 +121,11 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, int d) {
     const int me = warp_emu::lane_id();
     const uint64_t *x = warp_emu::exchange(warp_emu::to_bits(v));
     return warp_emu::from_bits<T>(x[me + d < 32 ? me + d : me]);
+}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) {
+    const int me = warp_emu::lane_id();
+    const uint64_t *x = warp_emu::exchange(warp_emu::to_bits(v));
+    return warp_emu::from_bits<T>(x[(me ^ m) & 31]);
 }
 inline unsigned __ballot_sync(unsigned, bool p) {
     const uint64_t *x = warp_emu::exchange(p ? 1 : 0);

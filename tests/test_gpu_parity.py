@@ -349,6 +349,8 @@ def test_warp_walker_and_serial_walker(sp, oracle, monkeypatch):
              ("stress", "hifi", 12, dict(locus_len=300000))]
     for mode in ("warp", "serial"):
         monkeypatch.setenv("SECPHASE_B200_WALK", mode)   # ("warp": also for alignments the default leaves to the serial walker)
+        # K2/K3 likewise: a lane per alignment (default, k_group_lanes) and a thread per read group (k_group)
+        monkeypatch.setenv("SECPHASE_B200_GROUP", "lanes" if mode == "warp" else "serial")
         for k, (spreset, ppreset, ng, over) in enumerate(cases):
             s, b, codes, off = make_case(spreset, ng, **over)
             exp = oracle.run(b, oracle.preset_params(ppreset), oracle_refseq(oracle, s))

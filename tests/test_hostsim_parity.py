@@ -264,3 +264,20 @@ def test_warp_walker_declines_or_agrees_on_damaged_input(hostsim, oracle):
             handled += r["handled"]
             total += r["alignments"]
     assert 0 < handled < total
+
+
+@pytest.mark.parametrize("name,spreset,ppreset,ng,over", CASES, ids=[c[0] for c in CASES])
+def test_lane_per_alignment_group_stages_bit_exact_vs_oracle(hostsim, oracle, name, spreset, ppreset, ng, over):
+    """K2 + K3 in the form k_group_lanes<2|4|16> runs them (sp_group_warp.cuh: a lane per alignment, the group's
+    lanes voting and handing lists to each other), on the emulated warp: every table of the job equals the
+    reference's, as with the thread-per-group form."""
+    s, b, codes, off = make_case(spreset, ng, **over)
+    op = oracle.preset_params(ppreset)
+    exp = oracle.run(b, op, oracle_refseq(oracle, s))
+    got = hostsim.run(b, hostsim.params_from_oracle(op), codes, off, group_lanes=True)
+    assert got["err"] == 0
+    bad = compare_results(exp, got, label="hostsim-lanes")
+    assert not bad, "\n".join(bad)
+    # and with the provable (larger) block workspaces of the capacity retry
+    got2 = hostsim.run(b, hostsim.params_from_oracle(op), codes, off, group_lanes=True, safe_caps=True)
+    assert got2["err"] == 0 and not compare_results(exp, got2, label="hostsim-lanes-safe")

@@ -59,7 +59,7 @@ prof)  # clock64 split of k_group / k_emit (lib/variants/lib_prof.so = -DSP_PROF
   cat $out/${tag}_prof.err | tail -24; cut -c1-330 $out/${tag}_prof.json ;;
 ontsms)  # bench line of one config (PRESET, default ont) vs the SM split (integer stages | HMM)
   for n in ${SMS_LIST:-16 24 32 40}; do
-    ( SECPHASE_B200_INT_SMS=$n timeout 300 python bench.py --preset ${PRESET:-ont} --no-cpu-baseline --no-per-config --steps 6 ) >> $out/${tag}_ontsms.json 2>> $out/${tag}_ontsms.err
+    ( SECPHASE_B200_INT_SMS=$n timeout 300 python bench.py --preset ${PRESET:-ont} --no-cpu-baseline --no-per-config --steps ${STEPS:-6} ) >> $out/${tag}_ontsms.json 2>> $out/${tag}_ontsms.err
   done
   python - <<EOF
 import json
@@ -113,9 +113,10 @@ ncu_hmm)  # launch list of one stage-bench run, then a full capture of the bulk 
     python tools/stage_bench.py --preset hifi --groups 8192 --locus-len 150000000 --iters 1 > $out/${tag}_ncu_full.log 2>&1
   ls -la $out/${tag}_k_hmm.ncu-rep ;;
 ncu_int)
-  for p in ont stress; do
-    timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_walk|k_group|k_emit' -s 3 -c 3 -f -o $out/${tag}_int_$p \
-      python tools/stage_bench.py --preset $p --groups 2048 --iters 1 > $out/${tag}_ncu_int_$p.log 2>&1
+  # (4 matching launches per batch: k_walk_warp, k_walk_list, k_group_lanes<W> | k_group, k_emit; the third batch is captured)
+  for p in ${NCU_PRESETS:-ont stress}; do
+    timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_walk|k_group_lanes|k_group$|k_emit' -s 8 -c 4 -f -o $out/${tag}_int_$p \
+      python tools/stage_bench.py --preset $p --groups ${NCU_GROUPS:-2048} --iters 1 > $out/${tag}_ncu_int_$p.log 2>&1
   done ;;
 *) echo "unknown step $step" ;;
 esac
