@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) k_walk(SpBatchPtrs B, const SpConst *__re
 // 32 bytes of text and a hundred-odd tokens in all (HiFi) the serial walker executes fewer warp instructions per
 // alignment (32 alignments a warp) than a warp that scans every byte; with thousands of tokens (ONT) it is the
 // other way round by a factor of three to four.
-__global__ void __launch_bounds__(128) k_walk_warp(SpBatchPtrs B, const SpConst *__restrict__ Cp, int min_ops) {
+__global__ void __launch_bounds__(128, 8) k_walk_warp(SpBatchPtrs B, const SpConst *__restrict__ Cp, int min_ops) {
     const int a = (int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (a >= B.A) return;
     if ((int) (B.ops_off[a + 1] - B.ops_off[a] - 1) < min_ops) {
