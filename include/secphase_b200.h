@@ -172,7 +172,14 @@ int sp_elapsed_since_mark(sp_ctx *ctx, int slot, float *ms);
 /* How the context split the GPU: the latency-bound integer stages of a batch run on *int_sms SMs of
  * their own (a CUDA green context) while the FP64 HMM kernels of the batches ahead of it keep the
  * other *hmm_sms.  Returns 1 when partitioned, 0 when not (both counts are then the whole GPU);
- * SECPHASE_B200_INT_SMS=<n> in the environment of sp_create changes the request (0 = off). */
+ * SECPHASE_B200_INT_SMS=<n> in the environment of sp_create changes the request (0 = off).
+ * Other switches read by sp_create, for tests and measurements (results are the same in every setting):
+ *   SECPHASE_B200_WALK=serial|warp|<n>   CIGAR/cs walk: a thread per alignment for all / a warp per alignment for
+ *                                        all / a warp for op tables planned at >= n entries (default 600)
+ *   SECPHASE_B200_GROUP=serial|lanes     marker merge + consensus blocks: a thread per read group for all / a lane
+ *                                        per alignment for all (default: lanes for groups of <= 4 alignments)
+ *   SECPHASE_B200_SCORE=serial|lanes     scoring pass likewise (default: lanes)
+ *   SECPHASE_B200_NO_PRIORITY=1          emit/sort/score kernels on the slot's ordinary stream */
 int sp_sm_partition(sp_ctx *ctx, int32_t *int_sms, int32_t *hmm_sms);
 
 /* --- device-resident variant used to time the kernels alone (bench `value`): the batch is
