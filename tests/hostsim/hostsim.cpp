@@ -288,6 +288,34 @@ int hs_walk_stats(const sp_flat_batch *b, const sp_params *p, int32_t *out /* [A
     return 0;
 }
 
+// Self-test of the warp emulator against what the intrinsics are defined to return: 0 = all good, else the number of
+// the first check that failed.
+int hs_warp_emu_selftest(void) {
+    int bad = 0;
+    auto fail = [&](int k) { if (!bad) bad = k; };
+    warp_emu::run_warp([&]() {
+        const int lane = warp_emu::lane_id();
+        if (__shfl_sync(SP_FULL, lane * 3, 7) != 21) fail(1);
+        if (__shfl_up_sync(SP_FULL, lane, 2) != (lane >= 2 ? lane - 2 : lane)) fail(2);
+        if (__shfl_down_sync(SP_FULL, lane, 5) != (lane + 5 < 32 ? lane + 5 : lane)) fail(3);
+        if (__shfl_xor_sync(SP_FULL, lane, 9) != (lane ^ 9)) fail(4);
+        if (__ballot_sync(SP_FULL, (lane % 3) == 0) != 0x49249249u) fail(5);
+        if (!__any_sync(SP_FULL, lane == 31) || __any_sync(SP_FULL, lane == 32)) fail(6);
+        if (__all_sync(SP_FULL, lane < 31) || !__all_sync(SP_FULL, lane < 32)) fail(7);
+        if (__reduce_min_sync(SP_FULL, 100 - lane) != 69 || __reduce_max_sync(SP_FULL, lane * lane) != 961) fail(8);
+        if (__reduce_add_sync(SP_FULL, lane) != 496 || __reduce_or_sync(SP_FULL, 1u << (lane & 7)) != 0xffu) fail(9);
+        if (sp_warp_incl_scan(lane + 1, lane) != (lane + 1) * (lane + 2) / 2) fail(10);
+        if (sp_seg_min<4>(31 - lane) != 31 - (lane | 3) || sp_seg_sum<8>(1) != 8 || sp_seg_or<2>(1 << (lane & 1)) != 3) fail(11);
+        // lanes may run different amounts of private work between two rendezvous
+        int acc = 0;
+        for (int k = 0; k < lane * 10; k++) acc += k;
+        if (__shfl_sync(SP_FULL, acc, 3) != 435) fail(12);
+        __syncwarp();
+        if (__fns(0xf0f0u, 0, 3) != 6 || __popc(0xf0f0u) != 8 || __clz(1) != 31 || __ffs(8) != 4) fail(13);
+    });
+    return bad;
+}
+
 // The warp-cooperative walker (sp_walk_warp.cuh, run on warp_emu.h's 32 coroutine lanes) against the serial walker
 // for every alignment of a batch.  out[0] alignments, out[1] handled by the warp walker (the others fell back),
 // out[2] alignments whose tables differ, out[3] the first of them (-1 none), out[4] what differed there

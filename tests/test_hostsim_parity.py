@@ -281,3 +281,9 @@ def test_lane_per_alignment_group_stages_bit_exact_vs_oracle(hostsim, oracle, na
     # and with the provable (larger) block workspaces of the capacity retry
     got2 = hostsim.run(b, hostsim.params_from_oracle(op), codes, off, group_lanes=True, safe_caps=True)
     assert got2["err"] == 0 and not compare_results(exp, got2, label="hostsim-lanes-safe")
+
+
+def test_warp_emulator_selftest(hostsim):
+    """tests/hostsim/warp_emu.h returns what the CUDA warp intrinsics are defined to return (shuffles, votes,
+    reductions, the repo's scans on top of them), with lanes doing unequal private work between rendezvous."""
+    assert hostsim.lib().hs_warp_emu_selftest() == 0
