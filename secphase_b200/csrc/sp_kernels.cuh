@@ -116,6 +116,9 @@ __global__ void __launch_bounds__(128) k_walk(SpBatchPtrs B, const SpConst *__re
 // alignment (32 alignments a warp) than a warp that scans every byte; with thousands of tokens (ONT) it is the
 // other way round by a factor of three to four.
 __global__ void __launch_bounds__(128, 8) k_walk_warp(SpBatchPtrs B, const SpConst *__restrict__ Cp, int min_ops) {
+    __shared__ uint8_t s_code[256];  // class of every byte value (sp_cs_code)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = (uint8_t) sp_cs_code((uint32_t) i);
+    __syncthreads();
     const int a = (int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (a >= B.A) return;
     if ((int) (B.ops_off[a + 1] - B.ops_off[a] - 1) < min_ops) {
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(128, 8) k_walk_warp(SpBatchPtrs B, const SpCon
                                            B.cigar_pool + B.cigar_off[a], B.tag_pool, B.tag_off[a], B.tag_off[a + 1],
                                            B.tag_kind[a], B.qual_pool + B.qual_off[a], B.ops + B.ops_off[a],
                                            (int) (B.ops_off[a + 1] - B.ops_off[a] - 1), B.imk + B.imk_off[a],
-                                           (int) (B.imk_off[a + 1] - B.imk_off[a]), cb, cap, &B.info[a]);
+                                           (int) (B.imk_off[a + 1] - B.imk_off[a]), cb, cap, &B.info[a], s_code);
     if ((threadIdx.x & 31) == 0) {
         if (ok) B.nb[a] = B.info[a].n_cb;
         else B.walk_fb[1 + atomicAdd(B.walk_fb, 1)] = a;

@@ -7,10 +7,11 @@
 //   ptMarker_get_initial_markers       (ptMarker.c:42-75)
 //   find_confident_blocks              (ptMarker.c:328-395).
 // The serial walker spends ~10^3 instructions per cs token with a quarter of its lanes active (32 different
-// alignments per warp, every lane in a different token); here the 32 lanes of a warp look at 32 consecutive
+// alignments per warp, every lane in a different token); here the 32 lanes of a warp look at 128 consecutive
 // bytes of ONE alignment's cs text:
-//   1. tokens are found by ballots (a token starts at ':', '+', '-' or at a '*' that does not continue a run of
-//      "*xy" groups), ':' numbers are evaluated by a short segmented scan, each token end writes its op;
+//   1. every lane classifies four bytes; tokens are found from the codes (a token starts at ':', '+', '-' or at a
+//      '*' that does not continue a run of "*xy" groups), ':' numbers are evaluated by a short scan of (x10, +digit)
+//      pairs across lanes and serially within a lane, each token end writes its op;
 //   2. the ops, 32 at a time: coordinates are prefix sums; the tokens are checked against the CIGAR -- between its
 //      end clips the CIGAR must be exactly the run structure of the tokens (an M op = a maximal run of ':'/'*'
 //      tokens of the same total length, an I/D op = a '+'/'-' token of the same length; with =/X CIGARs every
@@ -54,11 +55,25 @@ SP_WD int sp_op_step_mask(int op) {
            : op == SP_CSOFT ? 5 : op == SP_CHARD ? 4 : 0;
 }
 
-// true: tables written; false: run the serial walker instead.
+// classes of cs text bytes
+enum { K_OTHER = 0, K_DIGIT = 1, K_LOWER = 2, K_COLON = 3, K_STAR = 4, K_PLUS = 5, K_MINUS = 6 };
+SP_WD uint32_t sp_cs_code(uint32_t c) {  // (selects, not branches)
+    uint32_t k = (c - '0') < 10u ? K_DIGIT : K_OTHER;
+    k = (c - 'a') < 26u ? K_LOWER : k;
+    k = c == ':' ? K_COLON : k;
+    k = c == '*' ? K_STAR : k;
+    k = c == '+' ? K_PLUS : k;
+    k = c == '-' ? K_MINUS : k;
+    return k;
+}
+
+// true: tables written; false: run the serial walker instead.  lut: sp_cs_code of every byte value (shared memory
+// in the kernel), or null.
 SP_WDN bool sp_walk_alignment_warp(int indel_threshold, int min_q, int flag, int pos, int l_qseq, int n_cigar,
                                        const uint32_t *__restrict__ cigar, const uint8_t *__restrict__ tag, int64_t tag_beg,
                                        int64_t tag_end, int tag_kind, const uint8_t *__restrict__ qual, SpOp *ops, int ops_cap,
-                                       SpInitMarker *imk, int imk_cap, SpBlock *cb, int cb_cap, SpAlnInfo *info) {
+                                       SpInitMarker *imk, int imk_cap, SpBlock *cb, int cb_cap, SpAlnInfo *info,
+                                       const uint8_t *lut = nullptr) {
     const int lane = SP_LANE();
     const bool rev = (flag & SP_FREVERSE) != 0;
     if (tag_kind != 0 || n_cigar < 1 || tag_end <= tag_beg) return false;
@@ -115,102 +130,155 @@ SP_WDN bool sp_walk_alignment_warp(int indel_threshold, int min_q, int flag, int
         eqx = has_eqx;
     }
     // ---------------------------------------------------------------- 1. tokens
-    // Bytes are classified once (codes below); a lane sees its own code, the three before it and the one after.
-    // Carried across chunks (warp-uniform): codes of the last three bytes, the token the chunk begins in, the value
-    // of the number it begins in.
-    enum { K_OTHER = 0, K_DIGIT = 1, K_LOWER = 2, K_COLON = 3, K_STAR = 4, K_PLUS = 5, K_MINUS = 6 };
-    auto code_of = [](uint32_t c) -> uint32_t {  // (selects, not branches)
-        uint32_t k = (c - '0') < 10u ? K_DIGIT : K_OTHER;
-        k = (c - 'a') < 26u ? K_LOWER : k;
-        k = c == ':' ? K_COLON : k;
-        k = c == '*' ? K_STAR : k;
-        k = c == '+' ? K_PLUS : k;
-        k = c == '-' ? K_MINUS : k;
-        return k;
+    // A lane owns FOUR consecutive text bytes (one aligned word), an iteration of the warp covers 128: the bytes are
+    // classified once (a 256-entry table in shared memory), a lane sees the codes of its own four bytes, of the three
+    // before and of the one after in one 32-bit window, walks its four bytes serially (token tracking, number
+    // value) and meets the other lanes only for what crosses lane borders -- the token and the number a lane begins
+    // in, the rank of its token ends -- so the shuffles, ballots and carries of an iteration are shared by 128 bytes.
+    // Carried across iterations (warp-uniform): the codes of the last lane, the token and the value of the number
+    // the next iteration begins in.
+    const int n_text = (int) (tag_end - tag_beg);
+    const int64_t word0 = tag_beg & ~(int64_t) 3;           // first aligned word that holds text
+    const int p_first = (int) (word0 - tag_beg);           // text offset of its first byte (-3 .. 0)
+    const int n_iter = (n_text + 1 - p_first + 127) >> 7;  // (one virtual terminator byte)
+    auto classify = [&](uint32_t w, int p0) -> uint32_t {  // 4-bit codes of the four bytes of word w at text offset p0
+        uint32_t pk = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t c = (w >> (8 * j)) & 255u;
+            const uint32_t k = lut ? lut[c] : sp_cs_code(c);
+            pk |= ((p0 + j >= 0 && p0 + j < n_text) ? k : (uint32_t) K_OTHER) << (4 * j);
+        }
+        return pk;
     };
-    uint32_t pw = 0;                         // codes of the three bytes before the chunk, 4 bits each, nearest lowest
-    int cur_kind = 0;                        // code of the start character of the token the chunk begins in
-    int cur_start = 0;                       // (text offsets are relative to tag_beg)
-    uint32_t num_in = 0;                     // value of the number the chunk begins in
+    auto load_word = [&](int p0) -> uint32_t {  // (words that hold no text are not read)
+        return (p0 + 3 >= 0 && p0 < n_text) ? *reinterpret_cast<const uint32_t *>(tag + tag_beg + p0) : 0u;
+    };
+    uint32_t carry_pk = 0;  // codes of the last lane of the iteration before
+    int cur_kind = 0;       // code of the start character of the token the iteration begins in
+    int cur_start = 0;      // its text offset
+    uint32_t num_in = 0;    // value of the number the iteration begins in
     int n_tok = 0;
     bool invalid = false;
-    const uint8_t *text = tag + tag_beg;
-    const int n_text = (int) (tag_end - tag_beg);
-    const int n_chunks = (n_text + 1 + 31) >> 5;       // one virtual terminator byte
-    uint32_t c_nx = lane < n_text ? text[lane] : 0;    // the chunk ahead is loaded and classified one iteration early
-    uint32_t k_nx = code_of(c_nx);
-    for (int ch = 0; ch < n_chunks; ch++) {
-        const int cbase = ch << 5;
-        const int p = cbase + lane;
-        const bool in_range = p < n_text;
-        const uint32_t c0 = c_nx, k0 = k_nx;
-        c_nx = p + 32 < n_text ? text[p + 32] : 0;
-        k_nx = code_of(c_nx);
-        // codes at p, p-1, p-2, p-3 in 4-bit fields
-        uint32_t kw = k0 | (__shfl_up_sync(SP_FULL, k0, 1) << 4);
-        if (lane == 0) kw = k0 | ((pw & 15u) << 4);
-        uint32_t kw4 = kw | (__shfl_up_sync(SP_FULL, kw, 2) << 8);
-        if (lane == 0) kw4 = kw | ((pw >> 4) << 8);
-        if (lane == 1) kw4 = kw | ((pw & 255u) << 8);
-        const uint32_t k1 = (kw4 >> 4) & 15u, k2 = (kw4 >> 8) & 15u, k3 = (kw4 >> 12) & 15u;
-        uint32_t kx = __shfl_down_sync(SP_FULL, k0, 1);
-        const uint32_t kx31 = __shfl_sync(SP_FULL, k_nx, 0);
-        if (lane == 31) kx = kx31;
-        const bool isd = k0 == K_DIGIT, isl = k0 == K_LOWER;
-        const bool start = k0 == K_COLON || k0 >= K_PLUS || (k0 == K_STAR && !(k3 == K_STAR && k2 == K_LOWER && k1 == K_LOWER));
-        const bool start_nx = kx == K_COLON || kx >= K_PLUS || (kx == K_STAR && !(k2 == K_STAR && k1 == K_LOWER && k0 == K_LOWER));
-        const bool end = in_range && (p + 1 == n_text || start_nx);
-        // the cs grammar  (:[0-9]+ | \*[a-z][a-z] | [+-][a-z]+)*  checked looking backwards (the byte at tag_end is a
-        // virtual terminator)
-        if (p <= n_text) {
-            bool bad = false;
-            if (in_range) {
-                if (k0 == K_OTHER) bad = true;
-                if (p == 0 && k0 < K_COLON) bad = true;
-                if (isd && !(k1 == K_COLON || k1 == K_DIGIT)) bad = true;
-                if (isl && !(k1 >= K_STAR || k1 == K_LOWER)) bad = true;
-                if (isl && k1 == K_LOWER && k2 == K_LOWER && k3 == K_STAR) bad = true;  // third letter of a '*' group
-            }
-            if (!isd && k1 == K_COLON) bad = true;                   // ':' without a number
-            if (!isl && k1 >= K_STAR) bad = true;                    // sign or '*' without a letter
-            if (!isl && k1 == K_LOWER && k2 == K_STAR) bad = true;   // '*' group with a single letter
-            if (bad) invalid = true;
-        }
-        // which token does my byte belong to
-        const uint32_t le = lane == 31 ? 0xffffffffu : ((2u << lane) - 1);
-        const uint32_t sm = __ballot_sync(SP_FULL, start);
-        const uint32_t below = sm & le;
-        const int src = below ? 31 - __clz(below) : 0;
-        const uint32_t ck = __shfl_sync(SP_FULL, k0, src);
-        const int tk_kind = below ? (int) ck : cur_kind;
-        const int tk_start = below ? cbase + src : cur_start;
-        // numbers: value = num_in * m + a after a scan of (m, a) over 8 bytes (longer numbers: not a read's)
-        uint32_t m = isd ? 10u : 0u, a = isd ? c0 - '0' : 0u;
+    uint32_t w_nx = load_word(p_first + 4 * lane);  // the words ahead are loaded and classified one iteration early
+    uint32_t pk_nx = classify(w_nx, p_first + 4 * lane);
+    const uint32_t lt = (1u << lane) - 1;
+    for (int it = 0; it < n_iter; it++) {
+        const int p0 = p_first + (it << 7) + 4 * lane;  // text offset of my first byte
+        const uint32_t w = w_nx, pk = pk_nx;
+        w_nx = load_word(p0 + 128);
+        pk_nx = classify(w_nx, p0 + 128);
+        uint32_t prev = __shfl_up_sync(SP_FULL, pk, 1), next = __shfl_down_sync(SP_FULL, pk, 1);
+        const uint32_t next31 = __shfl_sync(SP_FULL, pk_nx, 0);
+        if (lane == 0) prev = carry_pk;
+        if (lane == 31) next = next31;
+        // window of codes: nibbles 0..2 = the three bytes before mine, 3..6 = mine, 7 = the byte after
+        const uint32_t win = ((prev >> 4) & 0xfffu) | (pk << 12) | ((next & 15u) << 28);
+        auto nib = [&](int i) -> uint32_t { return (win >> (4 * i)) & 15u; };
+        auto starts = [&](int i) -> bool {  // does the byte at window index i (3..7) start a token
+            const uint32_t k0 = nib(i);
+            return k0 == K_COLON || k0 >= K_PLUS ||
+                   (k0 == K_STAR && !(nib(i - 3) == K_STAR && nib(i - 2) == K_LOWER && nib(i - 1) == K_LOWER));
+        };
+        bool st[5];
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            const uint32_t pm = __shfl_up_sync(SP_FULL, m, o), pa = __shfl_up_sync(SP_FULL, a, o);
-            if (lane >= o) { a = pa * m + a; m = pm * m; }
+        for (int j = 0; j < 5; j++) st[j] = starts(3 + j);
+        bool en[4];
+        int n_end = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p = p0 + j;
+            en[j] = p >= 0 && p < n_text && (p + 1 == n_text || st[j + 1]);
+            n_end += en[j];
+            // the cs grammar  (:[0-9]+ | \*[a-z][a-z] | [+-][a-z]+)*  checked looking backwards (the byte at n_text is
+            // a virtual terminator)
+            if (p >= 0 && p <= n_text) {
+                const uint32_t k0 = nib(3 + j), k1 = nib(2 + j), k2 = nib(1 + j), k3 = nib(j);
+                const bool isd = k0 == K_DIGIT, isl = k0 == K_LOWER;
+                bool bad = false;
+                if (p < n_text) {
+                    if (k0 == K_OTHER) bad = true;
+                    if (p == 0 && k0 < K_COLON) bad = true;
+                    if (isd && !(k1 == K_COLON || k1 == K_DIGIT)) bad = true;
+                    if (isl && !(k1 >= K_STAR || k1 == K_LOWER)) bad = true;
+                    if (isl && k1 == K_LOWER && k2 == K_LOWER && k3 == K_STAR) bad = true;  // third letter of a '*' group
+                }
+                if (!isd && k1 == K_COLON) bad = true;                   // ':' without a number
+                if (!isl && k1 >= K_STAR) bad = true;                    // sign or '*' without a letter
+                if (!isl && k1 == K_LOWER && k2 == K_STAR) bad = true;   // '*' group with a single letter
+                if (bad) invalid = true;
+            }
         }
-        const uint32_t num = num_in * m + a;
-        const uint32_t em = __ballot_sync(SP_FULL, end);
-        if (end) {
-            int tlen, op;
-            if (tk_kind == K_COLON) { tlen = (int) num; op = SP_CEQUAL; if (p - tk_start > 8) invalid = true; }
-            else if (tk_kind == K_STAR) { tlen = (p - tk_start + 1) / 3; op = SP_CDIFF; }
-            else { tlen = p - tk_start; op = tk_kind == K_PLUS ? SP_CINS : SP_CDEL; }
-            if (tlen <= 0) invalid = true;  // ":0" ends the serial walk
-            const int idx = n_lead + n_tok + __popc(em & (le >> 1));
-            if (idx < ops_cap) ops[idx].oplen = (uint32_t) op | ((uint32_t) tlen << 4);  // coordinates follow in step 2
+        // the token my first byte lies in: the last start in the lanes below, else the iteration's carry
+        int my_last = -1;  // my own last start
+#pragma unroll
+        for (int j = 0; j < 4; j++) my_last = st[j] ? j : my_last;
+        const uint32_t hs = __ballot_sync(SP_FULL, my_last >= 0);
+        const uint32_t my_tok = my_last >= 0 ? (nib(3 + my_last) | ((uint32_t) my_last << 4)) : 0u;
+        const uint32_t below = hs & lt;
+        const int src = below ? 31 - __clz(below) : 0;
+        const uint32_t from = __shfl_sync(SP_FULL, my_tok, src);
+        int tk_kind = below ? (int) (from & 15u) : cur_kind;
+        int tk_start = below ? p_first + (it << 7) + 4 * src + (int) (from >> 4) : cur_start;
+        // the number my first byte lies in: my four bytes as (m, a) with value' = value * m + a, composed over the
+        // four lanes below (16 bytes; numbers longer than 8 digits are not a read's and are declined)
+        uint32_t m = 1, a = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool isd = nib(3 + j) == K_DIGIT;
+            const uint32_t d = ((w >> (8 * j)) & 255u) - '0';
+            a = isd ? a * 10u + d : 0u;
+            m = isd ? m * 10u : 0u;
         }
+        uint32_t im = m, ia = a;  // inclusive over lanes l-3 .. l
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            const uint32_t pm = __shfl_up_sync(SP_FULL, im, o), pa = __shfl_up_sync(SP_FULL, ia, o);
+            if (lane >= o) { ia = pa * im + ia; im = pm * im; }
+        }
+        uint32_t em_ = __shfl_up_sync(SP_FULL, im, 1), ea = __shfl_up_sync(SP_FULL, ia, 1);
+        if (lane == 0) { em_ = 1; ea = 0; }
+        uint32_t v = num_in * em_ + ea;  // value of the number at my first byte
+        // where my token ends go
+        const uint32_t e1 = __ballot_sync(SP_FULL, n_end >= 1), e2 = __ballot_sync(SP_FULL, n_end >= 2);
+        const int idx = n_lead + n_tok + __popc(e1 & lt) + __popc(e2 & lt);
+        // my four bytes in turn: which token, which number value; a lane sees at most two token ends (a token has at
+        // least two bytes -- text where it has fewer fails the grammar above and is declined), kept for the writes below
+        int e_p[2] = {0, 0}, e_kind[2] = {0, 0}, e_start[2] = {0, 0}, n_e = 0;
+        uint32_t e_v[2] = {0, 0};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t k0 = nib(3 + j);
+            if (st[j]) { tk_kind = (int) k0; tk_start = p0 + j; }
+            v = k0 == K_DIGIT ? v * 10u + (((w >> (8 * j)) & 255u) - '0') : 0u;
+            if (en[j]) {
+                const int c = n_e < 1 ? 0 : 1;
+                e_p[c] = p0 + j; e_kind[c] = tk_kind; e_start[c] = tk_start; e_v[c] = v;
+                n_e++;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (c < n_e) {
+                int tlen, op;
+                if (e_kind[c] == K_COLON) { tlen = (int) e_v[c]; op = SP_CEQUAL; if (e_p[c] - e_start[c] > 8) invalid = true; }
+                else if (e_kind[c] == K_STAR) { tlen = (e_p[c] - e_start[c] + 1) / 3; op = SP_CDIFF; }
+                else { tlen = e_p[c] - e_start[c]; op = e_kind[c] == K_PLUS ? SP_CINS : SP_CDEL; }
+                if (tlen <= 0) invalid = true;  // ":0" ends the serial walk
+                if (idx + c < ops_cap) ops[idx + c].oplen = (uint32_t) op | ((uint32_t) tlen << 4);  // coordinates follow in step 2
+            }
+        }
+        if (n_e > 2) invalid = true;
         // carries
-        n_tok += __popc(em);
-        if (sm) {
-            const int ls = 31 - __clz(sm);
-            cur_kind = (int) __shfl_sync(SP_FULL, k0, ls);
-            cur_start = cbase + ls;
+        n_tok += __popc(e1) + __popc(e2);
+        if (hs) {
+            const int ls = 31 - __clz(hs);
+            const uint32_t lastt = __shfl_sync(SP_FULL, my_tok, ls);
+            cur_kind = (int) (lastt & 15u);
+            cur_start = p_first + (it << 7) + 4 * ls + (int) (lastt >> 4);
         }
-        num_in = __shfl_sync(SP_FULL, num, 31);
-        pw = __shfl_sync(SP_FULL, kw4, 31) & 0xfffu;
+        num_in = __shfl_sync(SP_FULL, v, 31);
+        carry_pk = __shfl_sync(SP_FULL, pk, 31);
     }
     if (__any_sync(SP_FULL, invalid)) return false;
     if (eqx && n_tok != n_core) return false;
@@ -260,7 +328,6 @@ SP_WDN bool sp_walk_alignment_warp(int indel_threshold, int min_q, int flag, int
             ops[k] = o;
             if ((op == SP_CEQUAL || op == SP_CDIFF) && k < first_match) first_match = k;
         }
-        const uint32_t lt = (1u << lane) - 1;
         // ---- check against the CIGAR
         const bool is_tok = on && k >= n_lead && k < n_lead + n_tok;
         if (eqx) {

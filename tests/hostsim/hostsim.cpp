@@ -345,11 +345,13 @@ int hs_walk_warp_check(const sp_flat_batch *b, const sp_params *p, int64_t *out)
                           b->cigar_pool + b->cigar_off[a], tag_pool, b->tag_off[a], b->tag_off[a + 1], tk,
                           b->qual_pool + b->qual_off[a], ops.data(), ocap, imk.data(), mcap, cb.data(), ccap, &info);
         bool handled = false;
+        static uint8_t code_table[256];  // (as k_walk_warp's shared-memory table)
+        for (int c = 0; c < 256; c++) code_table[c] = (uint8_t) sp_cs_code((uint32_t) c);
         warp_emu::run_warp([&]() {
             const bool ok = sp_walk_alignment_warp(C.indel_threshold, C.min_q, b->flag[a], b->pos[a], b->l_qseq[a], b->n_cigar[a],
                                                    b->cigar_pool + b->cigar_off[a], tag_pool, b->tag_off[a], b->tag_off[a + 1], tk,
                                                    b->qual_pool + b->qual_off[a], ops2.data(), ocap, imk2.data(), mcap,
-                                                   cb2.data(), ccap, &info2);
+                                                   cb2.data(), ccap, &info2, (a & 1) ? code_table : nullptr);
             if (warp_emu::lane_id() == 0) handled = ok;
         });
         if (!handled) continue;
