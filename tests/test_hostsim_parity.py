@@ -287,3 +287,67 @@ def test_warp_emulator_selftest(hostsim):
     """tests/hostsim/warp_emu.h returns what the CUDA warp intrinsics are defined to return (shuffles, votes,
     reductions, the repo's scans on top of them), with lanes doing unequal private work between rendezvous."""
     assert hostsim.lib().hs_warp_emu_selftest() == 0
+
+
+def _handmade_batch(alns):
+    """One read group per alignment from (flag, pos, CIGAR string, cs string, l_qseq)."""
+    import re
+    from tools.flatbatch import FlatBatch
+    ops = "MIDNSHP=X"
+    cig, cig_off, tag, tag_off, seq_off, qual_off = [], [0], bytearray(), [0], [0], [0]
+    for flag, pos, cigar, cs, lq in alns:
+        for n, o in re.findall(r"(\d+)([MIDNSHP=X])", cigar):
+            cig.append((int(n) << 4) | ops.index(o))
+        cig_off.append(len(cig))
+        tag += cs.encode()
+        tag_off.append(len(tag))
+        seq_off.append(seq_off[-1] + (lq + 1) // 2)
+        qual_off.append(qual_off[-1] + lq)
+    n = len(alns)
+    rng = np.random.default_rng(3)
+    return FlatBatch(
+        grp_aln_off=np.arange(n + 1), qname_off=np.arange(n + 1) * 2, qname_pool=np.frombuffer(b"r\0" * n, np.uint8),
+        flag=[a[0] for a in alns], tid=np.zeros(n), pos=[a[1] for a in alns], l_qseq=[a[4] for a in alns],
+        n_cigar=np.diff(cig_off), tag_kind=np.zeros(n), cigar_off=cig_off, tag_off=tag_off, seq_off=seq_off,
+        qual_off=qual_off, cigar_pool=cig, tag_pool=np.frombuffer(bytes(tag), np.uint8),
+        seq_pool=np.zeros(seq_off[-1], np.uint8), qual_pool=rng.integers(0, 60, qual_off[-1]).astype(np.uint8))
+
+
+def test_warp_walker_handmade_alignments(hostsim, oracle):
+    """Hand-written CIGAR/cs pairs: every shape of the cs grammar at every byte alignment of the text (the warp walker
+    reads aligned words), tokens that span lanes and 128-byte iterations, both strands -- handled and identical to the
+    serial walker; text outside the grammar or disagreeing with the CIGAR -- declined (or, where the serial walker
+    gives the same answer anyway, identical)."""
+    ins300 = "acgt" * 75
+    good = [
+        ("5M", ":5", 5), ("3S5M2S", ":5", 10), ("2H3S4M1I3M2D2M4S1H", ":4+a:3-cg:2", 17),
+        ("10M", ":3*ag:2*ct*ga:2", 10), ("3=1X2=2X2=", ":3*ag:2*ct*ga:2", 10), ("1M", "*ag", 1), ("12M", ":12", 12),
+        ("5M300I5M", ":5+" + ins300 + ":5", 310), ("5=300I5=", ":5+" + ins300 + ":5", 310),
+        ("60M", ":5" + "*ag" * 50 + ":5", 60), ("5=50X5=", ":5" + "*ag" * 50 + ":5", 60),
+        ("1234567M", ":1234567", 1234567), ("4M1D4M", ":4-a:4", 8), ("1X1I1X", "*ag+c*tc", 3),
+        ("2M1I1M1D3M", "*ag:1+t*ca-g:2*gt", 7), ("100M", ":9" * 10 + ":10", 100),
+        ("7H40M7H", ":13*ag:13*ct:12", 40),
+    ]
+    # text padding so that consecutive tags start at all four byte alignments
+    alns = []
+    for k, (cigar, cs, lq) in enumerate(good * 4):
+        alns.append((16 if (k % 2) else 0, 1000 + k, cigar, cs, lq))
+        if k % len(good) == len(good) - 1:
+            alns.append((0, 5, "1M", ":1", 1))  # (2 bytes: shifts the alignment of everything after it)
+            alns.append((0, 5, "1M", "*ag", 1) if (k // len(good)) % 2 else (0, 5, "1M", ":1", 1))
+    b = _handmade_batch(alns)
+    assert len(set(int(x) % 4 for x in b.tag_off[:-1])) == 4
+    P = hostsim.params_from_oracle(oracle.preset_params("hifi"))
+    r = hostsim.walk_warp_check(b, P)
+    assert r["different"] == 0 and r["handled"] == r["alignments"] == len(alns), r
+    bad = [
+        ("5M", ":5:", 5), ("5M", ":5*a", 5), ("5M", ":4*agc", 5), ("5M", ":5+", 5), ("5M", "5", 5), ("5M", ":2 :3", 5),
+        ("5M", ":0:5", 5), ("5M", "::5", 5), ("5M", ":5-", 5), ("5M", ":2*a*g:2", 5), ("5M", ":2+:3", 5),
+        ("123456789M", ":123456789", 10), ("5M", ":4", 5), ("5M", ":6", 5), ("4M1I", ":5", 5), ("2M1I2M", ":2-a:2", 5),
+        ("2M1I2M", ":2+ac:2", 6), ("3=2X", ":5", 5), ("3M2=", ":5", 5), ("2M3S2M", ":2:2", 7), ("5M", "Z5", 5),
+        ("3M0I2M", ":5", 5), ("5M", ":5\t", 5),
+    ]
+    b2 = _handmade_batch([(16 if (k % 2) else 0, 77, cigar, cs, lq) for k, (cigar, cs, lq) in enumerate(bad * 4)])
+    r2 = hostsim.walk_warp_check(b2, P)
+    assert r2["different"] == 0, r2
+    assert r2["handled"] == 0, r2   # every one of them goes to the serial walker
