@@ -18,7 +18,7 @@ import subprocess
 
 import numpy as np
 
-from tools.flatbatch import CFlatBatch
+from secphase_b200.flatbatch import CFlatBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_LIB = os.path.join(_HERE, "_ref", "libsecphase_ref.so")
@@ -162,7 +162,7 @@ def select(grp_aln_off, flag, scores, params, seed=1):
 
 
 def run(batch, params, refseq, kind=None, keep_hmm=False, seed=1, outputs=None):
-    """Run every read group of `batch` (tools.flatbatch.FlatBatch; or a list of them, processed in
+    """Run every read group of `batch` (secphase_b200.flatbatch.FlatBatch; or a list of them, processed in
     order with one rand() stream) through the CPU checker.  outputs=(dir, prefix) additionally
     writes out.log and the two marker BED files the way secphase.c does (reference kind only)."""
     if kind is None:

@@ -181,7 +181,7 @@ def params_for(preset=None, **overrides):
 
 
 def _c_batch(batch):
-    """tools.flatbatch.FlatBatch (or anything with the same numpy attributes) -> _CFlatBatch."""
+    """secphase_b200.flatbatch.FlatBatch (or anything with the same numpy attributes) -> _CFlatBatch."""
     s = _CFlatBatch()
     s.n_groups = batch.n_groups
     s.n_alns = batch.n_alns

@@ -5,7 +5,7 @@ import subprocess
 
 import numpy as np
 
-from tools.flatbatch import CFlatBatch
+from secphase_b200.flatbatch import CFlatBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from tools.flatbatch import _FIELDS, FlatBatch
+from secphase_b200.flatbatch import _FIELDS, FlatBatch
 from tools.parity import ASCII2CODE, compare_results
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))

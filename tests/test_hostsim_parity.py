@@ -292,7 +292,7 @@ def test_warp_emulator_selftest(hostsim):
 def _handmade_batch(alns):
     """One read group per alignment from (flag, pos, CIGAR string, cs string, l_qseq)."""
     import re
-    from tools.flatbatch import FlatBatch
+    from secphase_b200.flatbatch import FlatBatch
     ops = "MIDNSHP=X"
     cig, cig_off, tag, tag_off, seq_off, qual_off = [], [0], bytearray(), [0], [0], [0]
     for flag, pos, cigar, cs, lq in alns:

@@ -14,7 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from tools.flatbatch import _FIELDS  # noqa: E402
+from secphase_b200.flatbatch import _FIELDS  # noqa: E402
 
 CASES = [
     # name, synth preset, params preset, groups, synth overrides

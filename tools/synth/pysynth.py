@@ -5,7 +5,7 @@ import subprocess
 
 import numpy as np
 
-from tools.flatbatch import CFlatBatch, FlatBatch
+from secphase_b200.flatbatch import CFlatBatch, FlatBatch
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 _LIB_PATH = os.path.join(_ROOT, "secphase_b200", "lib", "libsp_synth.so")
