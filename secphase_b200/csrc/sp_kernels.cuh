@@ -185,8 +185,6 @@ __global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__re
     W.flank = W.cons_b + W.cap;
     int margin = C.flank_margin, conf_len = 1;
     bool scored = false;
-    SpEmitCounts cnt;
-    memset(&cnt, 0, sizeof(cnt));
     if (P > 0) {
         conf_len = sp_consensus_loop(C, V, P, gpos, W, &margin, &err);
         SP_PROF(1);
@@ -195,7 +193,6 @@ __global__ void __launch_bounds__(64) k_group(SpBatchPtrs B, const SpConst *__re
         for (int i = 0; i < V.n; i++) W.nb[i] = 0;  // secphase.c:161: no markers, no confident blocks
     }
     SP_PROF(2);
-    (void) cnt;
     o.margin_eff = margin;
     o.conf_len = conf_len;
     o.scored = scored ? 1 : 0;
