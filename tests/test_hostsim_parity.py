@@ -351,3 +351,19 @@ def test_warp_walker_handmade_alignments(hostsim, oracle):
     r2 = hostsim.walk_warp_check(b2, P)
     assert r2["different"] == 0, r2
     assert r2["handled"] == 0, r2   # every one of them goes to the serial walker
+
+
+@pytest.mark.parametrize("seed", [7919, 15838, 23757])
+def test_warp_cooperative_stages_other_seeds(hostsim, oracle, seed):
+    """The warp walker and the lane-per-alignment group/score stages on read groups from other seeds than the fixed
+    cases (HiFi, ONT, many secondaries): tables equal to the reference's, every cs alignment handled by the warp walker."""
+    for spreset, ppreset, ng, over in (("hifi", "hifi", 24, dict(locus_len=300000)), ("ont", "ont", 8, dict(locus_len=400000)),
+                                       ("stress", "hifi", 8, dict(locus_len=300000))):
+        s, b, codes, off = make_case(spreset, ng, seed=20240603 + seed, **over)
+        op = oracle.preset_params(ppreset)
+        P = hostsim.params_from_oracle(op)
+        exp = oracle.run(b, op, oracle_refseq(oracle, s))
+        got = hostsim.run(b, P, codes, off, group_lanes=True, hmm_mode=1)
+        assert got["err"] == 0 and not compare_results(exp, got, label=f"lanes-{spreset}-{seed}")
+        r = hostsim.walk_warp_check(b, P)
+        assert r["different"] == 0 and r["handled"] == r["alignments"], r
